@@ -1,0 +1,279 @@
+"""ctypes binding of ``include/hicpeaks_b200.h`` (the C-ABI drop-in boundary).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a only) as
+``hicpeaks_b200/libhicpeaks_b200.so``.  There is no Python / CPU implementation behind this module:
+if the library is missing, or no B200 is visible, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HP_MAX_PW = 8
+HP_MAX_WW = 20
+HP_MAX_STEPS = 160
+
+HP_OK = 0
+HP_ERR_INVALID = -1
+HP_ERR_CUDA = -2
+HP_ERR_NO_DEVICE = -3
+HP_ERR_STATE = -4
+HP_ERR_EMPTY_REFIDX = -5
+HP_ERR_CHUNK_OVERFLOW = -6
+HP_ERR_CAPACITY = -7
+
+SF_VALID_K, SF_VALID_Y, SF_REJECT_K, SF_REJECT_Y, SF_CEMY_NONZERO = 1, 2, 4, 8, 16
+
+LIB_NAME = "libhicpeaks_b200.so"
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+
+# every symbol include/hicpeaks_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "hp_abi_version", "hp_device_count", "hp_ctx_create", "hp_ctx_destroy", "hp_last_error",
+    "hp_band_upload", "hp_hiccups_score", "hp_hiccups_fdr", "hp_hiccups", "hp_get_survivors",
+    "hp_get_gaps", "hp_dump_levels", "hp_dump_plane", "hp_get_chunk_table", "hp_poisson_sf",
+]
+
+
+class BandDesc(C.Structure):
+    _fields_ = [("n", C.c_int64), ("num", C.c_int32), ("bal_first", C.c_int32),
+                ("raw_diags", C.POINTER(C.c_void_p)), ("bal_diags", C.POINTER(C.c_void_p)),
+                ("ir", C.c_void_p), ("b1", C.c_void_p), ("b2", C.c_void_p)]
+
+
+class HiccupsParams(C.Structure):
+    _fields_ = [("npw", C.c_int32), ("pw", C.c_int32 * HP_MAX_PW), ("ww", C.c_int32 * HP_MAX_PW),
+                ("maxww", C.c_int32), ("min_local_reads", C.c_int32), ("maxapart_bins", C.c_int64),
+                ("sig", C.c_double), ("dump", C.c_int32), ("reserved", C.c_int32)]
+
+
+class StepStat(C.Structure):
+    _fields_ = [("p", C.c_int32), ("w", C.c_int32), ("resolved", C.c_int64),
+                ("valid_ratio", C.c_double), ("left_ratio", C.c_double)]
+
+
+class LfStat(C.Structure):
+    _fields_ = [("n_valid", C.c_int64), ("e_max", C.c_double), ("numbin", C.c_int32),
+                ("reserved", C.c_int32), ("n_reject", C.c_int64)]
+
+
+class HiccupsSummary(C.Structure):
+    _fields_ = [("n_pixels", C.c_int64), ("band_pixels", C.c_int64), ("frozen_w", C.c_int32),
+                ("n_steps", C.c_int32), ("steps", StepStat * HP_MAX_STEPS),
+                ("lf", (LfStat * 2) * HP_MAX_PW), ("n_candidates", C.c_int64), ("n_survivors", C.c_int64),
+                ("ms_levels", C.c_float), ("ms_score", C.c_float), ("ms_fdr", C.c_float), ("ms_total", C.c_float),
+                ("launches", C.c_int32), ("reserved", C.c_int32)]
+
+
+SURVIVOR_DTYPE = np.dtype([("r", "<i4"), ("c", "<i4"), ("pair", "<i4"), ("flags", "<u4"), ("obs", "<f8"),
+                           ("ice", "<f8"), ("e", "<f8", (2,)), ("p", "<f8", (2,)), ("q", "<f8", (2,))])
+assert SURVIVOR_DTYPE.itemsize == 80
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("hicpeaks_b200 [%d]: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """Load the C-ABI library (no GPU needed to load; compute calls need a B200)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise EngineError(HP_ERR_NO_DEVICE, "%s not built -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)" % p)
+    lib = C.CDLL(p)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    lib.hp_abi_version.restype = C.c_int
+    lib.hp_device_count.argtypes = [C.POINTER(C.c_int)]
+    lib.hp_ctx_create.argtypes = [C.c_int, C.c_int, vp, C.POINTER(vp)]
+    lib.hp_ctx_destroy.argtypes = [vp]
+    lib.hp_ctx_destroy.restype = None
+    lib.hp_last_error.argtypes = [vp]
+    lib.hp_last_error.restype = C.c_char_p
+    lib.hp_band_upload.argtypes = [vp, C.POINTER(BandDesc)]
+    lib.hp_hiccups_score.argtypes = [vp, C.POINTER(HiccupsParams), C.POINTER(HiccupsSummary)]
+    lib.hp_hiccups_fdr.argtypes = [vp, vp, C.POINTER(HiccupsSummary)]
+    lib.hp_hiccups.argtypes = [vp, C.POINTER(HiccupsParams), C.POINTER(HiccupsSummary)]
+    lib.hp_get_survivors.argtypes = [vp, vp, i64, C.POINTER(i64)]
+    lib.hp_get_gaps.argtypes = [vp, vp, i64]
+    lib.hp_dump_levels.argtypes = [vp, vp, i64]
+    lib.hp_dump_plane.argtypes = [vp, i32, i32, i32, vp, i64]
+    lib.hp_get_chunk_table.argtypes = [vp, i32, i32, C.POINTER(i32), vp, vp, vp, vp, i64]
+    lib.hp_poisson_sf.argtypes = [vp, vp, vp, vp, i64]
+    for name in SYMBOLS:
+        fn = getattr(lib, name)
+        if name not in ("hp_ctx_destroy", "hp_last_error"):
+            fn.restype = C.c_int
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def chunk_edges(max_chunks: int) -> np.ndarray:
+    """Upper lambda-chunk edges rv_i, i = 1..max_chunks, evaluated exactly as the reference does
+    (/root/reference/hicpeaks/callers.py:33-37)."""
+    out = np.empty(max_chunks, dtype=np.float64)
+    for i in range(1, max_chunks + 1):
+        out[i - 1] = 1 if i == 1 else np.power(2, ((i - 1) / 3.))
+    return out
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One engine context = one GPU + one stream (see include/hicpeaks_b200.h)."""
+
+    def __init__(self, device: int = 0, max_chunks: int = 52):
+        self.lib = load_library()
+        self.max_chunks = max_chunks
+        self._h = C.c_void_p()
+        edges = chunk_edges(max_chunks)
+        rc = self.lib.hp_ctx_create(device, max_chunks, _ptr(edges), C.byref(self._h))
+        if rc != HP_OK:
+            raise EngineError(rc, (self.lib.hp_last_error(None) or b"").decode())
+        self.n = self.num = 0
+        self.params = None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.hp_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != HP_OK:
+            raise EngineError(rc, (self.lib.hp_last_error(self._h) or b"").decode())
+
+    # -- input ---------------------------------------------------------------------------------
+    def upload(self, n, num, bal_first, Diags, cDiags, ir, b1, b2):
+        """Diags: ``num`` int32 arrays (length n-d); cDiags: ``num - bal_first`` float64 arrays;
+        ir: float64[num - bal_first]; b1, b2: float64[n].  Arrays must already be C-contiguous of the
+        right dtype (the caller normalises); they are only read during this call."""
+        keep = []
+        rp = (C.c_void_p * num)()
+        for d in range(num):
+            a = Diags[d]
+            if a.dtype != np.int32 or not a.flags.c_contiguous or a.size != n - d:
+                raise ValueError("Diags[%d] must be contiguous int32 of length %d" % (d, n - d))
+            rp[d] = a.ctypes.data
+        nb = num - bal_first
+        bp = (C.c_void_p * nb)()
+        for i in range(nb):
+            a = cDiags[i]
+            if a.dtype != np.float64 or not a.flags.c_contiguous or a.size != n - bal_first - i:
+                raise ValueError("cDiags[%d] must be contiguous float64 of length %d" % (i, n - bal_first - i))
+            bp[i] = a.ctypes.data
+        ir = np.ascontiguousarray(ir, dtype=np.float64)
+        b1 = np.ascontiguousarray(b1, dtype=np.float64)
+        b2 = np.ascontiguousarray(b2, dtype=np.float64)
+        if ir.size != nb or b1.size != n or b2.size != n:
+            raise ValueError("ir / bias length mismatch")
+        keep += [ir, b1, b2]
+        desc = BandDesc(n, num, bal_first, C.cast(rp, C.POINTER(C.c_void_p)), C.cast(bp, C.POINTER(C.c_void_p)),
+                        ir.ctypes.data, b1.ctypes.data, b2.ctypes.data)
+        self._check(self.lib.hp_band_upload(self._h, C.byref(desc)))
+        self.n, self.num = int(n), int(num)
+
+    # -- scoring -------------------------------------------------------------------------------
+    @staticmethod
+    def make_params(pw, ww, maxww, sig, maxapart_bins, min_local_reads, dump=False):
+        if len(pw) != len(ww) or not 1 <= len(pw) <= HP_MAX_PW:
+            raise ValueError("need 1..%d (pw, ww) pairs" % HP_MAX_PW)
+        P = HiccupsParams()
+        P.npw = len(pw)
+        for i, (p, w) in enumerate(zip(pw, ww)):
+            P.pw[i], P.ww[i] = int(p), int(w)
+        P.maxww, P.min_local_reads = int(maxww), int(min_local_reads)
+        P.maxapart_bins, P.sig, P.dump = int(maxapart_bins), float(sig), int(bool(dump))
+        return P
+
+    def score(self, P):
+        S = HiccupsSummary()
+        self.params = P
+        self._check(self.lib.hp_hiccups_score(self._h, C.byref(P), C.byref(S)))
+        return S
+
+    def fdr(self, numbin_override=None):
+        S = HiccupsSummary()
+        ov = None
+        if numbin_override is not None:
+            ov = np.ascontiguousarray(numbin_override, dtype=np.int32)
+        self._check(self.lib.hp_hiccups_fdr(self._h, None if ov is None else _ptr(ov), C.byref(S)))
+        return S
+
+    def hiccups(self, P):
+        S = HiccupsSummary()
+        self.params = P
+        self._check(self.lib.hp_hiccups(self._h, C.byref(P), C.byref(S)))
+        return S
+
+    def survivors(self):
+        cnt = C.c_int64()
+        self._check(self.lib.hp_get_survivors(self._h, None, 0, C.byref(cnt)))
+        out = np.zeros(cnt.value, dtype=SURVIVOR_DTYPE)
+        if cnt.value:
+            self._check(self.lib.hp_get_survivors(self._h, _ptr(out), cnt.value, C.byref(cnt)))
+        return out
+
+    def gaps(self):
+        out = np.zeros(self.n, dtype=np.uint8)
+        self._check(self.lib.hp_get_gaps(self._h, _ptr(out), self.n))
+        return out.astype(bool)
+
+    # -- inspection ----------------------------------------------------------------------------
+    def dump_levels(self):
+        out = np.empty((self.num, self.n), dtype=np.uint8)
+        self._check(self.lib.hp_dump_levels(self._h, _ptr(out), out.size))
+        return out
+
+    def dump_plane(self, pair, background, what):
+        out = np.empty((self.num, self.n), dtype=np.float64)
+        self._check(self.lib.hp_dump_plane(self._h, pair, background, what, _ptr(out), out.size))
+        return out
+
+    def chunk_table(self, pair, background):
+        nb = C.c_int32()
+        widths = np.zeros(64, dtype=np.int32)
+        self._check(self.lib.hp_get_chunk_table(self._h, pair, background, C.byref(nb), _ptr(widths), None, None, None, 0))
+        widths = widths[:nb.value]
+        tot = int(widths.sum())
+        hist = np.zeros(tot, dtype=np.int64)
+        p = np.zeros(tot, dtype=np.float64)
+        q = np.zeros(tot, dtype=np.float64)
+        if tot:
+            self._check(self.lib.hp_get_chunk_table(self._h, pair, background, C.byref(nb), _ptr(widths), _ptr(hist),
+                                                    _ptr(p), _ptr(q), tot))
+        off = np.concatenate([[0], np.cumsum(widths)]).astype(np.int64)
+        return nb.value, widths, off, hist, p, q
+
+    def poisson_sf(self, k, mu):
+        k = np.ascontiguousarray(k, dtype=np.float64)
+        mu = np.ascontiguousarray(np.broadcast_to(mu, k.shape), dtype=np.float64)
+        out = np.empty_like(k)
+        self._check(self.lib.hp_poisson_sf(self._h, _ptr(k), _ptr(mu), _ptr(out), k.size))
+        return out
+
+
+def device_count() -> int:
+    lib = load_library()
+    n = C.c_int()
+    lib.hp_device_count(C.byref(n))
+    return n.value

@@ -1,0 +1,689 @@
+// Host side of the C ABI declared in include/hicpeaks_b200.h: context, band upload, the sweep
+// program builder (callers.py:15-23,132-198), the frozen_w replay (callers.py:203-232) and the
+// launch sequence  K1 levels -> replay -> bE table -> K2 score -> K3 BH -> survivor filter.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "hp_kernels.cuh"
+
+using namespace hp;
+
+static thread_local std::string g_err;
+
+struct hp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    std::string err;
+    // chunk tables
+    Chunks chunks{};
+    std::vector<double> h_ptab;
+    double* d_ptab = nullptr;
+    // band
+    int64_t n = 0;
+    int num = 0, bal_first = 0, pitch = 0;
+    size_t plane = 0;                 // num * pitch
+    size_t cap_plane = 0, cap_n = 0;
+    int* d_raw = nullptr;
+    double* d_bal = nullptr;
+    unsigned char* d_lvl = nullptr;
+    double *d_ir = nullptr, *d_b1 = nullptr, *d_b2 = nullptr;
+    unsigned int* d_rownz = nullptr;
+    void* h_stage = nullptr;          // pinned staging for uploads
+    size_t cap_stage = 0;
+    bool have_band = false;
+    // run state
+    hp_hiccups_params prm{};
+    Prog prog{};
+    std::vector<signed char> opa, opb;
+    std::vector<unsigned char> opy, opr;
+    bool scored = false, fdr_done = false;
+    hp_hiccups_summary sum{};
+    int dlo = 0, dhi = -1;
+    unsigned long long* d_lhist = nullptr;      // [HP_MAX_STEPS + 2]
+    double* d_betab = nullptr; size_t cap_betab = 0;
+    unsigned int* d_hist = nullptr; size_t cap_hist = 0;
+    double* d_qtab = nullptr; size_t cap_qtab = 0;
+    unsigned long long* d_small = nullptr;      // [0..15] emax bits, [16..31] nvalid, [32..47] nreject
+    unsigned int* d_cnt = nullptr;              // [0..3] cand counters, [4..7] survivor counters
+    int* d_numbin = nullptr;                    // [16]
+    Cand* d_cand = nullptr; size_t cap_cand = 0;
+    hp_survivor* d_surv = nullptr; size_t cap_surv = 0;
+    double* d_dump = nullptr; size_t cap_dump = 0;
+    int numbin[HP_MAX_PW * 2] = {};
+    unsigned int ncand = 0, nsurv = 0;
+    PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+};
+
+static int fail(hp_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(ctx, HP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+
+template <typename T>
+static cudaError_t ensure(T** p, size_t* cap, size_t want) {
+    if (*cap >= want && *p) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc((void**)p, want * sizeof(T));
+    if (e == cudaSuccess) *cap = want;
+    return e;
+}
+
+extern "C" int hp_abi_version(void) { return HP_ABI_VERSION; }
+
+extern "C" int hp_device_count(int* count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return fail(nullptr, HP_ERR_NO_DEVICE, cudaGetErrorString(e)); }
+    *count = n;
+    return HP_OK;
+}
+
+extern "C" const char* hp_last_error(const hp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+static int build_chunks(hp_ctx* ctx, int max_chunks, const double* edges) {
+    Chunks& C = ctx->chunks;
+    memset(&C, 0, sizeof(C));
+    C.maxchunk = max_chunks;
+    C.rv[0] = 0.0;
+    int off = 0;
+    for (int i = 1; i <= max_chunks; ++i) {
+        C.rv[i] = edges ? edges[i - 1] : (i == 1 ? 1.0 : pow(2.0, (i - 1) / 3.0));
+        if (!(C.rv[i] > C.rv[i - 1])) return fail(ctx, HP_ERR_INVALID, "chunk edges must increase");
+        C.hoff[i] = off;
+        C.hw[i] = (int)ceil(C.rv[i] + 12.0 * sqrt(C.rv[i]) + 40.0);
+        off += C.hw[i];
+    }
+    C.hoff[max_chunks + 1] = off;
+    C.total_bins = off;
+    return HP_OK;
+}
+
+extern "C" int hp_ctx_create(int device, int max_chunks, const double* edges, hp_ctx** out) {
+    if (!out) return fail(nullptr, HP_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (max_chunks == 0) max_chunks = 52;
+    if (max_chunks < 1 || max_chunks > kMaxChunk) return fail(nullptr, HP_ERR_INVALID, "max_chunks out of range [1,64]");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, HP_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(nullptr, HP_ERR_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+        return fail(nullptr, HP_ERR_NO_DEVICE, "device is not sm_100 (kernels are built for sm_100a only)");
+    hp_ctx* ctx = new hp_ctx();
+    ctx->device = device;
+    auto bail = [&](int code) { hp_ctx_destroy(ctx); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(fail(nullptr, HP_ERR_CUDA, "cudaSetDevice failed"));
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(nullptr, HP_ERR_CUDA, "stream create failed"));
+    for (auto& e : ctx->ev) cudaEventCreate(&e);
+    cudaDriverEntryPointQueryResult qres;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+        return bail(fail(nullptr, HP_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver"));
+    ctx->encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    int rc = build_chunks(ctx, max_chunks, edges);
+    if (rc) { g_err = ctx->err; return bail(rc); }
+    const size_t tb = ctx->chunks.total_bins;
+    bool ok = cudaMalloc(&ctx->d_ptab, tb * sizeof(double)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_lhist, (HP_MAX_STEPS + 2) * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_small, 48 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_cnt, 8 * sizeof(unsigned int)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_numbin, 16 * sizeof(int)) == cudaSuccess;
+    if (!ok) return bail(fail(nullptr, HP_ERR_CUDA, "device allocation failed"));
+    // Poisson table (universal): p[i][k] = 1 - pdtr(k, rv_i)
+    for (int i = 1; i <= max_chunks; ++i) ctx->chunks.kcand[i] = 0;
+    if (cudaMemcpyToSymbolAsync(c_chunks, &ctx->chunks, sizeof(Chunks), 0, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+        return bail(fail(nullptr, HP_ERR_CUDA, "constant upload failed"));
+    k_ptab<<<(unsigned)((tb + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_ptab);
+    ctx->h_ptab.resize(tb);
+    cudaMemcpyAsync(ctx->h_ptab.data(), ctx->d_ptab, tb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return bail(fail(nullptr, HP_ERR_CUDA, std::string("Poisson table kernel: ") + cudaGetErrorString(e)));
+    for (int i = 1; i <= max_chunks; ++i)
+        if (ctx->h_ptab[ctx->chunks.hoff[i] + ctx->chunks.hw[i] - 1] != 0.0)
+            return bail(fail(nullptr, HP_ERR_INVALID, "internal: Poisson table too narrow for chunk " + std::to_string(i)));
+    *out = ctx;
+    return HP_OK;
+}
+
+extern "C" void hp_ctx_destroy(hp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    void* ptrs[] = {ctx->d_ptab, ctx->d_raw, ctx->d_bal, ctx->d_lvl, ctx->d_ir, ctx->d_b1, ctx->d_b2, ctx->d_rownz,
+                    ctx->d_lhist, ctx->d_betab, ctx->d_hist, ctx->d_qtab, ctx->d_small, ctx->d_cnt, ctx->d_numbin,
+                    ctx->d_cand, ctx->d_surv, ctx->d_dump};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
+    if (!ctx || !b) return fail(ctx, HP_ERR_INVALID, "NULL argument");
+    if (b->n <= 0 || b->n > (1ll << 30) || b->num <= 0 || b->num > b->n || b->bal_first < 0 || b->bal_first >= b->num)
+        return fail(ctx, HP_ERR_INVALID, "bad band geometry (need 0 < num <= n, 0 <= bal_first < num)");
+    if (!b->raw_diags || !b->bal_diags || !b->ir || !b->b1 || !b->b2) return fail(ctx, HP_ERR_INVALID, "NULL band array");
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_band = false; ctx->scored = false; ctx->fdr_done = false;
+    const int64_t n = b->n;
+    const int num = b->num;
+    const int pitch = (int)((n + 31) / 32 * 32);
+    const size_t plane = (size_t)num * pitch;
+    if (plane > ctx->cap_plane) {
+        for (void* p : {(void*)ctx->d_raw, (void*)ctx->d_bal, (void*)ctx->d_lvl}) if (p) cudaFree(p);
+        ctx->d_raw = nullptr; ctx->d_bal = nullptr; ctx->d_lvl = nullptr; ctx->cap_plane = 0;
+        CK(cudaMalloc(&ctx->d_raw, plane * sizeof(int)));
+        CK(cudaMalloc(&ctx->d_bal, plane * sizeof(double)));
+        CK(cudaMalloc(&ctx->d_lvl, plane));
+        ctx->cap_plane = plane;
+    }
+    if ((size_t)n > ctx->cap_n) {
+        for (void* p : {(void*)ctx->d_ir, (void*)ctx->d_b1, (void*)ctx->d_b2, (void*)ctx->d_rownz}) if (p) cudaFree(p);
+        ctx->d_ir = ctx->d_b1 = ctx->d_b2 = nullptr; ctx->d_rownz = nullptr; ctx->cap_n = 0;
+        CK(cudaMalloc(&ctx->d_ir, n * sizeof(double)));
+        CK(cudaMalloc(&ctx->d_b1, n * sizeof(double)));
+        CK(cudaMalloc(&ctx->d_b2, n * sizeof(double)));
+        CK(cudaMalloc(&ctx->d_rownz, n * sizeof(unsigned int)));
+        ctx->cap_n = n;
+    }
+    const size_t stage_bytes = plane * 12 + (size_t)num * 8;
+    if (stage_bytes > ctx->cap_stage) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr; ctx->cap_stage = 0;
+        CK(cudaHostAlloc(&ctx->h_stage, stage_bytes, cudaHostAllocDefault));
+        ctx->cap_stage = stage_bytes;
+    }
+    double* hbal = (double*)ctx->h_stage;
+    int* hraw = (int*)((char*)ctx->h_stage + plane * 8);
+    double* hir = (double*)((char*)ctx->h_stage + plane * 12);
+    // pack the diagonals into the pitched planes (zero tails), a few host threads
+    const int bf = b->bal_first;
+    auto pack = [&](int d_begin, int d_end) {
+        for (int d = d_begin; d < d_end; ++d) {
+            const size_t len = (size_t)(n - d);
+            int* rr = hraw + (size_t)d * pitch;
+            memcpy(rr, b->raw_diags[d], len * sizeof(int));
+            memset(rr + len, 0, (pitch - len) * sizeof(int));
+            double* br = hbal + (size_t)d * pitch;
+            if (d >= bf) {
+                memcpy(br, b->bal_diags[d - bf], len * sizeof(double));
+                memset(br + len, 0, (pitch - len) * sizeof(double));
+            } else {
+                memset(br, 0, (size_t)pitch * sizeof(double));
+            }
+        }
+    };
+    unsigned nthreads = std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
+    if (plane < (1u << 20)) nthreads = 1;
+    if (nthreads == 1) {
+        pack(0, num);
+    } else {
+        std::vector<std::thread> th;
+        const int per = (num + nthreads - 1) / nthreads;
+        for (unsigned t = 0; t < nthreads; ++t) {
+            const int a = t * per, e = std::min(num, a + per);
+            if (a < e) th.emplace_back(pack, a, e);
+        }
+        for (auto& t : th) t.join();
+    }
+    for (int d = 0; d < num; ++d) hir[d] = d >= bf ? b->ir[d - bf] : 0.0;
+    CK(cudaMemcpyAsync(ctx->d_bal, hbal, plane * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_raw, hraw, plane * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_ir, hir, (size_t)num * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_b1, b->b1, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_b2, b->b2, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n = n; ctx->num = num; ctx->bal_first = bf; ctx->pitch = pitch; ctx->plane = plane;
+    ctx->have_band = true;
+    return HP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sweep program: callers.py:15-23 (step order) and :138-198 (offsets of one step)
+static int build_program(hp_ctx* ctx, const hp_hiccups_params& P) {
+    Prog& G = ctx->prog;
+    memset(&G, 0, sizeof(G));
+    ctx->opa.clear(); ctx->opb.clear(); ctx->opy.clear(); ctx->opr.clear();
+    G.npw = P.npw; G.thr = P.min_local_reads;
+    int minp = P.pw[0];
+    for (int i = 0; i < P.npw; ++i) { G.pw[i] = P.pw[i]; G.ww[i] = P.ww[i]; minp = std::min(minp, P.pw[i]); }
+    struct St { int w, p, pi; };
+    std::vector<St> steps;
+    for (int i = 0; i < P.npw; ++i)
+        for (int w = P.ww[i]; w <= P.maxww; ++w) steps.push_back({w, P.pw[i], i});
+    std::stable_sort(steps.begin(), steps.end(), [](const St& a, const St& b) { return a.w != b.w ? a.w < b.w : a.p < b.p; });
+    if ((int)steps.size() > HP_MAX_STEPS) return fail(ctx, HP_ERR_INVALID, "too many sweep steps");
+    if (steps.empty()) return fail(ctx, HP_ERR_INVALID, "no sweep step (ww > maxww)");
+    G.nsteps = (int)steps.size();
+    bool limit = false;
+    int last_p = 0, last_w = 0, nr = 0;
+    for (int s = 0; s < G.nsteps; ++s) {
+        const int p = steps[s].p, w = steps[s].w;
+        for (int a = -w; a <= w; ++a)
+            for (int b = -w; b <= w; ++b) {
+                const int g = std::max(abs(a), abs(b));
+                if (limit && ((g <= last_w && g > std::max(p, last_p)) || g <= std::min(p, last_p))) continue;
+                if (a == 0 || b == 0) continue;
+                if (abs(a) <= p && abs(b) <= p) continue;
+                const bool isy = a > 0 && b < 0;
+                const bool isr = isy && (!limit || (p == minp && g > last_w));
+                ctx->opa.push_back((signed char)a); ctx->opb.push_back((signed char)b);
+                ctx->opy.push_back(isy); ctx->opr.push_back(isr);
+                nr += isr;
+            }
+        limit = true; last_p = p; last_w = w;
+        G.step_pi[s] = steps[s].pi; G.step_w[s] = w;
+        G.op_end[s] = (int)ctx->opa.size();
+        G.rop_end[s] = nr;
+    }
+    if ((int)ctx->opa.size() > kMaxOps || nr > kMaxROps)
+        return fail(ctx, HP_ERR_INVALID, "sweep program too long for this build (" + std::to_string(ctx->opa.size()) + " offsets)");
+    return HP_OK;
+}
+
+static int make_map(hp_ctx* ctx, CUtensorMap* map, CUtensorMapDataType dt, int esize, void* base, int box_r, int box_d) {
+    cuuint64_t dims[2] = {(cuuint64_t)ctx->pitch, (cuuint64_t)ctx->num};
+    cuuint64_t strides[1] = {(cuuint64_t)ctx->pitch * esize};
+    cuuint32_t box[2] = {(cuuint32_t)box_r, (cuuint32_t)box_d};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = ctx->encode(map, dt, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, HP_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    return HP_OK;
+}
+
+static int64_t band_pixel_count(int64_t n, int64_t lo, int64_t hi) {
+    hi = std::min(hi, n - 1);
+    if (hi < lo) return 0;
+    const int64_t k = hi - lo + 1;
+    return k * n - (lo + hi) * k / 2;
+}
+
+extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hiccups_summary* out) {
+    if (!ctx || !prm) return fail(ctx, HP_ERR_INVALID, "NULL argument");
+    if (!ctx->have_band) return fail(ctx, HP_ERR_STATE, "hp_band_upload must come first");
+    const hp_hiccups_params& P = *prm;
+    if (P.npw < 1 || P.npw > HP_MAX_PW) return fail(ctx, HP_ERR_INVALID, "npw out of range");
+    if (P.maxww < 1 || P.maxww > HP_MAX_WW) return fail(ctx, HP_ERR_INVALID, "maxww out of range [1,20]");
+    int minww = P.ww[0], maxw0 = P.ww[0];
+    for (int i = 0; i < P.npw; ++i) {
+        if (P.pw[i] < 0 || P.ww[i] < 1 || P.ww[i] > P.maxww) return fail(ctx, HP_ERR_INVALID, "need 0 <= pw, 1 <= ww <= maxww");
+        for (int j = 0; j < i; ++j) if (P.pw[j] == P.pw[i]) return fail(ctx, HP_ERR_INVALID, "duplicate pw value");
+        minww = std::min(minww, P.ww[i]); maxw0 = std::max(maxw0, P.ww[i]);
+    }
+    if (minww != ctx->bal_first) return fail(ctx, HP_ERR_INVALID, "band was uploaded with bal_first != min(ww)");
+    if (!(P.sig >= 0.0)) return fail(ctx, HP_ERR_INVALID, "sig must be >= 0");
+    CK(cudaSetDevice(ctx->device));
+    ctx->scored = false; ctx->fdr_done = false;
+    ctx->prm = P;
+    int rc = build_program(ctx, P);
+    if (rc) return rc;
+    Prog& G = ctx->prog;
+    hp_hiccups_summary& S = ctx->sum;
+    memset(&S, 0, sizeof(S));
+    const int n = (int)ctx->n, num = ctx->num, pitch = ctx->pitch;
+    const int dlo = minww;
+    const int dhi = (int)std::min<int64_t>(std::min<int64_t>(P.maxapart_bins, num - 1), n - 1);
+    ctx->dlo = dlo; ctx->dhi = dhi;
+    S.band_pixels = band_pixel_count(n, dlo, std::min<int64_t>(P.maxapart_bins, n - 1));
+    if (dhi < dlo) return fail(ctx, HP_ERR_EMPTY_REFIDX, "no band pixel: the reference fails at callers.py:205-208");
+    cudaStream_t st = ctx->stream;
+    const int nops = (int)ctx->opa.size();
+    int launches = 0;
+
+    // ---- K1: levels --------------------------------------------------------------------------
+    const int F1 = P.maxww, TD1 = 32;
+    const int BR1 = (kTR + F1 + 3) / 4 * 4, BD1 = TD1 + 2 * F1;
+    {
+        std::vector<int> roff;
+        for (int i = 0; i < nops; ++i)
+            if (ctx->opr[i]) roff.push_back((ctx->opb[i] - ctx->opa[i]) * BR1 + ctx->opa[i]);
+        G.nsteps_exec = G.nsteps;
+        CK(cudaMemcpyToSymbolAsync(c_prog, &G, sizeof(Prog), 0, cudaMemcpyHostToDevice, st));
+        if (!roff.empty()) CK(cudaMemcpyToSymbolAsync(c_roff, roff.data(), roff.size() * sizeof(int), 0, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyToSymbolAsync(c_opa, ctx->opa.data(), nops, 0, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyToSymbolAsync(c_opb, ctx->opb.data(), nops, 0, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyToSymbolAsync(c_opy, ctx->opy.data(), nops, 0, cudaMemcpyHostToDevice, st));
+    }
+    CUtensorMap tm_raw;
+    rc = make_map(ctx, &tm_raw, CU_TENSOR_MAP_DATA_TYPE_INT32, 4, ctx->d_raw, BR1, BD1);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[0], st));
+    CK(cudaMemsetAsync(ctx->d_lhist, 0, (HP_MAX_STEPS + 2) * sizeof(unsigned long long), st));
+    {
+        LevelArgs A{ctx->d_lvl, ctx->d_lhist, n, pitch, dlo, dhi, F1, BR1, BD1, TD1};
+        const size_t smem = (size_t)BR1 * BD1 * 4 + 16 + (G.nsteps + 2) * 4;
+        CK(cudaFuncSetAttribute(k_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((n + kTR - 1) / kTR, (dhi - dlo + TD1) / TD1);
+        k_levels<<<grid, kThreads, smem, st>>>(tm_raw, A);
+        ++launches;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(ctx->ev[1], st));
+    std::vector<unsigned long long> lh(G.nsteps + 1);
+    CK(cudaMemcpyAsync(lh.data(), ctx->d_lhist, lh.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+
+    // ---- replay of the adaptive-width control flow (callers.py:203-232) ------------------------
+    unsigned long long total = 0;
+    for (auto v : lh) total += v;
+    S.n_pixels = (int64_t)total;
+    std::vector<unsigned long long> cum(G.nsteps + 1);
+    { unsigned long long c = 0; for (int s = 0; s <= G.nsteps; ++s) { c += lh[s]; cum[s] = c; } }
+    unsigned long long ini[HP_MAX_PW];
+    int lastp[HP_MAX_PW];
+    for (int i = 0; i < P.npw; ++i) { ini[i] = total; lastp[i] = -1; }
+    int frozen = P.maxww, nexec = 0;
+    for (int s = 0; s < G.nsteps; ++s) {
+        const int pi = G.step_pi[s], w = G.step_w[s];
+        if (w > frozen) break;                      // steps are sorted by w: the rest is skipped too
+        if (ini[pi] == 0)
+            return fail(ctx, HP_ERR_EMPTY_REFIDX, "unresolved set of p=" + std::to_string(P.pw[pi]) + " is empty at step (" +
+                                                       std::to_string(P.pw[pi]) + "," + std::to_string(w) +
+                                                       "): the reference fails at callers.py:205-208");
+        const unsigned long long resolved = cum[s] - (lastp[pi] >= 0 ? cum[lastp[pi]] : 0ull);
+        const double valid = (double)resolved / (double)ini[pi];
+        ini[pi] -= resolved;
+        const double left = (double)ini[pi] / (double)total;
+        S.steps[nexec] = hp_step_stat{P.pw[pi], w, (int64_t)resolved, valid, left};
+        lastp[pi] = s;
+        ++nexec;
+        if (w >= maxw0 && (valid < 0.3 || left < 0.03)) frozen = w;
+    }
+    S.frozen_w = frozen; S.n_steps = nexec;
+    G.nsteps_exec = nexec;
+    for (int pi = 0; pi < P.npw; ++pi)
+        for (int sv = 0; sv <= G.nsteps + 1; ++sv) {
+            unsigned char r = kNoStep;
+            for (int s = sv; s < nexec; ++s) if (G.step_pi[s] == pi) { r = (unsigned char)s; break; }
+            G.next_step[pi][sv] = r;
+        }
+
+    // ---- tables for K2 ------------------------------------------------------------------------
+    const int F = frozen, HR = (F + 1) & ~1;   // TMA box start (r0 - HR) must stay 16-byte aligned
+    int TD = 32;
+    const int sh_pairs = std::min(P.npw, kShPairs);
+    auto smem_for = [&](int td) {
+        return (size_t)(kTR + 2 * HR) * (td + 4 * F) * 8 + 224 + kStage * sizeof(Cand) + (size_t)sh_pairs * 2 * kShI * kShK * 4;
+    };
+    while (TD > 8 && smem_for(TD) > 110 * 1024) TD /= 2;     // keep two CTAs per SM where possible
+    const int BR = kTR + 2 * HR, BD = TD + 4 * F;
+    if (smem_for(TD) > 227 * 1024) return fail(ctx, HP_ERR_INVALID, "tile does not fit shared memory");
+    {
+        std::vector<int> off2(nops);
+        for (int i = 0; i < nops; ++i) off2[i] = (((ctx->opb[i] - ctx->opa[i]) * BR + ctx->opa[i]) << 1) | (ctx->opy[i] ? 1 : 0);
+        CK(cudaMemcpyToSymbolAsync(c_off2, off2.data(), nops * sizeof(int), 0, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyToSymbolAsync(c_prog, &G, sizeof(Prog), 0, cudaMemcpyHostToDevice, st));
+        // candidate thresholds for this sig (host copy of the universal Poisson table)
+        Chunks& C = ctx->chunks;
+        const double lim = P.sig * (1.0 + 1e-9) + 1e-300;
+        for (int i = 1; i <= C.maxchunk; ++i) {
+            const double* p = ctx->h_ptab.data() + C.hoff[i];
+            int k = 0;
+            while (k < C.hw[i] && !(p[k] <= lim)) ++k;
+            C.kcand[i] = k;
+        }
+        CK(cudaMemcpyToSymbolAsync(c_chunks, &C, sizeof(Chunks), 0, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));   // host vectors above go out of scope
+    }
+    const size_t tb = ctx->chunks.total_bins;
+    CK(ensure(&ctx->d_betab, &ctx->cap_betab, (size_t)2 * nexec * num));
+    CK(ensure(&ctx->d_hist, &ctx->cap_hist, (size_t)P.npw * 2 * tb));
+    CK(ensure(&ctx->d_qtab, &ctx->cap_qtab, (size_t)P.npw * 2 * tb));
+    if (P.dump) {
+        CK(ensure(&ctx->d_dump, &ctx->cap_dump, (size_t)P.npw * 6 * ctx->plane));
+        const long long cnt = (long long)P.npw * 6 * ctx->plane;
+        k_fill_f64<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(ctx->d_dump, nan(""), cnt);
+        ++launches;
+    }
+    size_t want = std::min<size_t>((size_t)total * P.npw, (size_t)((double)total * P.npw * std::max(0.15, 1.5 * P.sig)) + 65536);
+    want = std::max<size_t>(want, 65536);
+    CUtensorMap tm_bal;
+    rc = make_map(ctx, &tm_bal, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, ctx->d_bal, BR, BD);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[2], st));
+    k_betab<<<dim3((num + 127) / 128, nexec), 128, 0, st>>>(ctx->d_ir, ctx->d_betab, num, ctx->bal_first, nexec);
+    ++launches;
+    unsigned int cnt[4] = {0, 0, 0, 0};
+    unsigned long long small[48];
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CK(ensure(&ctx->d_cand, &ctx->cap_cand, want));
+        CK(cudaMemsetAsync(ctx->d_hist, 0, (size_t)P.npw * 2 * tb * sizeof(unsigned int), st));
+        CK(cudaMemsetAsync(ctx->d_small, 0, 48 * sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(ctx->d_cnt, 0, 8 * sizeof(unsigned int), st));
+        CK(cudaMemsetAsync(ctx->d_rownz, 0, (size_t)n * sizeof(unsigned int), st));
+        ScoreArgs A{};
+        A.raw = ctx->d_raw; A.lvl = ctx->d_lvl; A.ir = ctx->d_ir; A.b1 = ctx->d_b1; A.b2 = ctx->d_b2;
+        A.betab = ctx->d_betab; A.hist = ctx->d_hist; A.emax_bits = ctx->d_small; A.nvalid = ctx->d_small + 16;
+        A.rownz = ctx->d_rownz; A.cand = ctx->d_cand; A.cand_count = ctx->d_cnt;
+        A.cand_cap = (unsigned)std::min<size_t>(ctx->cap_cand, 0xffffffffu);
+        A.dump = P.dump ? ctx->d_dump : nullptr; A.plane = (long long)ctx->plane;
+        A.n = n; A.num = num; A.pitch = pitch; A.dlo = dlo; A.dhi = dhi; A.F = F; A.HR = HR; A.BR = BR; A.BD = BD; A.TD = TD;
+        A.bal_first = ctx->bal_first; A.sh_pairs = sh_pairs;
+        const size_t smem = smem_for(TD);
+        CK(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((n + kTR - 1) / kTR, (dhi - dlo + TD) / TD);
+        k_score<<<grid, kThreads, smem, st>>>(tm_bal, A);
+        ++launches;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[3], st));
+        CK(cudaMemcpyAsync(cnt, ctx->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(small, ctx->d_small, sizeof(small), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (cnt[1] == 0) break;
+        if (attempt == 1) return fail(ctx, HP_ERR_CAPACITY, "candidate buffer overflow");
+        want = (size_t)total * P.npw + 1024;      // every pixel can be a candidate at most once per pair
+    }
+    if (cnt[2]) return fail(ctx, HP_ERR_CHUNK_OVERFLOW,
+                            std::to_string(cnt[2]) + " expected values exceed the last lambda-chunk edge " +
+                                std::to_string(ctx->chunks.rv[ctx->chunks.maxchunk]) + "; create the context with a larger max_chunks");
+    ctx->ncand = cnt[0];
+    S.n_candidates = cnt[0];
+    for (int i = 0; i < P.npw; ++i)
+        for (int fl = 0; fl < 2; ++fl) {
+            hp_lf_stat& L = S.lf[i][fl];
+            L.n_valid = (int64_t)small[16 + i * 2 + fl];
+            double em;
+            memcpy(&em, &small[i * 2 + fl], 8);
+            L.e_max = em;
+            L.numbin = (L.n_valid > 0) ? (int)ceil(log(em) / log(2.0) * 3 + 1) : 0;
+        }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); S.ms_levels = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); S.ms_score = ms;
+    S.ms_total = S.ms_levels + S.ms_score;
+    S.launches = launches;
+    ctx->scored = true;
+    if (out) *out = S;
+    return HP_OK;
+}
+
+extern "C" int hp_hiccups_fdr(hp_ctx* ctx, const int32_t* numbin_override, hp_hiccups_summary* out) {
+    if (!ctx) return fail(ctx, HP_ERR_INVALID, "NULL ctx");
+    if (!ctx->scored) return fail(ctx, HP_ERR_STATE, "hp_hiccups_score must come first");
+    CK(cudaSetDevice(ctx->device));
+    const hp_hiccups_params& P = ctx->prm;
+    hp_hiccups_summary& S = ctx->sum;
+    cudaStream_t st = ctx->stream;
+    int nb[16] = {0};
+    int maxnb = 0;
+    for (int i = 0; i < P.npw; ++i)
+        for (int fl = 0; fl < 2; ++fl) {
+            int v = numbin_override ? numbin_override[i * 2 + fl] : S.lf[i][fl].numbin;
+            S.lf[i][fl].numbin = v;
+            v = std::max(0, std::min(v, ctx->chunks.maxchunk));
+            nb[i * 2 + fl] = v;
+            maxnb = std::max(maxnb, v);
+        }
+    CK(cudaEventRecord(ctx->ev[4], st));
+    CK(cudaMemcpyAsync(ctx->d_numbin, nb, sizeof(nb), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->d_small + 32, 0, 16 * sizeof(unsigned long long), st));
+    int launches = 0;
+    if (maxnb > 0) {
+        k_bh<<<dim3(maxnb, P.npw * 2), kThreads, 0, st>>>(ctx->d_hist, ctx->d_ptab, ctx->d_qtab, ctx->d_numbin);
+        ++launches;
+        CK(cudaGetLastError());
+    }
+    unsigned int cnt[4] = {0, 0, 0, 0};
+    size_t want = std::max<size_t>(65536, ctx->ncand / 4 + 1024);
+    for (int attempt = 0; attempt < 2 && ctx->ncand > 0; ++attempt) {
+        CK(ensure(&ctx->d_surv, &ctx->cap_surv, want));
+        CK(cudaMemsetAsync(ctx->d_cnt + 4, 0, 4 * sizeof(unsigned int), st));
+        CK(cudaMemsetAsync(ctx->d_small + 32, 0, 16 * sizeof(unsigned long long), st));
+        FilterArgs A{};
+        A.cand = ctx->d_cand; A.ncand = ctx->ncand; A.ptab = ctx->d_ptab; A.qtab = ctx->d_qtab; A.numbin = ctx->d_numbin;
+        A.bal = ctx->d_bal; A.out = ctx->d_surv; A.out_count = ctx->d_cnt + 4;
+        A.out_cap = (unsigned)std::min<size_t>(ctx->cap_surv, 0xffffffffu);
+        A.nreject = ctx->d_small + 32; A.sig = P.sig; A.pitch = ctx->pitch;
+        k_filter<<<(ctx->ncand + 255) / 256, 256, 0, st>>>(A);
+        ++launches;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(cnt, ctx->d_cnt + 4, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (cnt[1] == 0) break;
+        if (attempt == 1) return fail(ctx, HP_ERR_CAPACITY, "survivor buffer overflow");
+        want = (size_t)ctx->ncand + 16;
+    }
+    CK(cudaEventRecord(ctx->ev[5], st));
+    unsigned long long nrej[16] = {0};
+    CK(cudaMemcpyAsync(nrej, ctx->d_small + 32, sizeof(nrej), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < P.npw; ++i)
+        for (int fl = 0; fl < 2; ++fl) S.lf[i][fl].n_reject = (int64_t)nrej[i * 2 + fl];
+    ctx->nsurv = cnt[0];
+    S.n_survivors = cnt[0];
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
+    S.ms_fdr = ms;
+    S.ms_total = S.ms_levels + S.ms_score + S.ms_fdr;
+    S.launches += launches;
+    memcpy(ctx->numbin, nb, sizeof(nb));
+    ctx->fdr_done = true;
+    if (out) *out = S;
+    return HP_OK;
+}
+
+extern "C" int hp_hiccups(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hiccups_summary* out) {
+    int rc = hp_hiccups_score(ctx, prm, nullptr);
+    if (rc) return rc;
+    return hp_hiccups_fdr(ctx, nullptr, out);
+}
+
+extern "C" int hp_get_survivors(hp_ctx* ctx, hp_survivor* buf, int64_t capacity, int64_t* count) {
+    if (!ctx || !count) return fail(ctx, HP_ERR_INVALID, "NULL argument");
+    if (!ctx->fdr_done) return fail(ctx, HP_ERR_STATE, "hp_hiccups_fdr must come first");
+    *count = ctx->nsurv;
+    if (!buf) return HP_OK;
+    if (capacity < (int64_t)ctx->nsurv) return fail(ctx, HP_ERR_CAPACITY, "survivor buffer too small");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->nsurv) {
+        CK(cudaMemcpyAsync(buf, ctx->d_surv, (size_t)ctx->nsurv * sizeof(hp_survivor), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return HP_OK;
+}
+
+extern "C" int hp_get_gaps(hp_ctx* ctx, uint8_t* out, int64_t n) {
+    if (!ctx || !out) return fail(ctx, HP_ERR_INVALID, "NULL argument");
+    if (!ctx->scored) return fail(ctx, HP_ERR_STATE, "hp_hiccups_score must come first");
+    if (n < ctx->n) return fail(ctx, HP_ERR_CAPACITY, "gap buffer too small");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<unsigned int> nz(ctx->n);
+    CK(cudaMemcpyAsync(nz.data(), ctx->d_rownz, (size_t)ctx->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int64_t i = 0; i < ctx->n; ++i) out[i] = nz[i] ? 0 : 1;
+    return HP_OK;
+}
+
+extern "C" int hp_dump_levels(hp_ctx* ctx, uint8_t* out, int64_t capacity) {
+    if (!ctx || !out) return fail(ctx, HP_ERR_INVALID, "NULL argument");
+    if (!ctx->scored) return fail(ctx, HP_ERR_STATE, "hp_hiccups_score must come first");
+    if (capacity < (int64_t)ctx->num * ctx->n) return fail(ctx, HP_ERR_CAPACITY, "level buffer too small");
+    CK(cudaSetDevice(ctx->device));
+    memset(out, kLvlNone, (size_t)ctx->num * ctx->n);
+    const int rows = ctx->dhi - ctx->dlo + 1;
+    CK(cudaMemcpy2DAsync(out + (size_t)ctx->dlo * ctx->n, ctx->n, ctx->d_lvl + (size_t)ctx->dlo * ctx->pitch, ctx->pitch,
+                         ctx->n, rows, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HP_OK;
+}
+
+extern "C" int hp_dump_plane(hp_ctx* ctx, int32_t pair, int32_t background, int32_t what, double* out, int64_t capacity) {
+    if (!ctx || !out) return fail(ctx, HP_ERR_INVALID, "NULL argument");
+    if (!ctx->scored || !ctx->prm.dump || !ctx->d_dump) return fail(ctx, HP_ERR_STATE, "score with params.dump != 0 first");
+    if (pair < 0 || pair >= ctx->prm.npw || background < 0 || background > 1 || what < 0 || what > 2)
+        return fail(ctx, HP_ERR_INVALID, "bad plane selector");
+    if (capacity < (int64_t)ctx->num * ctx->n) return fail(ctx, HP_ERR_CAPACITY, "plane buffer too small");
+    CK(cudaSetDevice(ctx->device));
+    const double* src = ctx->d_dump + (size_t)((pair * 2 + background) * 3 + what) * ctx->plane;
+    CK(cudaMemcpy2DAsync(out, ctx->n * 8, src, (size_t)ctx->pitch * 8, ctx->n * 8, ctx->num, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HP_OK;
+}
+
+extern "C" int hp_get_chunk_table(hp_ctx* ctx, int32_t pair, int32_t background, int32_t* numbin, int32_t* widths,
+                                  int64_t* hist, double* p, double* q, int64_t capacity) {
+    if (!ctx || !numbin) return fail(ctx, HP_ERR_INVALID, "NULL argument");
+    if (!ctx->fdr_done) return fail(ctx, HP_ERR_STATE, "hp_hiccups_fdr must come first");
+    if (pair < 0 || pair >= ctx->prm.npw || background < 0 || background > 1) return fail(ctx, HP_ERR_INVALID, "bad selector");
+    const int lf = pair * 2 + background;
+    const int nb = ctx->numbin[lf];
+    *numbin = nb;
+    const Chunks& C = ctx->chunks;
+    if (widths) for (int i = 1; i <= nb; ++i) widths[i - 1] = C.hw[i];
+    if (!hist && !p && !q) return HP_OK;
+    const size_t cnt = nb ? (size_t)C.hoff[nb] + C.hw[nb] : 0;
+    if ((size_t)capacity < cnt) return fail(ctx, HP_ERR_CAPACITY, "table buffer too small");
+    CK(cudaSetDevice(ctx->device));
+    if (cnt == 0) return HP_OK;
+    if (hist) {
+        std::vector<unsigned int> h(cnt);
+        CK(cudaMemcpyAsync(h.data(), ctx->d_hist + (size_t)lf * C.total_bins, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < cnt; ++i) hist[i] = h[i];
+    }
+    if (p) memcpy(p, ctx->h_ptab.data(), cnt * 8);
+    if (q) {
+        CK(cudaMemcpyAsync(q, ctx->d_qtab + (size_t)lf * C.total_bins, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return HP_OK;
+}
+
+extern "C" int hp_poisson_sf(hp_ctx* ctx, const double* k, const double* mu, double* out, int64_t count) {
+    if (!ctx || !k || !mu || !out || count < 0) return fail(ctx, HP_ERR_INVALID, "bad argument");
+    if (count == 0) return HP_OK;
+    CK(cudaSetDevice(ctx->device));
+    double* d = nullptr;
+    CK(cudaMalloc(&d, (size_t)count * 24));
+    cudaError_t e = cudaMemcpyAsync(d, k, count * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + count, mu, count * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        k_poisson_sf<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(d, d + count, d + 2 * count, count);
+        e = cudaMemcpyAsync(out, d + 2 * count, count * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, HP_ERR_CUDA, cudaGetErrorString(e));
+    return HP_OK;
+}

@@ -1,0 +1,72 @@
+// Device-side tables, small PTX helpers (mbarrier + TMA) and shared structs of the HiCCUPS engine.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <stdint.h>
+
+#include "../../include/hicpeaks_b200.h"
+
+namespace hp {
+
+constexpr int kTR = 128;          // tile rows (matrix row index r), one lane per r
+constexpr int kThreads = 256;
+constexpr int kMaxOps = 6144;     // stencil offsets of one whole sweep program
+constexpr int kMaxROps = 512;     // offsets that feed Reads (<= maxww^2)
+constexpr int kMaxChunk = 64;     // lambda-chunk cap
+constexpr int kShI = 20;          // smem-privatised histogram: chunks 1..kShI
+constexpr int kShK = 64;          //                            bins 0..kShK-1
+constexpr int kShPairs = 4;
+constexpr int kStage = 512;       // per-CTA candidate staging records
+constexpr unsigned char kLvlNever = 0xFE, kLvlNone = 0xFF, kNoStep = 0xFF;
+
+struct Prog {                     // the sweep program (callers.py:132-198 unrolled by the host)
+    int nsteps, nsteps_exec, npw, thr;
+    int pw[HP_MAX_PW], ww[HP_MAX_PW];
+    int step_pi[HP_MAX_STEPS], step_w[HP_MAX_STEPS];
+    int op_end[HP_MAX_STEPS];     // ops [op_end[s-1], op_end[s]) belong to step s
+    int rop_end[HP_MAX_STEPS];
+    unsigned char next_step[HP_MAX_PW][HP_MAX_STEPS + 2];  // [pair][s*] -> executed step resolving it
+};
+
+struct Chunks {                   // lambda-chunk geometry (callers.py:30-38) + table layout
+    double rv[kMaxChunk + 2];     // rv[i] = upper edge of chunk i (1-based); rv[0] = 0
+    int hoff[kMaxChunk + 2];      // first bin of chunk i in the flat tables
+    int hw[kMaxChunk + 2];        // bins of chunk i (observed counts >= hw-1 share the last bin, p == 0)
+    int kcand[kMaxChunk + 2];     // smallest observed count with p <= sig (candidate threshold)
+    int maxchunk, total_bins;
+};
+
+struct Cand {                     // 32 B: a pixel whose Poisson p can pass sig for K or Y
+    int r, d, obs;
+    unsigned char pair, flags, chunk_k, chunk_y;
+    double e_k, e_y;
+};
+
+// ---- mbarrier / TMA -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+// 2-D tiled bulk tensor load global -> shared; out-of-bounds elements arrive as zeros
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+}  // namespace hp

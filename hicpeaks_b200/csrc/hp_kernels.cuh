@@ -1,0 +1,509 @@
+// sm_100a kernels of the HiCCUPS scoring path.  Band layout in HBM: diagonal-major planes
+// X[d][r] = matrix element (r, r + d), row pitch `pitch` elements (multiple of 32), zero beyond the
+// chromosome end; shift(X, a, b)[r, c] = X[r + a, c + b] is plane element [d + b - a][r + a].
+#pragma once
+#include "hp_device.cuh"
+#include "hp_poisson.cuh"
+
+namespace hp {
+
+__constant__ Prog c_prog;
+__constant__ Chunks c_chunks;
+__constant__ int c_off2[kMaxOps];            // score kernel: (tile offset << 1) | isY
+__constant__ signed char c_opa[kMaxOps];
+__constant__ signed char c_opb[kMaxOps];
+__constant__ unsigned char c_opy[kMaxOps];
+__constant__ int c_roff[kMaxROps];           // level kernel: tile offsets of the Reads ops
+
+// ============================================================================================
+// K1  level kernel -- callers.py:197-198 (Reads accumulation) + :203-206 (Reads >= min_local_reads)
+// For every non-zero band pixel: the first sweep step s* after which the raw lower-left sum reaches
+// the threshold.  Integer work on the raw plane only; one TMA tile (+ lower-left halo) per CTA.
+// ============================================================================================
+struct LevelArgs {
+    unsigned char* lvl;            // [num][pitch]
+    unsigned long long* hist;      // [nsteps + 1]   (index nsteps = never)
+    int n, pitch, dlo, dhi, F, BR, BD, TD;
+};
+
+__global__ void __launch_bounds__(kThreads) k_levels(const __grid_constant__ CUtensorMap tm_raw, LevelArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    int* tile = reinterpret_cast<int*>(smem);
+    const int tile_bytes = A.BR * A.BD * 4;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + tile_bytes);
+    unsigned int* sh_hist = reinterpret_cast<unsigned int*>(smem + tile_bytes + 16);
+
+    const int r0 = blockIdx.x * kTR;
+    const int d0 = A.dlo + blockIdx.y * A.TD;
+    const int nsteps = c_prog.nsteps;
+    for (int i = threadIdx.x; i <= nsteps; i += kThreads) sh_hist[i] = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, (uint32_t)tile_bytes);
+        tma_load_2d(tile, &tm_raw, r0, d0 - 2 * A.F, bar);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    const int rl = threadIdx.x & (kTR - 1);
+    const int r = r0 + rl;
+    const long long thr = c_prog.thr;
+    for (int dl = threadIdx.x >> 7; dl < A.TD; dl += kThreads / kTR) {
+        const int d = d0 + dl;
+        if (d > A.dhi || r >= A.n) continue;
+        const int* ctr = tile + (dl + 2 * A.F) * A.BR + rl;
+        unsigned char out = kLvlNone;
+        if (r + d < A.n && *ctr != 0) {
+            long long R = 0;
+            int opi = 0;
+            out = kLvlNever;
+            for (int s = 0; s < nsteps; ++s) {
+                const int e = c_prog.rop_end[s];
+                for (; opi < e; ++opi) R += ctr[c_roff[opi]];
+                if (R >= thr) { out = (unsigned char)s; break; }
+            }
+            const int slot = (out == kLvlNever) ? nsteps : out;
+            const unsigned m = __match_any_sync(__activemask(), slot);
+            if ((threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&sh_hist[slot], __popc(m));
+        }
+        A.lvl[(size_t)d * A.pitch + r] = out;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= nsteps; i += kThreads)
+        if (sh_hist[i]) atomicAdd(&A.hist[i], (unsigned long long)sh_hist[i]);
+}
+
+// ============================================================================================
+// expected-sum table for interior pixels: bE[fl][s][d] = ordered sum of IR over the offsets added
+// up to and including step s (callers.py:178,182,189-191).  Away from the chromosome ends the sum
+// only depends on the diagonal, so it never touches the band.
+// ============================================================================================
+__global__ void k_betab(const double* __restrict__ ir, double* __restrict__ betab, int num, int bal_first,
+                        int nsteps_exec) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (d >= num || s >= nsteps_exec) return;
+    double ek = 0.0, ey = 0.0;
+    const int e = c_prog.op_end[s];
+    for (int i = 0; i < e; ++i) {
+        const int dd = d + c_opb[i] - c_opa[i];
+        if (dd >= bal_first && dd < num) {
+            const double v = ir[dd];
+            ek = __dadd_rn(ek, v);
+            if (c_opy[i]) ey = __dadd_rn(ey, v);
+        }
+    }
+    betab[(size_t)s * num + d] = ek;
+    betab[(size_t)(nsteps_exec + s) * num + d] = ey;
+}
+
+// same sum for a pixel next to a chromosome end (some offsets fall outside [0, n)^2)
+__device__ __noinline__ void edge_be(const double* __restrict__ ir, int r, int d, int n, int num, int bal_first,
+                                     int s, double& ek, double& ey) {
+    ek = 0.0; ey = 0.0;
+    const int e = c_prog.op_end[s];
+    const int c = r + d;
+    for (int i = 0; i < e; ++i) {
+        const int a = c_opa[i], b = c_opb[i];
+        const int dd = d + b - a, rr = r + a, cc = c + b;
+        if (rr >= 0 && rr < n && cc >= 0 && cc < n && dd >= bal_first && dd < num) {
+            const double v = ir[dd];
+            ek = __dadd_rn(ek, v);
+            if (c_opy[i]) ey = __dadd_rn(ey, v);
+        }
+    }
+}
+
+// ============================================================================================
+// K2  score kernel -- callers.py:132-198 (donut / lower-left sums in the reference's fp64 order),
+// :212-213 (snapshot at the resolving step), :244-256 (E, validity), :25-41 (lambda-chunk id) and
+// the (chunk, observed) histogram that replaces the per-chunk sort of multipletests (:265-275).
+// One TMA tile of the balanced plane with halo (+-F rows, +-2F diagonals) per CTA.
+// ============================================================================================
+struct ScoreArgs {
+    const int* raw;
+    const unsigned char* lvl;
+    const double* ir;
+    const double* b1;
+    const double* b2;
+    const double* betab;               // [2][nsteps_exec][num]
+    unsigned int* hist;                // [npw*2][total_bins]
+    unsigned long long* emax_bits;     // [npw*2]
+    unsigned long long* nvalid;        // [npw*2]
+    unsigned int* rownz;               // [n] row has a non-zero stored balanced value
+    Cand* cand;
+    unsigned int* cand_count;          // [0] records, [1] dropped (capacity), [2] chunk overflow
+    unsigned int cand_cap;
+    double* dump;                      // optional [npw*2][3][num*pitch]
+    long long plane;
+    int n, num, pitch, dlo, dhi, F, HR, BR, BD, TD, bal_first, sh_pairs;   // HR: row halo, F rounded up to even
+};
+
+__device__ __forceinline__ int find_chunk(double E, bool& member) {
+    // smallest i >= 1 with E < rv[i]; member iff rv[i-1] < E (strict, callers.py:38)
+    const int mc = c_chunks.maxchunk;
+    int i = 1;
+    if (E >= 1.0) {
+        const int e = ilogb(E);
+        i = (e > 40) ? mc + 1 : 3 * e + 2;
+        if (i > mc + 1) i = mc + 1;
+    }
+    while (i <= mc && E >= c_chunks.rv[i]) ++i;
+    while (i > 1 && E < c_chunks.rv[i - 1]) --i;
+    member = (i <= mc) && (E > c_chunks.rv[i - 1]);
+    return i;
+}
+
+__global__ void __launch_bounds__(kThreads) k_score(const __grid_constant__ CUtensorMap tm_bal, ScoreArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    double* tile = reinterpret_cast<double*>(smem);
+    const int tile_bytes = A.BR * A.BD * 8;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + tile_bytes);
+    unsigned int* sh_cnt = reinterpret_cast<unsigned int*>(smem + tile_bytes + 8);   // staged count
+    unsigned long long* sh_emax = reinterpret_cast<unsigned long long*>(smem + tile_bytes + 16);  // [16]
+    unsigned int* sh_nval = reinterpret_cast<unsigned int*>(smem + tile_bytes + 16 + 128);        // [16]
+    unsigned int* sh_base = sh_nval + 16;                                                          // [1]
+    Cand* sh_stage = reinterpret_cast<Cand*>(smem + tile_bytes + 16 + 128 + 64 + 16);
+    unsigned int* sh_hist = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(sh_stage) + kStage * sizeof(Cand));
+    const int sh_bins = A.sh_pairs * 2 * kShI * kShK;
+
+    const int r0 = blockIdx.x * kTR;
+    const int d0 = A.dlo + blockIdx.y * A.TD;
+    const int npw = c_prog.npw;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, (uint32_t)tile_bytes);
+        tma_load_2d(tile, &tm_bal, r0 - A.HR, d0 - 2 * A.F, bar);   // box start must be 16-byte aligned
+        *sh_cnt = 0;
+    }
+    for (int i = threadIdx.x; i < sh_bins; i += kThreads) sh_hist[i] = 0;
+    if (threadIdx.x < 16) { sh_emax[threadIdx.x] = 0ull; sh_nval[threadIdx.x] = 0u; }
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    const int lane = threadIdx.x & 31;
+    const int rl = threadIdx.x & (kTR - 1);
+    const int r = r0 + rl;
+    const int nexec = c_prog.nsteps_exec;
+    const int total_bins = c_chunks.total_bins;
+    bool row_nz = false;
+
+    for (int dl = threadIdx.x >> 7; dl < A.TD; dl += kThreads / kTR) {
+        const int d = d0 + dl;                       // warp-uniform
+        if (d > A.dhi) break;
+        const double* ctr = tile + (dl + 2 * A.F) * A.BR + (rl + A.HR);
+        const bool inside = (r < A.n) && (r + d < A.n);
+        unsigned char lv = kLvlNone;
+        int obs = 0;
+        if (inside) {
+            lv = A.lvl[(size_t)d * A.pitch + r];
+            obs = A.raw[(size_t)d * A.pitch + r];
+            row_nz |= (*ctr != 0.0);
+        }
+        int last = -1;
+        if (lv < kLvlNever) {
+            for (int pi = 0; pi < npw; ++pi) {
+                if (d < c_prog.ww[pi]) continue;
+                const int rs = c_prog.next_step[pi][lv];
+                if (rs != kNoStep && rs > last) last = rs;
+            }
+        }
+        const int wlast = __reduce_max_sync(0xffffffffu, last);
+        if (wlast < 0) continue;
+        const bool edge = (r < A.F) || (r + d >= A.n - A.F);
+        double SK = 0.0, SY = 0.0;
+        int opi = 0;
+        for (int s = 0; s <= wlast; ++s) {
+            const int oe = c_prog.op_end[s];
+            if (s <= last) {
+                for (; opi < oe; ++opi) {
+                    const int o = c_off2[opi];
+                    const double v = ctr[o >> 1];
+                    SK = __dadd_rn(SK, v);
+                    if (o & 1) SY = __dadd_rn(SY, v);
+                }
+            }
+            const int pi = c_prog.step_pi[s];
+            const bool em = (s <= last) && (d >= c_prog.ww[pi]) && (c_prog.next_step[pi][lv] == s);
+            bool cand = false;
+            unsigned char flags = 0, chk[2] = {0, 0};
+            double Ev[2] = {0.0, 0.0};
+            if (em) {
+                double be[2];
+                if (edge) {
+                    edge_be(A.ir, r, d, A.n, A.num, A.bal_first, s, be[0], be[1]);
+                } else {
+                    be[0] = A.betab[(size_t)s * A.num + d];
+                    be[1] = A.betab[(size_t)(nexec + s) * A.num + d];
+                }
+                const double ird = A.ir[d], bb1 = A.b1[r], bb2 = A.b2[r + d];
+#pragma unroll
+                for (int fl = 0; fl < 2; ++fl) {
+                    const double bs = fl ? SY : SK;
+                    double E = 0.0;
+                    bool valid = false;
+                    if (be[fl] != 0.0) {
+                        const double ratio = __ddiv_rn(bs, be[fl]);
+                        const double cem = __dmul_rn(ird, ratio);
+                        E = __dmul_rn(__dmul_rn(cem, bb1), bb2);
+                        const bool cnz = (ratio != 0.0) && (cem != 0.0);
+                        valid = cnz && (E > 0.0);
+                        if (fl == 1 && cnz) flags |= HP_SF_CEMY_NONZERO;
+                    }
+                    if (A.dump) {
+                        double* dp = A.dump + (size_t)((pi * 2 + fl) * 3) * A.plane + (size_t)d * A.pitch + r;
+                        dp[0] = bs;
+                        dp[A.plane] = be[fl];
+                        dp[2 * A.plane] = valid ? E : 0.0;
+                    }
+                    if (valid) {
+                        flags |= (fl ? HP_SF_VALID_Y : HP_SF_VALID_K);
+                        Ev[fl] = E;
+                        bool member;
+                        const int ci = find_chunk(E, member);
+                        if (ci > c_chunks.maxchunk) atomicAdd(&A.cand_count[2], 1u);
+                        if (member) {
+                            chk[fl] = (unsigned char)ci;
+                            const int w = c_chunks.hw[ci];
+                            const int kb = obs < w - 1 ? obs : w - 1;
+                            if (pi < A.sh_pairs && ci <= kShI && kb < kShK)
+                                atomicAdd(&sh_hist[((pi * 2 + fl) * kShI + (ci - 1)) * kShK + kb], 1u);
+                            else
+                                atomicAdd(&A.hist[(size_t)(pi * 2 + fl) * total_bins + c_chunks.hoff[ci] + kb], 1u);
+                            cand |= (obs >= c_chunks.kcand[ci]);
+                        }
+                    }
+                }
+            }
+            // warp-converged bookkeeping: valid counts, E max, candidate staging
+            const unsigned any = __ballot_sync(0xffffffffu, em);
+            if (any) {
+#pragma unroll
+                for (int fl = 0; fl < 2; ++fl) {
+                    const unsigned mv = __ballot_sync(0xffffffffu, (flags & (fl ? HP_SF_VALID_Y : HP_SF_VALID_K)) != 0);
+                    if (mv) {
+                        unsigned long long eb = (unsigned long long)__double_as_longlong(Ev[fl]);
+#pragma unroll
+                        for (int o = 16; o; o >>= 1) {
+                            const unsigned long long t = __shfl_xor_sync(0xffffffffu, eb, o);
+                            eb = t > eb ? t : eb;
+                        }
+                        if (lane == 0) {
+                            atomicAdd(&sh_nval[pi * 2 + fl], (unsigned)__popc(mv));
+                            atomicMax(&sh_emax[pi * 2 + fl], eb);
+                        }
+                    }
+                }
+                const unsigned mc = __ballot_sync(0xffffffffu, cand);
+                if (mc) {
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(sh_cnt, (unsigned)__popc(mc));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (cand) {
+                        const unsigned slot = base + __popc(mc & ((1u << lane) - 1u));
+                        Cand cr;
+                        cr.r = r; cr.d = d; cr.obs = obs;
+                        cr.pair = (unsigned char)pi; cr.flags = flags; cr.chunk_k = chk[0]; cr.chunk_y = chk[1];
+                        cr.e_k = Ev[0]; cr.e_y = Ev[1];
+                        if (slot < kStage) {
+                            sh_stage[slot] = cr;
+                        } else {  // staging full: straight to the global list
+                            const unsigned g = atomicAdd(&A.cand_count[0], 1u);
+                            if (g < A.cand_cap) A.cand[g] = cr; else atomicAdd(&A.cand_count[1], 1u);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (row_nz && r < A.n) A.rownz[r] = 1u;
+    __syncthreads();
+    // flush: privatised histogram, counters, staged candidates
+    for (int i = threadIdx.x; i < sh_bins; i += kThreads) {
+        const unsigned v = sh_hist[i];
+        if (v) {
+            const int kb = i % kShK, ci = (i / kShK) % kShI + 1, lf = i / (kShK * kShI);
+            atomicAdd(&A.hist[(size_t)lf * total_bins + c_chunks.hoff[ci] + kb], v);
+        }
+    }
+    if (threadIdx.x < 2 * npw) {
+        if (sh_nval[threadIdx.x]) atomicAdd(&A.nvalid[threadIdx.x], (unsigned long long)sh_nval[threadIdx.x]);
+        if (sh_emax[threadIdx.x]) atomicMax(&A.emax_bits[threadIdx.x], sh_emax[threadIdx.x]);
+    }
+    unsigned staged = *sh_cnt;
+    if (staged > kStage) staged = kStage;
+    if (staged) {
+        if (threadIdx.x == 0) *sh_base = atomicAdd(&A.cand_count[0], staged);
+        __syncthreads();
+        const unsigned base = *sh_base;
+        for (unsigned i = threadIdx.x; i < staged; i += kThreads) {
+            if (base + i < A.cand_cap) A.cand[base + i] = sh_stage[i];
+            else atomicAdd(&A.cand_count[1], 1u);
+        }
+    }
+}
+
+// ============================================================================================
+// Poisson tables: p[i][k] = 1 - pdtr(k, rv_i)  (callers.py:268-270); universal, built once per ctx
+// ============================================================================================
+__global__ void k_ptab(double* __restrict__ ptab) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= c_chunks.total_bins) return;
+    int lo = 1, hi = c_chunks.maxchunk;          // chunk containing flat bin idx
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (c_chunks.hoff[mid] <= idx) lo = mid; else hi = mid - 1;
+    }
+    ptab[idx] = poisson_sf((double)(idx - c_chunks.hoff[lo]), c_chunks.rv[lo]);
+}
+
+// ============================================================================================
+// K3  Benjamini-Hochberg per lambda-chunk from the histogram -- replaces multipletests(fdr_bh)
+// (callers.py:273): with N>=(k) = #pixels of the chunk with observed >= k and n the chunk size,
+// raw(k) = p(k) / (N>=(k) / float(n)),  q(k) = min(1, min_{k' <= k, h[k'] > 0} raw(k')).
+// One CTA per (chunk, pair*2+background).
+// ============================================================================================
+__device__ __forceinline__ unsigned long long block_scan_add(unsigned long long v, unsigned long long* sh, unsigned long long& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += t;
+    }
+    __syncthreads();
+    if (lane == 31) sh[wid] = x;
+    __syncthreads();
+    unsigned long long pre = 0, tot = 0;
+    for (int w = 0; w < kThreads / 32; ++w) { if (w < wid) pre += sh[w]; tot += sh[w]; }
+    total = tot;
+    return x + pre;   // inclusive
+}
+__device__ __forceinline__ double block_scan_min(double v, double* sh, double& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x = fmin(x, t);
+    }
+    __syncthreads();
+    if (lane == 31) sh[wid] = x;
+    __syncthreads();
+    double pre = INFINITY, tot = INFINITY;
+    for (int w = 0; w < kThreads / 32; ++w) { if (w < wid) pre = fmin(pre, sh[w]); tot = fmin(tot, sh[w]); }
+    total = tot;
+    return fmin(x, pre);
+}
+
+__global__ void __launch_bounds__(kThreads) k_bh(const unsigned int* __restrict__ hist, const double* __restrict__ ptab,
+                                                  double* __restrict__ qtab, const int* __restrict__ numbin) {
+    __shared__ unsigned long long sh_u[kThreads / 32];
+    __shared__ double sh_d[kThreads / 32];
+    const int ci = blockIdx.x + 1, lf = blockIdx.y;
+    if (ci > numbin[lf]) return;
+    const int w = c_chunks.hw[ci], off = c_chunks.hoff[ci];
+    const unsigned int* h = hist + (size_t)lf * c_chunks.total_bins + off;
+    double* q = qtab + (size_t)lf * c_chunks.total_bins + off;
+    const double* p = ptab + off;
+    // n = chunk size
+    unsigned long long part = 0, n = 0;
+    for (int k = threadIdx.x; k < w; k += kThreads) part += h[k];
+    block_scan_add(part, sh_u, n);
+    __syncthreads();
+    if (n == 0) {
+        for (int k = threadIdx.x; k < w; k += kThreads) q[k] = 1.0;
+        return;
+    }
+    const double fn = (double)n;
+    // pass 1 (k descending): suffix counts -> raw(k) stored in q
+    unsigned long long carry = 0;
+    for (int base = w - 1; base >= 0; base -= kThreads) {
+        const int k = base - (int)threadIdx.x;
+        const unsigned long long hv = (k >= 0) ? h[k] : 0ull;
+        unsigned long long tot;
+        const unsigned long long inc = block_scan_add(hv, sh_u, tot) + carry;
+        if (k >= 0) q[k] = hv ? __ddiv_rn(p[k], __ddiv_rn((double)inc, fn)) : INFINITY;
+        carry += tot;
+        __syncthreads();
+    }
+    __syncthreads();
+    // pass 2 (k ascending): running minimum, clip at 1
+    double cmin = INFINITY;
+    for (int base = 0; base < w; base += kThreads) {
+        const int k = base + (int)threadIdx.x;
+        const double rv = (k < w) ? q[k] : INFINITY;
+        double tot;
+        const double m = fmin(block_scan_min(rv, sh_d, tot), cmin);
+        if (k < w) q[k] = m > 1.0 ? 1.0 : m;
+        cmin = fmin(cmin, tot);
+        __syncthreads();
+    }
+}
+
+// ============================================================================================
+// survivor selection: q <= sig for K or Y (callers.py:279-287), over the candidate list only
+// ============================================================================================
+struct FilterArgs {
+    const Cand* cand;
+    unsigned int ncand;
+    const double* ptab;
+    const double* qtab;
+    const int* numbin;              // [npw*2]
+    const double* bal;
+    hp_survivor* out;
+    unsigned int* out_count;        // [0] survivors, [1] dropped
+    unsigned int out_cap;
+    unsigned long long* nreject;    // [npw*2]
+    double sig;
+    int pitch;
+};
+
+__global__ void k_filter(FilterArgs A) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= A.ncand) return;
+    const Cand c = A.cand[idx];
+    hp_survivor sv;
+    sv.r = c.r; sv.c = c.r + c.d; sv.pair = c.pair; sv.flags = c.flags;
+    sv.obs = (double)c.obs;
+    sv.e[0] = c.e_k; sv.e[1] = c.e_y;
+    bool any = false;
+#pragma unroll
+    for (int fl = 0; fl < 2; ++fl) {
+        const int lf = c.pair * 2 + fl;
+        const int ci = fl ? c.chunk_y : c.chunk_k;
+        double p = 1.0, q = 1.0;
+        if (ci >= 1 && ci <= A.numbin[lf]) {
+            const int w = c_chunks.hw[ci];
+            const int kb = c.obs < w - 1 ? c.obs : w - 1;
+            p = A.ptab[c_chunks.hoff[ci] + kb];
+            q = A.qtab[(size_t)lf * c_chunks.total_bins + c_chunks.hoff[ci] + kb];
+        }
+        sv.p[fl] = p; sv.q[fl] = q;
+        const bool valid = (c.flags & (fl ? HP_SF_VALID_Y : HP_SF_VALID_K)) != 0;
+        if (valid && q <= A.sig) {
+            sv.flags |= (fl ? HP_SF_REJECT_Y : HP_SF_REJECT_K);
+            atomicAdd(&A.nreject[lf], 1ull);
+            any = true;
+        }
+    }
+    if (any) {
+        sv.ice = A.bal[(size_t)c.d * A.pitch + c.r];
+        const unsigned g = atomicAdd(&A.out_count[0], 1u);
+        if (g < A.out_cap) A.out[g] = sv; else atomicAdd(&A.out_count[1], 1u);
+    }
+}
+
+__global__ void k_poisson_sf(const double* __restrict__ k, const double* __restrict__ mu, double* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = poisson_sf(k[i], mu[i]);
+}
+
+__global__ void k_fill_f64(double* __restrict__ p, double v, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace hp

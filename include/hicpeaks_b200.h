@@ -1,0 +1,166 @@
+/*
+ * hicpeaks_b200 -- C ABI of the B200-native HiCCUPS scoring engine.
+ *
+ * This is the drop-in boundary for the hot path of XiaoTaoWang/HiCPeaks.  The reference has no FFI
+ * (it is pure Python); the interface being replaced is the Python operator
+ *
+ *     hicpeaks.callers.hiccups(M, cM, B1, B2, IR, chromLen, Diags, cDiags, num, chrom, pw, ww, maxww,
+ *                              sig, sumq, double_fold, single_fold, maxapart, res, use_raw,
+ *                              min_marginal_peaks, onlyanchor, min_local_reads)
+ *                                                      -- /root/reference/hicpeaks/callers.py:44-46
+ *     hicpeaks.callers.bhfdr(...)                      -- callers.py:364-365
+ *     hicpeaks.apa.apa_submatrix / apa_analysis        -- /root/reference/hicpeaks/apa.py:11,30
+ *
+ * as called by the per-chromosome worker (/root/reference/scripts/pyHICCUPS:139-175).  Each entry
+ * point below cites the reference lines it replaces.  `hicpeaks_b200/callers.py` is the ctypes
+ * binding that re-exposes the same Python signatures on top of this ABI.
+ *
+ * Conventions: plain C, no exceptions.  Every function returns HP_OK (0) or a negative hp_status;
+ * hp_last_error(ctx) returns a message for the last failure on that context (ctx == NULL: the last
+ * context-less failure of the calling thread).  Host buffers are caller-owned and only read during
+ * the call; device memory is owned by the context.  A context is bound to one GPU and one CUDA
+ * stream; it is not thread-safe, distinct contexts are independent.  There is NO CPU fallback: a
+ * missing GPU / driver is an error.
+ */
+#ifndef HICPEAKS_B200_H
+#define HICPEAKS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HP_ABI_VERSION 1
+#define HP_MAX_PW 8        /* (pw, ww) pairs per run                                   */
+#define HP_MAX_WW 20       /* largest supported maxww (reference function default: 20) */
+#define HP_MAX_STEPS 160   /* sweep steps: sum over pairs of (maxww - ww + 1)          */
+
+typedef enum hp_status {
+    HP_OK = 0,
+    HP_ERR_INVALID = -1,        /* bad argument                                                     */
+    HP_ERR_CUDA = -2,           /* CUDA runtime / driver failure (message has the CUDA error)        */
+    HP_ERR_NO_DEVICE = -3,      /* no usable sm_100 GPU                                              */
+    HP_ERR_STATE = -4,          /* call sequence violated (e.g. score before upload)                 */
+    HP_ERR_EMPTY_REFIDX = -5,   /* the reference raises here: unresolved set of some p became empty
+                                   before the sweep ended, or no pixel at all (callers.py:205-208)    */
+    HP_ERR_CHUNK_OVERFLOW = -6, /* an expected value needs a lambda-chunk beyond max_chunks           */
+    HP_ERR_CAPACITY = -7        /* candidate / survivor buffer too small; retry with larger capacity  */
+} hp_status;
+
+typedef struct hp_ctx hp_ctx;
+
+/* ---- library / context --------------------------------------------------------------------- */
+int hp_abi_version(void);
+int hp_device_count(int* count);
+/* max_chunks: largest lambda-chunk index for which Poisson tables are kept (0 = default 52,
+ * i.e. expected values up to 2^17; at most 64).  edges: NULL, or max_chunks doubles with the upper
+ * edge rv_i of chunk i = 1..max_chunks exactly as the caller's numpy evaluates
+ * np.power(2, (i - 1) / 3.) (callers.py:36-37); NULL uses the C library's pow(). */
+int hp_ctx_create(int device, int max_chunks, const double* edges, hp_ctx** out);
+void hp_ctx_destroy(hp_ctx* ctx);
+const char* hp_last_error(const hp_ctx* ctx);
+
+/* ---- input: the diagonal band of one chromosome --------------------------------------------- */
+/* Replaces the containers the worker builds at scripts/pyHICCUPS:146-166 (Diags, M, cDiags, cM, IR,
+ * biases).  Diagonal-major, exactly the reference's lists: raw_diags[d] has n - d int32 counts
+ * (d in [0, num)); bal_diags[i] is balanced diagonal (bal_first + i) with n - bal_first - i doubles,
+ * NaN already replaced by 0 (pyHICCUPS:157); ir[i] = IR[bal_first + i]; b1/b2 = biases (length n). */
+typedef struct hp_band_desc {
+    int64_t n;                        /* chromLen in bins                                   */
+    int32_t num;                      /* stored raw diagonals, offsets 0 .. num-1           */
+    int32_t bal_first;                /* first balanced offset == min(ww)                   */
+    const int32_t* const* raw_diags;  /* [num]                                              */
+    const double* const* bal_diags;   /* [num - bal_first]                                  */
+    const double* ir;                 /* [num - bal_first]                                  */
+    const double* b1;                 /* [n]                                                */
+    const double* b2;                 /* [n]                                                */
+} hp_band_desc;
+int hp_band_upload(hp_ctx* ctx, const hp_band_desc* band);
+
+/* ---- HiCCUPS scoring: callers.py:98-287 ------------------------------------------------------ */
+typedef struct hp_hiccups_params {
+    int32_t npw;                 /* number of (pw, ww) pairs                                   */
+    int32_t pw[HP_MAX_PW];
+    int32_t ww[HP_MAX_PW];
+    int32_t maxww;
+    int32_t min_local_reads;     /* callers.py:206                                             */
+    int64_t maxapart_bins;       /* maxapart // res  (callers.py:102)                          */
+    double sig;                  /* callers.py:273,279                                         */
+    int32_t dump;                /* !=0: keep per-pixel bS/bE/E planes for hp_dump_plane (tests) */
+    int32_t reserved;
+} hp_hiccups_params;
+
+typedef struct hp_step_stat {    /* one executed sweep step, callers.py:203-232                 */
+    int32_t p, w;
+    int64_t resolved;            /* 'Valid Contact Number from This Loop'                       */
+    double valid_ratio, left_ratio;
+} hp_step_stat;
+
+typedef struct hp_lf_stat {      /* one (p, background) pair, callers.py:244-264                */
+    int64_t n_valid;             /* pixels with E > 0                                           */
+    double e_max;                /* E.max() (0 if n_valid == 0)                                 */
+    int32_t numbin;              /* lambdachunk(): number of chunks                             */
+    int32_t reserved;
+    int64_t n_reject;            /* pixels with q <= sig (before the gap filter)                */
+} hp_lf_stat;
+
+typedef struct hp_hiccups_summary {
+    int64_t n_pixels;            /* 'Observed Contact Number' (callers.py:114)                  */
+    int64_t band_pixels;         /* dense band pixels min(ww) <= d <= maxapart_bins (the metric) */
+    int32_t frozen_w;
+    int32_t n_steps;             /* executed steps                                              */
+    hp_step_stat steps[HP_MAX_STEPS];
+    hp_lf_stat lf[HP_MAX_PW][2]; /* [pair][0 = donut 'K', 1 = lower-left 'Y']                    */
+    int64_t n_candidates;
+    int64_t n_survivors;         /* records available to hp_get_survivors                       */
+    float ms_levels, ms_score, ms_fdr, ms_total; /* device time (CUDA events on the ctx stream) */
+    int32_t launches;            /* kernels launched by this call                               */
+    int32_t reserved;
+} hp_hiccups_summary;
+
+/* sweep (levels + adaptive width) + expected values + lambda-chunk histograms            */
+int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hiccups_summary* out);
+/* Poisson + BH per lambda-chunk, survivor selection.  numbin_override: NULL, or [npw*2] chunk
+ * counts to use instead of ceil(log(Emax)/log(2)*3+1) evaluated with the C library.        */
+int hp_hiccups_fdr(hp_ctx* ctx, const int32_t* numbin_override, hp_hiccups_summary* out);
+/* both of the above */
+int hp_hiccups(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hiccups_summary* out);
+
+typedef struct hp_survivor {     /* a pixel with q <= sig for K or Y of one pair                */
+    int32_t r, c;                /* bin coordinates (x, y), c > r                               */
+    int32_t pair;                /* index into pw/ww                                            */
+    uint32_t flags;              /* HP_SF_*                                                     */
+    double obs;                  /* raw count O                                                 */
+    double ice;                  /* balanced value cM[r, c]                                     */
+    double e[2];                 /* expected E for K, Y (0 if not valid)                        */
+    double p[2];                 /* Poisson p                                                   */
+    double q[2];                 /* BH q                                                        */
+} hp_survivor;
+#define HP_SF_VALID_K 1u         /* E_K > 0                                                     */
+#define HP_SF_VALID_Y 2u
+#define HP_SF_REJECT_K 4u        /* q_K <= sig                                                  */
+#define HP_SF_REJECT_Y 8u
+#define HP_SF_CEMY_NONZERO 16u   /* reference's cEM[ci,cj] != 0 for the Y background (callers.py:330) */
+int hp_get_survivors(hp_ctx* ctx, hp_survivor* buf, int64_t capacity, int64_t* count);
+
+/* rows of cM whose stored band is all zero ('gaps', callers.py:238): out[r] = 1 if row r is a gap */
+int hp_get_gaps(hp_ctx* ctx, uint8_t* out, int64_t n);
+
+/* ---- inspection (parity tests) --------------------------------------------------------------- */
+/* per-pixel first sweep step at which Reads >= min_local_reads; 0xFE never, 0xFF not a pixel.
+ * out is [num][n] row = diagonal. */
+int hp_dump_levels(hp_ctx* ctx, uint8_t* out, int64_t capacity);
+/* planes kept when params.dump != 0: what = 0 bS, 1 bE, 2 E ; out is [num][n] doubles, NaN = unset */
+int hp_dump_plane(hp_ctx* ctx, int32_t pair, int32_t background, int32_t what, double* out, int64_t capacity);
+/* lambda-chunk tables of one (pair, background): hist/p/q for chunk i in [1, numbin], bin k in
+ * [0, width_i).  Call with NULL arrays to query sizes: widths[i-1] filled for i <= *numbin.     */
+int hp_get_chunk_table(hp_ctx* ctx, int32_t pair, int32_t background, int32_t* numbin, int32_t* widths,
+                       int64_t* hist, double* p, double* q, int64_t capacity);
+/* device Poisson tail exactly as used for the tables: out[i] = 1 - pdtr(k[i], mu[i])           */
+int hp_poisson_sf(hp_ctx* ctx, const double* k, const double* mu, double* out, int64_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HICPEAKS_B200_H */

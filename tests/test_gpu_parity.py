@@ -1,0 +1,48 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle on seeded synthetic inputs."""
+import numpy as np
+import pytest
+
+from hicpeaks_b200 import _capi
+from hicpeaks_b200.synth import synth_chromosome
+
+from helpers import compare_with_oracle
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # n, band, pw, ww, maxww, scale, decay, thr, seed
+    (600, 60, [2], [5], 8, 300.0, 1.08, 16, 1),          # dense: freezes at the first level
+    (500, 60, [2], [5], 10, 40.0, 1.08, 16, 1),          # two levels
+    (500, 80, [1, 2, 4], [3, 5, 7], 10, 40.0, 1.08, 16, 1),   # union mode, re-added rings
+    (400, 80, [1, 2], [3, 5], 8, 100.0, 1.3, 25, 1),     # union, deeper levels
+    (700, 90, [1], [3], 10, 20.0, 1.0, 16, 3),           # (1,3), many levels
+    (300, 40, [4], [7], 12, 60.0, 1.2, 30, 4),           # (4,7)
+    (129, 30, [2], [5], 7, 80.0, 1.1, 16, 5),            # ragged: n just above one tile
+    (1000, 200, [2], [5], 10, 300.0, 1.08, 16, 7),       # several tiles in both directions
+]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = _capi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "n%d_b%d_%s" % (c[0], c[1], "-".join(map(str, c[2]))))
+def test_cutpoints_match_oracle(ctx, case):
+    n, band, pw, ww, maxww, scale, decay, thr, seed = case
+    inp = synth_chromosome(n, band, min(ww), maxww=maxww, seed=seed, scale=scale, decay=decay)
+    st = compare_with_oracle(ctx, inp, pw, ww, maxww, 0.1, band, thr)
+    print(case, st)
+    assert st["n_pixels"] > 0
+
+
+def test_poisson_tail_matches_scipy(ctx):
+    from scipy.special import pdtr
+    rng = np.random.default_rng(0)
+    mu = np.exp(rng.uniform(np.log(1e-3), np.log(5e4), 100000))
+    k = np.floor(np.maximum(0, mu + rng.normal(0, 1, mu.size) * np.sqrt(mu) * 4 + rng.uniform(0, 3, mu.size)))
+    got = ctx.poisson_sf(k, mu)
+    ref = 1 - pdtr(k, mu)
+    assert np.abs(got - ref).max() < 2e-14
