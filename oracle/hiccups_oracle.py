@@ -191,6 +191,7 @@ def expected_and_fdr(inp, sw, p, w0, fl, sig):
         keep0 = (cem != 0) & (ratio != 0)          # lil assignment of a 0 ratio stores nothing
         E = cem * B[x] * B[y]
         keep = keep0 & (E > 0)
+    cem_nz = (x[keep0], y[keep0])                  # where the reference's cEM matrix has a non-zero entry
     x, y, d, E, cem = x[keep], y[keep], d[keep], E[keep], cem[keep]
     O = sw["raw"][d, x].astype(np.float64)
     ice = sw["bal"][d, x]
@@ -209,7 +210,7 @@ def expected_and_fdr(inp, sw, p, w0, fl, sig):
                 qv[idx] = bh_fdr(cp)
                 chunk[idx] = i
     return dict(x=x, y=y, E=E, O=O, ice=ice, fold=fold, p=pv, q=qv, chunk=chunk, numbin=numbin,
-                reject=qv <= sig, cem_zero_mask=None)
+                reject=qv <= sig, cem_nz=cem_nz)
 
 
 def score(inp, pw, ww, maxww=20, sig=0.1, maxapart_bins=200, min_local_reads=25):
