@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Headline benchmark: diagonal-band pixels scored per second (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (`config.workload`): BASELINE.json configs[1] -- synthetic chromosome of 20 000 bins @10 kb,
+5 Mb band (num = 511 stored diagonals), (p, w) = (2, 5), maxww 10, min_local_reads 16, sig 0.1,
+generator of SURVEY.md 8(d).  One step = one pass of the whole hot path (level kernel, frozen_w
+replay, score kernel, BH kernel, survivor filter) over a batch of `--chroms` such chromosomes that
+are resident in HBM (batch > L2, so every step streams from HBM).  For N > 1 (torchrun, one rank
+per GPU) every rank owns its own batch (weak scaling, chromosomes are independent: no collective
+on the data path); value = all pixels / max-over-ranks time.
+
+`value`  : inputs resident in HBM, whole-job.        `e2e` : same steps with HOST buffers -- pack +
+H2D upload + kernels + survivor/gap D2H inside the timed region, through the C-ABI calls the
+reference-facing operator (hicpeaks_b200.callers.hiccups) makes.
+`--impl reference`: the CPU restatement of the reference path (oracle/, kind "port") on all host
+cores, bounded sample, same metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(n=20000, band=500, pw=[2], ww=[5], maxww=10, min_local_reads=16, sig=0.1)
+ALG_BYTES_PER_PIXEL = 12        # int32 raw count + fp64 balanced value, each read once
+METRIC = "diagonal-band pixels scored/sec"
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batch(rank, nchrom):
+    from hicpeaks_b200.synth import synth_chromosome
+    W = WORKLOAD
+    return [synth_chromosome(W["n"], W["band"], min(W["ww"]), maxww=W["maxww"], seed=1000 * rank + 17 + i)
+            for i in range(nchrom)]
+
+
+def engine_arrays(inp):
+    Diags = [np.ascontiguousarray(d, dtype=np.int32) for d in inp["Diags"]]
+    cDiags = [np.ascontiguousarray(c, dtype=np.float64) for c in inp["cDiags"]]
+    ir = np.array([inp["IR"][d] for d in range(inp["min_ww"], inp["num"])], dtype=np.float64)
+    return Diags, cDiags, ir
+
+
+def oracle_rate(n_sample, seed):
+    """One chromosome sample through the CPU restatement; returns (pixels, seconds)."""
+    from hicpeaks_b200.synth import band_pixels, synth_chromosome
+    from oracle import glue_oracle, hiccups_oracle as ho
+    W = WORKLOAD
+    inp = synth_chromosome(n_sample, W["band"], min(W["ww"]), maxww=W["maxww"], seed=seed)
+    t = time.perf_counter()
+    sw, out = ho.score(inp, W["pw"], W["ww"], maxww=W["maxww"], sig=W["sig"], maxapart_bins=W["band"],
+                       min_local_reads=W["min_local_reads"])
+    glue_oracle.finish_hiccups(inp, sw, out, W["pw"], W["ww"], 10000, 0.01, 1.75, 2, False, 2, False)
+    return band_pixels(n_sample, min(W["ww"]), W["band"]), time.perf_counter() - t
+
+
+def _oracle_worker(a):
+    return oracle_rate(*a)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n_sample = 3000
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(cores) as pool:
+        for step in range(args.warmup + args.steps):
+            t = time.perf_counter()
+            res = pool.map(_oracle_worker, [(n_sample, 100 * step + i) for i in range(cores)])
+            dt = time.perf_counter() - t
+            if step >= args.warmup:
+                times.append((sum(r[0] for r in res), dt))
+    px = sum(t[0] for t in times)
+    sec = sum(t[1] for t in times)
+    val = px / sec
+    sample = "%d chromosomes of %d bins (band %d, cfg2 generator) per step, one per host core" % (cores, n_sample, WORKLOAD["band"])
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "pixels/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2: synthetic 20000-bin chromosome @10kb, 5 Mb band, p=2 w=5 (bounded sample)",
+                   "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "pixels/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chroms", type=int, default=4, help="chromosomes per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from hicpeaks_b200 import _capi
+    W = WORKLOAD
+    batch = make_batch(rank, args.chroms)
+    arrays = [engine_arrays(inp) for inp in batch]
+    ctxs = [_capi.Context(local) for _ in batch]
+    P = _capi.Context.make_params(W["pw"], W["ww"], W["maxww"], W["sig"], W["band"], W["min_local_reads"])
+    h2d = 0
+    for ctx, inp, (Dg, cD, ir) in zip(ctxs, batch, arrays):
+        ctx.upload(inp["n"], inp["num"], inp["min_ww"], Dg, cD, ir, inp["biases"], inp["biases"])
+        h2d += sum(a.nbytes for a in Dg) + sum(a.nbytes for a in cD) + ir.nbytes + 2 * inp["biases"].nbytes
+
+    def barrier():
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def resident_step():
+        acc = dict(px=0, launches=0, ms_levels=0.0, ms_score=0.0, ms_fdr=0.0, surv=0)
+        for ctx in ctxs:
+            S = ctx.hiccups(P)          # returns after the stream is synchronised
+            acc["px"] += S.band_pixels; acc["launches"] += S.launches; acc["surv"] += S.n_survivors
+            acc["ms_levels"] += S.ms_levels; acc["ms_score"] += S.ms_score; acc["ms_fdr"] += S.ms_fdr
+        return acc
+
+    def e2e_step():
+        px = d2h = 0
+        for ctx, inp, (Dg, cD, ir) in zip(ctxs, batch, arrays):
+            ctx.upload(inp["n"], inp["num"], inp["min_ww"], Dg, cD, ir, inp["biases"], inp["biases"])
+            S = ctx.hiccups(P)
+            sv = ctx.survivors()
+            g = ctx.gaps()
+            px += S.band_pixels
+            d2h += sv.nbytes + g.size * 4
+        return px, d2h
+
+    for _ in range(args.warmup):
+        resident_step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    accs = [resident_step() for _ in range(args.steps)]
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_res = [e2e_step() for _ in range(args.steps)]
+    barrier()
+    dt_e2e = time.perf_counter() - t0
+
+    px_step = accs[0]["px"]
+    if dist is not None:
+        import torch
+        t = torch.tensor([dt, dt_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, dt_e2e = t.tolist()
+        c = torch.tensor([px_step], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        px_total = c.item()
+    else:
+        px_total = px_step
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    value = px_total * args.steps / dt
+    e2e_value = px_total * args.steps / dt_e2e
+    peak, peak_src = read_peaks()
+    ms_score = float(np.mean([a["ms_score"] for a in accs])) / len(ctxs)      # per launch of k_score
+    px_launch = px_step / len(ctxs)
+    achieved = ALG_BYTES_PER_PIXEL * px_launch / (ms_score * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "k_score_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    out = {
+        "metric": METRIC, "value": value, "unit": "pixels/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2: synthetic 20000-bin chromosome @10kb, 5 Mb band (num=511), p=2 w=5, maxww 10",
+                   "chromosomes_per_gpu_per_step": len(ctxs), "pixels_per_step": px_total,
+                   "l2": "batch of %d chromosomes = %.0f MB resident input per GPU > 126 MB L2" % (len(ctxs), h2d / 1e6),
+                   "timing": "host clock between device-synchronised points (every C-ABI call ends with a stream sync); "
+                             "kernel times from CUDA events on the engine stream",
+                   "parallelism": "chromosome-sharded, no collective"},
+        "kernel_ms_per_step": {k: float(np.mean([a[k] for a in accs])) for k in ("ms_levels", "ms_score", "ms_fdr")},
+        "roofline": {"bound": "hbm", "kernel": "k_score", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "alg_bytes_per_pixel": ALG_BYTES_PER_PIXEL, "pixels_per_launch": px_launch,
+                     "avg_launch_ms": ms_score},
+        "e2e": {"value": e2e_value, "unit": "pixels/s", "h2d_bytes_per_step": h2d * world,
+                "d2h_bytes_per_step": int(np.mean([r[1] for r in e2e_res])) * world,
+                "ms_per_step": 1e3 * dt_e2e / args.steps},
+        "gpu_launches": int(sum(a["launches"] for a in accs)),
+        "clocks": clocks,
+        "survivors_per_step": accs[0]["surv"],
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        n_sample = 6000
+        px, sec = oracle_rate(n_sample, 4242)
+        out["cpu_baseline"] = {"value": px / sec, "unit": "pixels/s", "cores": 1, "kind": "port",
+                               "sample": "one %d-bin chromosome of the same generator/band/parameters (%.1f s)" % (n_sample, sec)}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

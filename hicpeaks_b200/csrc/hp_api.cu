@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -15,6 +16,9 @@
 using namespace hp;
 
 static thread_local std::string g_err;
+// the sweep program and chunk tables live in __constant__ memory (one copy per device): calls that
+// upload and use them are serialised per device
+static std::mutex g_dev_mutex[64];
 
 struct hp_ctx {
     int device = 0;
@@ -148,6 +152,7 @@ extern "C" int hp_ctx_create(int device, int max_chunks, const double* edges, hp
     if (!ok) return bail(fail(nullptr, HP_ERR_CUDA, "device allocation failed"));
     // Poisson table (universal): p[i][k] = 1 - pdtr(k, rv_i)
     for (int i = 1; i <= max_chunks; ++i) ctx->chunks.kcand[i] = 0;
+    std::lock_guard<std::mutex> lock(g_dev_mutex[device & 63]);
     if (cudaMemcpyToSymbolAsync(c_chunks, &ctx->chunks, sizeof(Chunks), 0, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
         return bail(fail(nullptr, HP_ERR_CUDA, "constant upload failed"));
     k_ptab<<<(unsigned)((tb + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_ptab);
@@ -334,6 +339,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     if (minww != ctx->bal_first) return fail(ctx, HP_ERR_INVALID, "band was uploaded with bal_first != min(ww)");
     if (!(P.sig >= 0.0)) return fail(ctx, HP_ERR_INVALID, "sig must be >= 0");
     CK(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lock(g_dev_mutex[ctx->device & 63]);
     ctx->scored = false; ctx->fdr_done = false;
     ctx->prm = P;
     int rc = build_program(ctx, P);
@@ -535,6 +541,8 @@ extern "C" int hp_hiccups_fdr(hp_ctx* ctx, const int32_t* numbin_override, hp_hi
             nb[i * 2 + fl] = v;
             maxnb = std::max(maxnb, v);
         }
+    std::lock_guard<std::mutex> lock(g_dev_mutex[ctx->device & 63]);
+    CK(cudaMemcpyToSymbolAsync(c_chunks, &ctx->chunks, sizeof(Chunks), 0, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(ctx->ev[4], st));
     CK(cudaMemcpyAsync(ctx->d_numbin, nb, sizeof(nb), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctx->d_small + 32, 0, 16 * sizeof(unsigned long long), st));
