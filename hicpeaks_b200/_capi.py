@@ -24,6 +24,7 @@ HP_ERR_EMPTY_REFIDX = -5
 HP_ERR_CHUNK_OVERFLOW = -6
 HP_ERR_CAPACITY = -7
 
+PF_GENERIC_KERNEL = 1
 SF_VALID_K, SF_VALID_Y, SF_REJECT_K, SF_REJECT_Y, SF_CEMY_NONZERO = 1, 2, 4, 8, 16
 
 LIB_NAME = "libhicpeaks_b200.so"
@@ -46,7 +47,7 @@ class BandDesc(C.Structure):
 class HiccupsParams(C.Structure):
     _fields_ = [("npw", C.c_int32), ("pw", C.c_int32 * HP_MAX_PW), ("ww", C.c_int32 * HP_MAX_PW),
                 ("maxww", C.c_int32), ("min_local_reads", C.c_int32), ("maxapart_bins", C.c_int64),
-                ("sig", C.c_double), ("dump", C.c_int32), ("reserved", C.c_int32)]
+                ("sig", C.c_double), ("dump", C.c_int32), ("flags", C.c_int32)]
 
 
 class StepStat(C.Structure):
@@ -64,7 +65,7 @@ class HiccupsSummary(C.Structure):
                 ("n_steps", C.c_int32), ("steps", StepStat * HP_MAX_STEPS),
                 ("lf", (LfStat * 2) * HP_MAX_PW), ("n_candidates", C.c_int64), ("n_survivors", C.c_int64),
                 ("ms_levels", C.c_float), ("ms_score", C.c_float), ("ms_fdr", C.c_float), ("ms_total", C.c_float),
-                ("launches", C.c_int32), ("reserved", C.c_int32)]
+                ("launches", C.c_int32), ("spec_kernel", C.c_int32)]
 
 
 SURVIVOR_DTYPE = np.dtype([("r", "<i4"), ("c", "<i4"), ("pair", "<i4"), ("flags", "<u4"), ("obs", "<f8"),
@@ -194,7 +195,7 @@ class Context:
 
     # -- scoring -------------------------------------------------------------------------------
     @staticmethod
-    def make_params(pw, ww, maxww, sig, maxapart_bins, min_local_reads, dump=False):
+    def make_params(pw, ww, maxww, sig, maxapart_bins, min_local_reads, dump=False, generic_kernel=False):
         if len(pw) != len(ww) or not 1 <= len(pw) <= HP_MAX_PW:
             raise ValueError("need 1..%d (pw, ww) pairs" % HP_MAX_PW)
         P = HiccupsParams()
@@ -203,6 +204,7 @@ class Context:
             P.pw[i], P.ww[i] = int(p), int(w)
         P.maxww, P.min_local_reads = int(maxww), int(min_local_reads)
         P.maxapart_bins, P.sig, P.dump = int(maxapart_bins), float(sig), int(bool(dump))
+        P.flags = PF_GENERIC_KERNEL if generic_kernel else 0
         return P
 
     def score(self, P):

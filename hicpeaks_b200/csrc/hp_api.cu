@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "hp_kernels.cuh"
+#include "hp_score_spec.cuh"
 
 using namespace hp;
 
@@ -39,6 +40,7 @@ struct hp_ctx {
     unsigned char* d_lvl = nullptr;
     double *d_ir = nullptr, *d_b1 = nullptr, *d_b2 = nullptr;
     unsigned int* d_rownz = nullptr;
+    double* d_tmp = nullptr;          // plain-layout landing zone of the balanced upload
     void* h_stage = nullptr;          // pinned staging for uploads
     size_t cap_stage = 0;
     bool have_band = false;
@@ -62,6 +64,7 @@ struct hp_ctx {
     double* d_dump = nullptr; size_t cap_dump = 0;
     int numbin[HP_MAX_PW * 2] = {};
     unsigned int ncand = 0, nsurv = 0;
+    bool spec_used = false;
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
 };
 
@@ -173,7 +176,7 @@ extern "C" void hp_ctx_destroy(hp_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_ptab, ctx->d_raw, ctx->d_bal, ctx->d_lvl, ctx->d_ir, ctx->d_b1, ctx->d_b2, ctx->d_rownz,
                     ctx->d_lhist, ctx->d_betab, ctx->d_hist, ctx->d_qtab, ctx->d_small, ctx->d_cnt, ctx->d_numbin,
-                    ctx->d_cand, ctx->d_surv, ctx->d_dump};
+                    ctx->d_cand, ctx->d_surv, ctx->d_dump, ctx->d_tmp};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -194,10 +197,11 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
     const int pitch = (int)((n + 31) / 32 * 32);
     const size_t plane = (size_t)num * pitch;
     if (plane > ctx->cap_plane) {
-        for (void* p : {(void*)ctx->d_raw, (void*)ctx->d_bal, (void*)ctx->d_lvl}) if (p) cudaFree(p);
-        ctx->d_raw = nullptr; ctx->d_bal = nullptr; ctx->d_lvl = nullptr; ctx->cap_plane = 0;
+        for (void* p : {(void*)ctx->d_raw, (void*)ctx->d_bal, (void*)ctx->d_lvl, (void*)ctx->d_tmp}) if (p) cudaFree(p);
+        ctx->d_raw = nullptr; ctx->d_bal = nullptr; ctx->d_lvl = nullptr; ctx->d_tmp = nullptr; ctx->cap_plane = 0;
         CK(cudaMalloc(&ctx->d_raw, plane * sizeof(int)));
         CK(cudaMalloc(&ctx->d_bal, plane * sizeof(double)));
+        CK(cudaMalloc(&ctx->d_tmp, plane * sizeof(double)));
         CK(cudaMalloc(&ctx->d_lvl, plane));
         ctx->cap_plane = plane;
     }
@@ -251,7 +255,10 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
         for (auto& t : th) t.join();
     }
     for (int d = 0; d < num; ++d) hir[d] = d >= bf ? b->ir[d - bf] : 0.0;
-    CK(cudaMemcpyAsync(ctx->d_bal, hbal, plane * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_tmp, hbal, plane * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_rownz, 0, (size_t)n * sizeof(unsigned int), ctx->stream));
+    k_relayout<<<dim3((pitch + 255) / 256, num), 256, 0, ctx->stream>>>(ctx->d_tmp, ctx->d_bal, ctx->d_rownz, pitch, num);
+    CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->d_raw, hraw, plane * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_ir, hir, (size_t)num * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_b1, b->b1, n * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -315,6 +322,46 @@ static int make_map(hp_ctx* ctx, CUtensorMap* map, CUtensorMapDataType dt, int e
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, HP_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
     return HP_OK;
+}
+
+// quad-interleaved balanced plane: dims (row quad, row & 3, diagonal)
+static int make_map_bal(hp_ctx* ctx, CUtensorMap* map, int box_q, int box_d) {
+    cuuint64_t dims[3] = {(cuuint64_t)ctx->pitch / 4, 4, (cuuint64_t)ctx->num};
+    cuuint64_t strides[2] = {(cuuint64_t)ctx->pitch / 4 * 8, (cuuint64_t)ctx->pitch * 8};
+    cuuint32_t box[3] = {(cuuint32_t)box_q, 4, (cuuint32_t)box_d};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, ctx->d_bal, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, HP_ERR_CUDA, "cuTensorMapEncodeTiled (balanced plane) failed: " + std::to_string((int)r));
+    return HP_OK;
+}
+
+// ---- specialised score kernels: sweep programs compiled in (hp_score_spec.cuh) --------------------
+struct SpecKernel {
+    bool (*matches)(const Prog&, int, const signed char*, const signed char*, const unsigned char*);
+    int (*launch)(hp_ctx*, const CUtensorMap&, const ScoreArgs&, dim3, size_t, cudaStream_t);
+    const char* name;
+};
+template <class PG>
+static int launch_spec(hp_ctx* ctx, const CUtensorMap& tm, const ScoreArgs& A, dim3 grid, size_t smem, cudaStream_t st) {
+    CK(cudaFuncSetAttribute(k_score_spec<PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_score_spec<PG><<<grid, kThreads, smem, st>>>(tm, A);
+    return HP_OK;
+}
+#define HP_SPEC(name, ...) {spec_matches<SProg<__VA_ARGS__>>, launch_spec<SProg<__VA_ARGS__>>, name}
+static const SpecKernel g_specs[] = {
+    HP_SPEC("p2w5", 10, 1, 2, 5),
+#ifndef HP_FAST_BUILD       // development builds compile one program only (each takes about a minute)
+    HP_SPEC("p1w3", 10, 1, 1, 3),
+    HP_SPEC("p4w7", 10, 1, 4, 7),
+    HP_SPEC("p124w357", 10, 3, 1, 3, 2, 5, 4, 7),
+#endif
+};
+static const SpecKernel* find_spec(hp_ctx* ctx, int nexec) {
+    for (const SpecKernel& k : g_specs)
+        if (k.matches(ctx->prog, nexec, ctx->opa.data(), ctx->opb.data(), ctx->opy.data())) return &k;
+    return nullptr;
 }
 
 static int64_t band_pixel_count(int64_t n, int64_t lo, int64_t hi) {
@@ -424,21 +471,45 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
             for (int s = sv; s < nexec; ++s) if (G.step_pi[s] == pi) { r = (unsigned char)s; break; }
             G.next_step[pi][sv] = r;
         }
+    for (int s = 0; s < nexec; ++s) {
+        int prev = -1;
+        for (int t = 0; t < s; ++t) if (G.step_pi[t] == G.step_pi[s]) prev = t;
+        G.step_lo[s] = (unsigned char)(prev + 1);
+    }
+    G.dspan = maxw0 - minww;
+    for (int k = 0; k <= G.dspan; ++k)
+        for (int sv = 0; sv <= G.nsteps + 1; ++sv) {
+            int last = -1;
+            for (int pi = 0; pi < P.npw; ++pi)
+                if (minww + k >= P.ww[pi] && G.next_step[pi][sv] != kNoStep) last = std::max(last, (int)G.next_step[pi][sv]);
+            G.last_need[k][sv] = last < 0 ? kNoStep : (unsigned char)last;
+        }
 
     // ---- tables for K2 ------------------------------------------------------------------------
-    const int F = frozen, HR = (F + 1) & ~1;   // TMA box start (r0 - HR) must stay 16-byte aligned
-    int TD = 32;
+    const int F = frozen;
     const int sh_pairs = std::min(P.npw, kShPairs);
-    auto smem_for = [&](int td) {
-        return (size_t)(kTR + 2 * HR) * (td + 4 * F) * 8 + 224 + kStage * sizeof(Cand) + (size_t)sh_pairs * 2 * kShI * kShK * 4;
-    };
-    while (TD > 8 && smem_for(TD) > 110 * 1024) TD /= 2;     // keep two CTAs per SM where possible
-    const int BR = kTR + 2 * HR, BD = TD + 4 * F;
-    if (smem_for(TD) > 227 * 1024) return fail(ctx, HP_ERR_INVALID, "tile does not fit shared memory");
+    const SpecKernel* spec = (P.flags & HP_PF_GENERIC_KERNEL) ? nullptr : (num <= 32767 ? find_spec(ctx, nexec) : nullptr);   // reserved bit 0: force the generic kernel
+    ScoreArgs A{};
+    size_t smem = 0;
+    dim3 grid;
+    if (spec) {
+        // 4x4 register-block kernel: one CTA per SM (all 8 warps share one big tile), TD diagonals per CTA
+        A.HR = kHR; A.NQ = kNQ;
+        int TD = 64;
+        while (TD > 8 && score_smem_bytes(TD + 3 + 4 * F, kNQ, sh_pairs, true) > 200 * 1024) TD /= 2;
+        A.TD = TD; A.BD = TD + 3 + 4 * F;
+        smem = score_smem_bytes(A.BD, kNQ, sh_pairs, true);
+        grid = dim3((n + kTR - 1) / kTR, (dhi - dlo + 3 + TD) / TD);
+    } else {
+        A.HR = (F + 7) & ~7; A.NQ = (kTR + 2 * A.HR) / 4;
+        int TD = 32;
+        while (TD > 8 && score_smem_bytes(TD + 4 * F, A.NQ, sh_pairs, false) > 110 * 1024) TD /= 2;   // two CTAs per SM where possible
+        A.TD = TD; A.BD = TD + 4 * F;
+        smem = score_smem_bytes(A.BD, A.NQ, sh_pairs, false);
+        grid = dim3((n + kTR - 1) / kTR, (dhi - dlo + TD) / TD);
+    }
+    if (smem > 227 * 1024) return fail(ctx, HP_ERR_INVALID, "tile does not fit shared memory");
     {
-        std::vector<int> off2(nops);
-        for (int i = 0; i < nops; ++i) off2[i] = (((ctx->opb[i] - ctx->opa[i]) * BR + ctx->opa[i]) << 1) | (ctx->opy[i] ? 1 : 0);
-        CK(cudaMemcpyToSymbolAsync(c_off2, off2.data(), nops * sizeof(int), 0, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyToSymbolAsync(c_prog, &G, sizeof(Prog), 0, cudaMemcpyHostToDevice, st));
         // candidate thresholds for this sig (host copy of the universal Poisson table)
         Chunks& C = ctx->chunks;
@@ -450,7 +521,6 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
             C.kcand[i] = k;
         }
         CK(cudaMemcpyToSymbolAsync(c_chunks, &C, sizeof(Chunks), 0, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));   // host vectors above go out of scope
     }
     const size_t tb = ctx->chunks.total_bins;
     CK(ensure(&ctx->d_betab, &ctx->cap_betab, (size_t)2 * nexec * num));
@@ -465,7 +535,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     size_t want = std::min<size_t>((size_t)total * P.npw, (size_t)((double)total * P.npw * std::max(0.15, 1.5 * P.sig)) + 65536);
     want = std::max<size_t>(want, 65536);
     CUtensorMap tm_bal;
-    rc = make_map(ctx, &tm_bal, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, ctx->d_bal, BR, BD);
+    rc = make_map_bal(ctx, &tm_bal, A.NQ, A.BD);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev[2], st));
     k_betab<<<dim3((num + 127) / 128, nexec), 128, 0, st>>>(ctx->d_ir, ctx->d_betab, num, ctx->bal_first, nexec);
@@ -477,19 +547,20 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
         CK(cudaMemsetAsync(ctx->d_hist, 0, (size_t)P.npw * 2 * tb * sizeof(unsigned int), st));
         CK(cudaMemsetAsync(ctx->d_small, 0, 48 * sizeof(unsigned long long), st));
         CK(cudaMemsetAsync(ctx->d_cnt, 0, 8 * sizeof(unsigned int), st));
-        CK(cudaMemsetAsync(ctx->d_rownz, 0, (size_t)n * sizeof(unsigned int), st));
-        ScoreArgs A{};
         A.raw = ctx->d_raw; A.lvl = ctx->d_lvl; A.ir = ctx->d_ir; A.b1 = ctx->d_b1; A.b2 = ctx->d_b2;
         A.betab = ctx->d_betab; A.hist = ctx->d_hist; A.emax_bits = ctx->d_small; A.nvalid = ctx->d_small + 16;
-        A.rownz = ctx->d_rownz; A.cand = ctx->d_cand; A.cand_count = ctx->d_cnt;
+        A.cand = ctx->d_cand; A.cand_count = ctx->d_cnt;
         A.cand_cap = (unsigned)std::min<size_t>(ctx->cap_cand, 0xffffffffu);
         A.dump = P.dump ? ctx->d_dump : nullptr; A.plane = (long long)ctx->plane;
-        A.n = n; A.num = num; A.pitch = pitch; A.dlo = dlo; A.dhi = dhi; A.F = F; A.HR = HR; A.BR = BR; A.BD = BD; A.TD = TD;
+        A.n = n; A.num = num; A.pitch = pitch; A.dlo = dlo; A.dhi = dhi; A.F = F;
         A.bal_first = ctx->bal_first; A.sh_pairs = sh_pairs;
-        const size_t smem = smem_for(TD);
-        CK(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((n + kTR - 1) / kTR, (dhi - dlo + TD) / TD);
-        k_score<<<grid, kThreads, smem, st>>>(tm_bal, A);
+        if (spec) {
+            rc = spec->launch(ctx, tm_bal, A, grid, smem, st);
+            if (rc) return rc;
+        } else {
+            CK(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_score<<<grid, kThreads, smem, st>>>(tm_bal, A);
+        }
         ++launches;
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[3], st));
@@ -500,6 +571,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
         if (attempt == 1) return fail(ctx, HP_ERR_CAPACITY, "candidate buffer overflow");
         want = (size_t)total * P.npw + 1024;      // every pixel can be a candidate at most once per pair
     }
+    ctx->spec_used = spec != nullptr;
     if (cnt[2]) return fail(ctx, HP_ERR_CHUNK_OVERFLOW,
                             std::to_string(cnt[2]) + " expected values exceed the last lambda-chunk edge " +
                                 std::to_string(ctx->chunks.rv[ctx->chunks.maxchunk]) + "; create the context with a larger max_chunks");
@@ -519,6 +591,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); S.ms_score = ms;
     S.ms_total = S.ms_levels + S.ms_score;
     S.launches = launches;
+    S.spec_kernel = ctx->spec_used ? 1 : 0;
     ctx->scored = true;
     if (out) *out = S;
     return HP_OK;
@@ -613,7 +686,7 @@ extern "C" int hp_get_survivors(hp_ctx* ctx, hp_survivor* buf, int64_t capacity,
 
 extern "C" int hp_get_gaps(hp_ctx* ctx, uint8_t* out, int64_t n) {
     if (!ctx || !out) return fail(ctx, HP_ERR_INVALID, "NULL argument");
-    if (!ctx->scored) return fail(ctx, HP_ERR_STATE, "hp_hiccups_score must come first");
+    if (!ctx->have_band) return fail(ctx, HP_ERR_STATE, "hp_band_upload must come first");
     if (n < ctx->n) return fail(ctx, HP_ERR_CAPACITY, "gap buffer too small");
     CK(cudaSetDevice(ctx->device));
     std::vector<unsigned int> nz(ctx->n);

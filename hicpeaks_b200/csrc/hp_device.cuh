@@ -9,8 +9,11 @@
 
 namespace hp {
 
-constexpr int kTR = 128;          // tile rows (matrix row index r), one lane per r
+constexpr int kTR = 128;          // tile rows (matrix row index r)
 constexpr int kThreads = 256;
+constexpr int kHR = 16;           // row halo of a balanced tile: >= maxww of the specialised kernels and a multiple of 8
+                                  // (a TMA box must start on a 16-byte boundary: an even row quad)
+constexpr int kNQ = (kTR + 2 * kHR) / 4;   // row quads of a balanced tile (40)
 constexpr int kMaxOps = 6144;     // stencil offsets of one whole sweep program
 constexpr int kMaxROps = 512;     // offsets that feed Reads (<= maxww^2)
 constexpr int kMaxChunk = 64;     // lambda-chunk cap
@@ -27,6 +30,10 @@ struct Prog {                     // the sweep program (callers.py:132-198 unrol
     int op_end[HP_MAX_STEPS];     // ops [op_end[s-1], op_end[s]) belong to step s
     int rop_end[HP_MAX_STEPS];
     unsigned char next_step[HP_MAX_PW][HP_MAX_STEPS + 2];  // [pair][s*] -> executed step resolving it
+    // [min(d - min(ww), dspan)][s*] -> last executed step a pixel on diagonal d with level s* needs (kNoStep: none)
+    unsigned char last_need[HP_MAX_WW + 1][HP_MAX_STEPS + 2];
+    int dspan;                    // max(ww) - min(ww)
+    unsigned char step_lo[HP_MAX_STEPS];   // executed step s resolves its pair for levels in [step_lo[s], s]
 };
 
 struct Chunks {                   // lambda-chunk geometry (callers.py:30-38) + table layout
@@ -42,6 +49,13 @@ struct Cand {                     // 32 B: a pixel whose Poisson p can pass sig 
     unsigned char pair, flags, chunk_k, chunk_y;
     double e_k, e_y;
 };
+
+// Balanced plane in HBM: "quad-interleaved" diagonal planes.  Element (r, r + d) lives at
+// [d][r & 3][r >> 2] (sub-plane pitch = pitch / 4): a thread that owns four consecutive matrix rows
+// then reads consecutive shared-memory words across the lanes of a warp for every row offset.
+__host__ __device__ __forceinline__ size_t bal_index(int d, int r, int pitch) {
+    return (size_t)d * pitch + (size_t)(r & 3) * (pitch >> 2) + (r >> 2);
+}
 
 // ---- mbarrier / TMA -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -67,6 +81,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 
 }  // namespace hp

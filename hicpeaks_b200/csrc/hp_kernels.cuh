@@ -9,7 +9,6 @@ namespace hp {
 
 __constant__ Prog c_prog;
 __constant__ Chunks c_chunks;
-__constant__ int c_off2[kMaxOps];            // score kernel: (tile offset << 1) | isY
 __constant__ signed char c_opa[kMaxOps];
 __constant__ signed char c_opb[kMaxOps];
 __constant__ unsigned char c_opy[kMaxOps];
@@ -116,10 +115,12 @@ __device__ __noinline__ void edge_be(const double* __restrict__ ir, int r, int d
 }
 
 // ============================================================================================
-// K2  score kernel -- callers.py:132-198 (donut / lower-left sums in the reference's fp64 order),
+// K2  score kernels -- callers.py:132-198 (donut / lower-left sums in the reference's fp64 order),
 // :212-213 (snapshot at the resolving step), :244-256 (E, validity), :25-41 (lambda-chunk id) and
 // the (chunk, observed) histogram that replaces the per-chunk sort of multipletests (:265-275).
-// One TMA tile of the balanced plane with halo (+-F rows, +-2F diagonals) per CTA.
+// One TMA tile of the quad-interleaved balanced plane with halo per CTA.  Two kernels share the
+// per-pixel tail `emit_pixel`: k_score (any sweep program, table-driven) and k_score_spec
+// (hp_score_spec.cuh: compile-time unrolled sweep programs, 4x4 register blocks).
 // ============================================================================================
 struct ScoreArgs {
     const int* raw;
@@ -131,77 +132,240 @@ struct ScoreArgs {
     unsigned int* hist;                // [npw*2][total_bins]
     unsigned long long* emax_bits;     // [npw*2]
     unsigned long long* nvalid;        // [npw*2]
-    unsigned int* rownz;               // [n] row has a non-zero stored balanced value
     Cand* cand;
     unsigned int* cand_count;          // [0] records, [1] dropped (capacity), [2] chunk overflow
     unsigned int cand_cap;
     double* dump;                      // optional [npw*2][3][num*pitch]
     long long plane;
-    int n, num, pitch, dlo, dhi, F, HR, BR, BD, TD, bal_first, sh_pairs;   // HR: row halo, F rounded up to even
+    int n, num, pitch, dlo, dhi, F, BD, TD, bal_first, sh_pairs;
+    int HR, NQ;                        // row halo (multiple of 4) and row quads of the tile: NQ = (kTR + 2 HR) / 4
 };
 
-__device__ __forceinline__ int find_chunk(double E, bool& member) {
-    // smallest i >= 1 with E < rv[i]; member iff rv[i-1] < E (strict, callers.py:38)
-    const int mc = c_chunks.maxchunk;
+struct ScoreSmem {                     // carve-up of the dynamic shared memory of a score CTA
+    double* tile;                      // [BD][4][NQ]
+    uint64_t* bar;
+    unsigned int* cnt;                 // staged candidate count
+    unsigned int* base;
+    unsigned long long* emax;          // [16]
+    unsigned int* nval;                // [16]
+    double* rv;                        // [kMaxChunk + 2] chunk edges (copy of c_chunks.rv: per-lane indexing)
+    int4* cinfo;                       // [kMaxChunk + 2] {hoff, hw, kcand, 0}
+    Cand* stage;                       // [kStage]
+    double2* qsum;                     // [warps][kQCap] resolved (bS_K, bS_Y) waiting for the tail (k_score_spec only)
+    int2* qmeta;                       // [warps][kQCap] {r, d << 16 | step << 8 | pair}
+    unsigned int* hist;                // [sh_pairs*2][kShI][kShK]
+};
+constexpr int kQCap = 160;             // per-warp queue: < 32 left over + one pixel row of a block (4 x 32)
+constexpr int kQueueBytes = (kThreads / 32) * kQCap * 24;
+constexpr int kChunkTabBytes = (kMaxChunk + 2) * 24;
+__host__ __device__ __forceinline__ size_t score_smem_bytes(int BD, int NQ, int sh_pairs, bool queue) {
+    return (size_t)BD * 4 * NQ * 8 + 16 + 128 + 64 + kChunkTabBytes + (size_t)kStage * sizeof(Cand) + (queue ? kQueueBytes : 0) +
+           (size_t)sh_pairs * 2 * kShI * kShK * 4;
+}
+__device__ __forceinline__ ScoreSmem score_smem(unsigned char* smem, int BD, int NQ, bool queue) {
+    ScoreSmem S;
+    unsigned char* p = smem;
+    S.tile = reinterpret_cast<double*>(p); p += (size_t)BD * 4 * NQ * 8;
+    S.bar = reinterpret_cast<uint64_t*>(p);
+    S.cnt = reinterpret_cast<unsigned int*>(p + 8);
+    S.base = reinterpret_cast<unsigned int*>(p + 12); p += 16;
+    S.emax = reinterpret_cast<unsigned long long*>(p); p += 128;
+    S.nval = reinterpret_cast<unsigned int*>(p); p += 64;
+    S.cinfo = reinterpret_cast<int4*>(p); p += (kMaxChunk + 2) * 16;
+    S.rv = reinterpret_cast<double*>(p); p += (kMaxChunk + 2) * 8;
+    S.stage = reinterpret_cast<Cand*>(p); p += (size_t)kStage * sizeof(Cand);
+    S.qsum = reinterpret_cast<double2*>(p);
+    S.qmeta = reinterpret_cast<int2*>(p + (queue ? (kThreads / 32) * kQCap * 16 : 0));
+    if (queue) p += kQueueBytes;
+    S.hist = reinterpret_cast<unsigned int*>(p);
+    return S;
+}
+
+// lambda-chunk of E > 0: smallest i >= 1 with E < rv[i]; member iff rv[i-1] < E (strict, callers.py:38).
+// rv[3e+1] <= 2^e <= E < 2^(e+1) <= rv[3e+4] up to the rounding of the edge table, hence the two fix-up loops
+// (they almost never iterate).  Returns maxchunk + 1 when E is beyond the last edge.
+__device__ __forceinline__ int find_chunk(const double* __restrict__ rv, int mc, double E, bool& member) {
     int i = 1;
     if (E >= 1.0) {
-        const int e = ilogb(E);
+        const int e = (int)((__double2hiint(E) >> 20) & 0x7ff) - 1023;
         i = (e > 40) ? mc + 1 : 3 * e + 2;
         if (i > mc + 1) i = mc + 1;
+        if (i <= mc && E >= rv[i]) { ++i; if (i <= mc && E >= rv[i]) ++i; }
     }
-    while (i <= mc && E >= c_chunks.rv[i]) ++i;
-    while (i > 1 && E < c_chunks.rv[i - 1]) --i;
-    member = (i <= mc) && (E > c_chunks.rv[i - 1]);
+    while (i <= mc && E >= rv[i]) ++i;
+    while (i > 1 && E < rv[i - 1]) --i;
+    member = (i <= mc) && (E > rv[i - 1]);
     return i;
 }
 
+// Per-pixel tail (callers.py:244-256 + chunk id + histograms), called by every lane of a converged warp.
+// `act`: this lane holds a pixel (r, r + d) that resolves pair `pi` at executed step `s` with donut /
+// lower-left sums SK, SY; s and pi may differ between lanes.  NPW > 0: compile-time pair count.
+template <int NPW>
+__device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem& sh, bool act, double SK, double SY,
+                                            int r, int d, int s, int pi, int lane) {
+    const int nexec = c_prog.nsteps_exec;
+    const int total_bins = c_chunks.total_bins;
+    const int mc = c_chunks.maxchunk;
+    bool cand = false;
+    unsigned flags = 0, chk[2] = {0, 0};
+    double Ev[2] = {0.0, 0.0};
+    int obs = 0;
+    if (act) {
+        obs = A.raw[(size_t)d * A.pitch + r];
+        double be[2];
+        const bool edge = (r < A.F) || (r + d >= A.n - A.F);
+        if (edge) {
+            edge_be(A.ir, r, d, A.n, A.num, A.bal_first, s, be[0], be[1]);
+        } else {
+            be[0] = A.betab[(size_t)s * A.num + d];
+            be[1] = A.betab[(size_t)(nexec + s) * A.num + d];
+        }
+        const double ird = A.ir[d], bb1 = A.b1[r], bb2 = A.b2[r + d];
+#pragma unroll
+        for (int fl = 0; fl < 2; ++fl) {
+            const double bs = fl ? SY : SK;
+            double E = 0.0;
+            bool valid = false;
+            if (be[fl] != 0.0) {
+                const double ratio = __ddiv_rn(bs, be[fl]);
+                const double cem = __dmul_rn(ird, ratio);
+                E = __dmul_rn(__dmul_rn(cem, bb1), bb2);
+                const bool cnz = (ratio != 0.0) && (cem != 0.0);
+                valid = cnz && (E > 0.0);
+                if (fl == 1 && cnz) flags |= HP_SF_CEMY_NONZERO;
+            }
+            if (A.dump) {
+                double* dp = A.dump + (size_t)((pi * 2 + fl) * 3) * A.plane + (size_t)d * A.pitch + r;
+                dp[0] = bs;
+                dp[A.plane] = be[fl];
+                dp[2 * A.plane] = valid ? E : 0.0;
+            }
+            if (valid) {
+                flags |= (fl ? HP_SF_VALID_Y : HP_SF_VALID_K);
+                Ev[fl] = E;
+                const unsigned long long eb = (unsigned long long)__double_as_longlong(E);
+                if (eb > sh.emax[pi * 2 + fl]) atomicMax(&sh.emax[pi * 2 + fl], eb);
+                bool member;
+                const int ci = find_chunk(sh.rv, mc, E, member);
+                if (ci > mc) atomicAdd(&A.cand_count[2], 1u);
+                if (member) {
+                    chk[fl] = (unsigned)ci;
+                    const int4 inf = sh.cinfo[ci];
+                    const int kb = obs < inf.y - 1 ? obs : inf.y - 1;
+                    if (pi < A.sh_pairs && ci <= kShI && kb < kShK)
+                        atomicAdd(&sh.hist[((pi * 2 + fl) * kShI + (ci - 1)) * kShK + kb], 1u);
+                    else
+                        atomicAdd(&A.hist[(size_t)(pi * 2 + fl) * total_bins + inf.x + kb], 1u);
+                    cand |= (obs >= inf.z);
+                }
+            }
+        }
+    }
+    // warp-converged bookkeeping: valid counts per (pair, background), candidate staging
+    const int npw = NPW > 0 ? NPW : c_prog.npw;
+#pragma unroll
+    for (int fl = 0; fl < 2; ++fl) {
+        const bool v = (flags & (fl ? HP_SF_VALID_Y : HP_SF_VALID_K)) != 0;
+        if (NPW == 1) {
+            const unsigned mv = __ballot_sync(0xffffffffu, v);
+            if (mv && lane == 0) atomicAdd(&sh.nval[fl], (unsigned)__popc(mv));
+        } else {
+            for (int k = 0; k < npw; ++k) {
+                const unsigned mv = __ballot_sync(0xffffffffu, v && pi == k);
+                if (mv && lane == 0) atomicAdd(&sh.nval[k * 2 + fl], (unsigned)__popc(mv));
+            }
+        }
+    }
+    const unsigned mcand = __ballot_sync(0xffffffffu, cand);
+    if (mcand) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(sh.cnt, (unsigned)__popc(mcand));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (cand) {
+            const unsigned slot = base + __popc(mcand & ((1u << lane) - 1u));
+            Cand cr;
+            cr.r = r; cr.d = d; cr.obs = obs;
+            cr.pair = (unsigned char)pi; cr.flags = (unsigned char)flags; cr.chunk_k = (unsigned char)chk[0]; cr.chunk_y = (unsigned char)chk[1];
+            cr.e_k = Ev[0]; cr.e_y = Ev[1];
+            if (slot < kStage) {
+                sh.stage[slot] = cr;
+            } else {  // staging full: straight to the global list
+                const unsigned g = atomicAdd(&A.cand_count[0], 1u);
+                if (g < A.cand_cap) A.cand[g] = cr; else atomicAdd(&A.cand_count[1], 1u);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void score_prologue(const ScoreSmem& sh, const CUtensorMap* tm, int tile_bytes, int q0, int plane0,
+                                               int sh_bins) {
+    if (threadIdx.x == 0) {
+        mbar_init(sh.bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(sh.bar, (uint32_t)tile_bytes);
+        tma_load_3d(sh.tile, tm, q0, 0, plane0, sh.bar);
+        *sh.cnt = 0;
+    }
+    for (int i = threadIdx.x; i < sh_bins; i += kThreads) sh.hist[i] = 0;
+    if (threadIdx.x < 16) { sh.emax[threadIdx.x] = 0ull; sh.nval[threadIdx.x] = 0u; }
+    for (int i = threadIdx.x; i < kMaxChunk + 2; i += kThreads) {
+        sh.rv[i] = c_chunks.rv[i];
+        sh.cinfo[i] = make_int4(c_chunks.hoff[i], c_chunks.hw[i], c_chunks.kcand[i], 0);
+    }
+    __syncthreads();
+    mbar_wait(sh.bar, 0);
+}
+
+// flush: privatised histogram, counters, staged candidates
+__device__ __forceinline__ void score_epilogue(const ScoreArgs& A, const ScoreSmem& sh, int sh_bins) {
+    __syncthreads();
+    const int total_bins = c_chunks.total_bins;
+    for (int i = threadIdx.x; i < sh_bins; i += kThreads) {
+        const unsigned v = sh.hist[i];
+        if (v) {
+            const int kb = i % kShK, ci = (i / kShK) % kShI + 1, lf = i / (kShK * kShI);
+            atomicAdd(&A.hist[(size_t)lf * total_bins + c_chunks.hoff[ci] + kb], v);
+        }
+    }
+    if (threadIdx.x < 2 * c_prog.npw) {
+        if (sh.nval[threadIdx.x]) atomicAdd(&A.nvalid[threadIdx.x], (unsigned long long)sh.nval[threadIdx.x]);
+        if (sh.emax[threadIdx.x]) atomicMax(&A.emax_bits[threadIdx.x], sh.emax[threadIdx.x]);
+    }
+    unsigned staged = *sh.cnt;
+    if (staged > kStage) staged = kStage;
+    if (staged) {
+        if (threadIdx.x == 0) *sh.base = atomicAdd(&A.cand_count[0], staged);
+        __syncthreads();
+        const unsigned base = *sh.base;
+        for (unsigned i = threadIdx.x; i < staged; i += kThreads) {
+            if (base + i < A.cand_cap) A.cand[base + i] = sh.stage[i];
+            else atomicAdd(&A.cand_count[1], 1u);
+        }
+    }
+}
+
+// generic kernel: walks the op table of the sweep program, one pixel per thread per diagonal
 __global__ void __launch_bounds__(kThreads) k_score(const __grid_constant__ CUtensorMap tm_bal, ScoreArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    double* tile = reinterpret_cast<double*>(smem);
-    const int tile_bytes = A.BR * A.BD * 8;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + tile_bytes);
-    unsigned int* sh_cnt = reinterpret_cast<unsigned int*>(smem + tile_bytes + 8);   // staged count
-    unsigned long long* sh_emax = reinterpret_cast<unsigned long long*>(smem + tile_bytes + 16);  // [16]
-    unsigned int* sh_nval = reinterpret_cast<unsigned int*>(smem + tile_bytes + 16 + 128);        // [16]
-    unsigned int* sh_base = sh_nval + 16;                                                          // [1]
-    Cand* sh_stage = reinterpret_cast<Cand*>(smem + tile_bytes + 16 + 128 + 64 + 16);
-    unsigned int* sh_hist = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(sh_stage) + kStage * sizeof(Cand));
+    const ScoreSmem sh = score_smem(smem, A.BD, A.NQ, false);
     const int sh_bins = A.sh_pairs * 2 * kShI * kShK;
-
     const int r0 = blockIdx.x * kTR;
     const int d0 = A.dlo + blockIdx.y * A.TD;
     const int npw = c_prog.npw;
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, (uint32_t)tile_bytes);
-        tma_load_2d(tile, &tm_bal, r0 - A.HR, d0 - 2 * A.F, bar);   // box start must be 16-byte aligned
-        *sh_cnt = 0;
-    }
-    for (int i = threadIdx.x; i < sh_bins; i += kThreads) sh_hist[i] = 0;
-    if (threadIdx.x < 16) { sh_emax[threadIdx.x] = 0ull; sh_nval[threadIdx.x] = 0u; }
-    __syncthreads();
-    mbar_wait(bar, 0);
+    score_prologue(sh, &tm_bal, A.BD * 4 * A.NQ * 8, (r0 - A.HR) / 4, d0 - 2 * A.F, sh_bins);
 
     const int lane = threadIdx.x & 31;
     const int rl = threadIdx.x & (kTR - 1);
     const int r = r0 + rl;
-    const int nexec = c_prog.nsteps_exec;
-    const int total_bins = c_chunks.total_bins;
-    bool row_nz = false;
+    const int rho = rl + A.HR;                       // row inside the tile
 
     for (int dl = threadIdx.x >> 7; dl < A.TD; dl += kThreads / kTR) {
         const int d = d0 + dl;                       // warp-uniform
         if (d > A.dhi) break;
-        const double* ctr = tile + (dl + 2 * A.F) * A.BR + (rl + A.HR);
         const bool inside = (r < A.n) && (r + d < A.n);
         unsigned char lv = kLvlNone;
-        int obs = 0;
-        if (inside) {
-            lv = A.lvl[(size_t)d * A.pitch + r];
-            obs = A.raw[(size_t)d * A.pitch + r];
-            row_nz |= (*ctr != 0.0);
-        }
+        if (inside) lv = A.lvl[(size_t)d * A.pitch + r];
         int last = -1;
         if (lv < kLvlNever) {
             for (int pi = 0; pi < npw; ++pi) {
@@ -212,137 +376,39 @@ __global__ void __launch_bounds__(kThreads) k_score(const __grid_constant__ CUte
         }
         const int wlast = __reduce_max_sync(0xffffffffu, last);
         if (wlast < 0) continue;
-        const bool edge = (r < A.F) || (r + d >= A.n - A.F);
         double SK = 0.0, SY = 0.0;
         int opi = 0;
         for (int s = 0; s <= wlast; ++s) {
             const int oe = c_prog.op_end[s];
             if (s <= last) {
                 for (; opi < oe; ++opi) {
-                    const int o = c_off2[opi];
-                    const double v = ctr[o >> 1];
+                    const int a = c_opa[opi], b = c_opb[opi];
+                    const int rr = rho + a;
+                    const double v = sh.tile[((dl + 2 * A.F + b - a) * 4 + (rr & 3)) * A.NQ + (rr >> 2)];
                     SK = __dadd_rn(SK, v);
-                    if (o & 1) SY = __dadd_rn(SY, v);
+                    if (c_opy[opi]) SY = __dadd_rn(SY, v);
                 }
             }
             const int pi = c_prog.step_pi[s];
             const bool em = (s <= last) && (d >= c_prog.ww[pi]) && (c_prog.next_step[pi][lv] == s);
-            bool cand = false;
-            unsigned char flags = 0, chk[2] = {0, 0};
-            double Ev[2] = {0.0, 0.0};
-            if (em) {
-                double be[2];
-                if (edge) {
-                    edge_be(A.ir, r, d, A.n, A.num, A.bal_first, s, be[0], be[1]);
-                } else {
-                    be[0] = A.betab[(size_t)s * A.num + d];
-                    be[1] = A.betab[(size_t)(nexec + s) * A.num + d];
-                }
-                const double ird = A.ir[d], bb1 = A.b1[r], bb2 = A.b2[r + d];
-#pragma unroll
-                for (int fl = 0; fl < 2; ++fl) {
-                    const double bs = fl ? SY : SK;
-                    double E = 0.0;
-                    bool valid = false;
-                    if (be[fl] != 0.0) {
-                        const double ratio = __ddiv_rn(bs, be[fl]);
-                        const double cem = __dmul_rn(ird, ratio);
-                        E = __dmul_rn(__dmul_rn(cem, bb1), bb2);
-                        const bool cnz = (ratio != 0.0) && (cem != 0.0);
-                        valid = cnz && (E > 0.0);
-                        if (fl == 1 && cnz) flags |= HP_SF_CEMY_NONZERO;
-                    }
-                    if (A.dump) {
-                        double* dp = A.dump + (size_t)((pi * 2 + fl) * 3) * A.plane + (size_t)d * A.pitch + r;
-                        dp[0] = bs;
-                        dp[A.plane] = be[fl];
-                        dp[2 * A.plane] = valid ? E : 0.0;
-                    }
-                    if (valid) {
-                        flags |= (fl ? HP_SF_VALID_Y : HP_SF_VALID_K);
-                        Ev[fl] = E;
-                        bool member;
-                        const int ci = find_chunk(E, member);
-                        if (ci > c_chunks.maxchunk) atomicAdd(&A.cand_count[2], 1u);
-                        if (member) {
-                            chk[fl] = (unsigned char)ci;
-                            const int w = c_chunks.hw[ci];
-                            const int kb = obs < w - 1 ? obs : w - 1;
-                            if (pi < A.sh_pairs && ci <= kShI && kb < kShK)
-                                atomicAdd(&sh_hist[((pi * 2 + fl) * kShI + (ci - 1)) * kShK + kb], 1u);
-                            else
-                                atomicAdd(&A.hist[(size_t)(pi * 2 + fl) * total_bins + c_chunks.hoff[ci] + kb], 1u);
-                            cand |= (obs >= c_chunks.kcand[ci]);
-                        }
-                    }
-                }
-            }
-            // warp-converged bookkeeping: valid counts, E max, candidate staging
-            const unsigned any = __ballot_sync(0xffffffffu, em);
-            if (any) {
-#pragma unroll
-                for (int fl = 0; fl < 2; ++fl) {
-                    const unsigned mv = __ballot_sync(0xffffffffu, (flags & (fl ? HP_SF_VALID_Y : HP_SF_VALID_K)) != 0);
-                    if (mv) {
-                        unsigned long long eb = (unsigned long long)__double_as_longlong(Ev[fl]);
-#pragma unroll
-                        for (int o = 16; o; o >>= 1) {
-                            const unsigned long long t = __shfl_xor_sync(0xffffffffu, eb, o);
-                            eb = t > eb ? t : eb;
-                        }
-                        if (lane == 0) {
-                            atomicAdd(&sh_nval[pi * 2 + fl], (unsigned)__popc(mv));
-                            atomicMax(&sh_emax[pi * 2 + fl], eb);
-                        }
-                    }
-                }
-                const unsigned mc = __ballot_sync(0xffffffffu, cand);
-                if (mc) {
-                    unsigned base = 0;
-                    if (lane == 0) base = atomicAdd(sh_cnt, (unsigned)__popc(mc));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (cand) {
-                        const unsigned slot = base + __popc(mc & ((1u << lane) - 1u));
-                        Cand cr;
-                        cr.r = r; cr.d = d; cr.obs = obs;
-                        cr.pair = (unsigned char)pi; cr.flags = flags; cr.chunk_k = chk[0]; cr.chunk_y = chk[1];
-                        cr.e_k = Ev[0]; cr.e_y = Ev[1];
-                        if (slot < kStage) {
-                            sh_stage[slot] = cr;
-                        } else {  // staging full: straight to the global list
-                            const unsigned g = atomicAdd(&A.cand_count[0], 1u);
-                            if (g < A.cand_cap) A.cand[g] = cr; else atomicAdd(&A.cand_count[1], 1u);
-                        }
-                    }
-                }
-            }
+            if (__any_sync(0xffffffffu, em)) emit_record<0>(A, sh, em, SK, SY, r, d, s, pi, lane);
         }
     }
-    if (row_nz && r < A.n) A.rownz[r] = 1u;
-    __syncthreads();
-    // flush: privatised histogram, counters, staged candidates
-    for (int i = threadIdx.x; i < sh_bins; i += kThreads) {
-        const unsigned v = sh_hist[i];
-        if (v) {
-            const int kb = i % kShK, ci = (i / kShK) % kShI + 1, lf = i / (kShK * kShI);
-            atomicAdd(&A.hist[(size_t)lf * total_bins + c_chunks.hoff[ci] + kb], v);
-        }
-    }
-    if (threadIdx.x < 2 * npw) {
-        if (sh_nval[threadIdx.x]) atomicAdd(&A.nvalid[threadIdx.x], (unsigned long long)sh_nval[threadIdx.x]);
-        if (sh_emax[threadIdx.x]) atomicMax(&A.emax_bits[threadIdx.x], sh_emax[threadIdx.x]);
-    }
-    unsigned staged = *sh_cnt;
-    if (staged > kStage) staged = kStage;
-    if (staged) {
-        if (threadIdx.x == 0) *sh_base = atomicAdd(&A.cand_count[0], staged);
-        __syncthreads();
-        const unsigned base = *sh_base;
-        for (unsigned i = threadIdx.x; i < staged; i += kThreads) {
-            if (base + i < A.cand_cap) A.cand[base + i] = sh_stage[i];
-            else atomicAdd(&A.cand_count[1], 1u);
-        }
-    }
+    score_epilogue(A, sh, sh_bins);
+}
+
+// ============================================================================================
+// upload helper: plain diagonal-major staging plane -> quad-interleaved balanced plane, plus the
+// "row has a non-zero stored balanced value" flags behind the gap mask (callers.py:238)
+// ============================================================================================
+__global__ void k_relayout(const double* __restrict__ src, double* __restrict__ dst, unsigned int* __restrict__ rownz,
+                           int pitch, int num) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int d = blockIdx.y;
+    if (r >= pitch || d >= num) return;
+    const double v = src[(size_t)d * pitch + r];
+    dst[bal_index(d, r, pitch)] = v;
+    if (v != 0.0) rownz[r] = 1u;
 }
 
 // ============================================================================================
@@ -490,7 +556,7 @@ __global__ void k_filter(FilterArgs A) {
         }
     }
     if (any) {
-        sv.ice = A.bal[(size_t)c.d * A.pitch + c.r];
+        sv.ice = A.bal[bal_index(c.d, c.r, A.pitch)];
         const unsigned g = atomicAdd(&A.out_count[0], 1u);
         if (g < A.out_cap) A.out[g] = sv; else atomicAdd(&A.out_count[1], 1u);
     }

@@ -1,0 +1,299 @@
+// k_score_spec: the score kernel for sweep programs known at compile time.
+//
+// The reference accumulates every donut cell into one fp64 sum per pixel in a fixed order (steps in
+// (w, p) order; inside a step rows a = -w..w outer, columns b = -w..w inner, callers.py:147-198), and the
+// sums must be reproduced bit for bit because lambda-chunk membership and the fold thresholds are
+// discontinuous in them.  That order leaves no algebraic reuse between pixels, so the kernel is
+// bound by fp64 add issue and by shared-memory operand bandwidth, not by HBM.  This kernel attacks
+// both: the whole program (which rings every step adds) is a template parameter, so each add is one
+// DADD fed by one LDS.64 with an immediate offset, and every thread owns a 4 x 4 block of pixels
+// (4 consecutive matrix rows x 4 consecutive columns) so that a loaded operand feeds up to
+// 4 x min(4, 2w) accumulators from registers.  The quad-interleaved plane layout (hp_device.cuh)
+// makes those loads conflict-free: lane l owns rows 4l..4l+3, and for a fixed row offset the 32
+// lanes read 32 consecutive doubles.
+#pragma once
+#include <type_traits>
+
+#include "hp_kernels.cuh"
+
+namespace hp {
+
+// ---- compile-time sweep program (callers.py:15-23 step order, :150-152 skip rule) -------------
+template <int MAXW_, int NPW_, int P0, int W0, int P1 = 0, int W1 = 0, int P2 = 0, int W2 = 0, int P3 = 0, int W3 = 0>
+struct SProg {
+    static constexpr int maxww = MAXW_;
+    static constexpr int npw = NPW_;
+    __host__ __device__ static constexpr int pw(int i) { return i == 0 ? P0 : i == 1 ? P1 : i == 2 ? P2 : P3; }
+    __host__ __device__ static constexpr int ww(int i) { return i == 0 ? W0 : i == 1 ? W1 : i == 2 ? W2 : W3; }
+    __host__ __device__ static constexpr int nsteps() {
+        int k = 0;
+        for (int i = 0; i < npw; ++i) k += maxww - ww(i) + 1;
+        return k;
+    }
+    // pair index of step s; steps sorted by (w, p)
+    __host__ __device__ static constexpr int step_pi(int s) {
+        int k = 0;
+        for (int w = 1; w <= maxww; ++w) {
+            int lastp = -1;                        // pairs with ww <= w in ascending p
+            for (int t = 0; t < npw; ++t) {
+                int best = -1;
+                for (int i = 0; i < npw; ++i)
+                    if (ww(i) <= w && pw(i) > lastp && (best < 0 || pw(i) < pw(best))) best = i;
+                if (best < 0) break;
+                if (k == s) return best;
+                ++k;
+                lastp = pw(best);
+            }
+        }
+        return -1;
+    }
+    __host__ __device__ static constexpr int step_w(int s) {
+        int k = 0;
+        for (int w = 1; w <= maxww; ++w)
+            for (int i = 0; i < npw; ++i)
+                if (ww(i) <= w) { if (k == s) return w; ++k; }
+        return -1;
+    }
+    __host__ __device__ static constexpr int step_p(int s) { return pw(step_pi(s)); }
+    // rings g = max(|a|, |b|) whose cells (off the cross) step s adds
+    __host__ __device__ static constexpr unsigned mask(int s) {
+        const int p = step_p(s), w = step_w(s);
+        const bool limit = s > 0;
+        const int lp = limit ? step_p(s - 1) : 0, lw = limit ? step_w(s - 1) : 0;
+        const int mx = p > lp ? p : lp, mn = p < lp ? p : lp;
+        unsigned m = 0;
+        for (int g = 1; g <= w; ++g) {
+            if (limit && ((g <= lw && g > mx) || g <= mn)) continue;
+            if (g <= p) continue;                  // current peak square
+            m |= 1u << g;
+        }
+        return m;
+    }
+    // previous step of the same pair, -1 if none: pixels with level in (prev, s] resolve the pair at s
+    __host__ __device__ static constexpr int prev_same_pair(int s) {
+        const int pi = step_pi(s);
+        for (int t = s - 1; t >= 0; --t)
+            if (step_pi(t) == pi) return t;
+        return -1;
+    }
+};
+
+__host__ __device__ constexpr int hp_top_ring(unsigned m) {
+    int w = 0;
+    for (int g = 1; g < 32; ++g) if ((m >> g) & 1u) w = g;
+    return w;
+}
+
+constexpr int kTC = 4;     // pixel block: 4 rows x kTC columns per thread
+
+// offset (in doubles) of matrix element (row r + rho, column c + kappa) from the thread's base
+// pointer &tile[d'(c - r)][0][quad(r)]
+__host__ __device__ constexpr int spec_off(int rho, int kappa) {
+    return ((kappa - rho) * 4 + (rho & 3)) * kNQ + (rho >> 2);
+}
+
+// compile-time loop: f(integral_constant<int, B>), ..., f(integral_constant<int, E - 1>).  Used instead of
+// `#pragma unroll` because every condition inside the sweep must fold to a constant (nvcc keeps the
+// big outer loops rolled and predicates the adds otherwise).
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+__host__ __device__ constexpr int hp_iabs(int x) { return x < 0 ? -x : x; }
+__host__ __device__ constexpr bool hp_cell_in(unsigned mask, int a, int b) {
+    return a != 0 && b != 0 && ((mask >> (hp_iabs(a) > hp_iabs(b) ? hp_iabs(a) : hp_iabs(b))) & 1u) != 0u;
+}
+// does matrix element (rho, kappa) of the block's window feed any of the 16 pixels under MASK / W?
+__host__ __device__ constexpr bool hp_strip_used(unsigned mask, int W, int rho, int kappa) {
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            const int a = rho - i, b = kappa - j;
+            if (a >= -W && a <= W && b >= -W && b <= W && hp_cell_in(mask, a, b)) return true;
+        }
+    return false;
+}
+
+// one sweep step: add the cells of the rings in MASK to the 16 pixels of the thread
+template <unsigned MASK>
+__device__ __forceinline__ void spec_accumulate(const double* __restrict__ base, double (&aK)[4][kTC], double (&aY)[4][kTC]) {
+    constexpr int W = hp_top_ring(MASK);
+    static_for<-W, W + 4>([&](auto RHO) {                 // matrix row, relative to the block's first row
+        constexpr int rho = decltype(RHO)::value;
+        double strip[2 * W + kTC];
+        static_for<0, 2 * W + kTC>([&](auto KK) {
+            constexpr int k = decltype(KK)::value;
+            if constexpr (hp_strip_used(MASK, W, rho, k - W)) strip[k] = base[spec_off(rho, k - W)];
+        });
+        static_for<0, 4>([&](auto II) {
+            constexpr int i = decltype(II)::value;
+            constexpr int a = rho - i;
+            if constexpr (a >= -W && a <= W && a != 0) {
+                static_for<0, kTC>([&](auto JJ) {
+                    constexpr int j = decltype(JJ)::value;
+                    static_for<-W, W + 1>([&](auto BB) {
+                        constexpr int b = decltype(BB)::value;
+                        if constexpr (hp_cell_in(MASK, a, b)) {
+                            const double v = strip[j + b + W];
+                            aK[i][j] = __dadd_rn(aK[i][j], v);
+                            if constexpr (a > 0 && b < 0) aY[i][j] = __dadd_rn(aY[i][j], v);
+                        }
+                    });
+                });
+            }
+        });
+    });
+}
+
+// run-time step index -> the compile-time accumulate code of that step
+template <class PG, int S>
+__device__ __forceinline__ void spec_dispatch(int s, const double* base, double (&aK)[4][kTC], double (&aY)[4][kTC]) {
+    if constexpr (S < PG::nsteps()) {
+        if (s == S) {
+            constexpr unsigned M = PG::mask(S);
+            if constexpr (M != 0u) spec_accumulate<M>(base, aK, aY);
+        } else {
+            spec_dispatch<PG, S + 1>(s, base, aK, aY);
+        }
+    }
+}
+
+// CTA: kTR rows x TD diagonals of (row, column)-aligned 4 x 4 pixel blocks; warp w owns the blocks of
+// columns [dc, dc + 4) with dc = d0 + 4 (w + 8 t), lane l the rows 4l..4l+3.  Rows with (r & 3) = i
+// cover the diagonals [d0 - i, d0 + TD - i): consecutive CTAs in d tile the band without overlap,
+// and the first / last CTA mask the <= 3 diagonals that stick out of [dlo, dhi].
+//
+// Per step the warp accumulates (all lanes, all 16 pixels: zero pixels ride along), then pixels that
+// resolve a pair at this step push (bS_K, bS_Y, r, d, step, pair) on a per-warp queue; whenever 32
+// records are waiting the warp runs the per-pixel tail on them fully converged.
+#ifndef HP_SPEC_MINB
+#define HP_SPEC_MINB 1
+#endif
+template <class PG>
+__global__ void __launch_bounds__(kThreads, HP_SPEC_MINB) k_score_spec(const __grid_constant__ CUtensorMap tm_bal, ScoreArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const ScoreSmem sh = score_smem(smem, A.BD, kNQ, true);
+    const int sh_bins = A.sh_pairs * 2 * kShI * kShK;
+    const int r0 = blockIdx.x * kTR;
+    const int d0 = A.dlo + blockIdx.y * A.TD;
+    const int plane0 = d0 - 3 - 2 * A.F;
+    score_prologue(sh, &tm_bal, A.BD * 4 * kNQ * 8, (r0 - kHR) / 4, plane0, sh_bins);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = r0 + 4 * lane;
+    const unsigned lt = (1u << lane) - 1u;
+    const int dspan = c_prog.dspan;
+    double2* qs = sh.qsum + warp * kQCap;
+    int2* qm = sh.qmeta + warp * kQCap;
+    int cnt = 0;                                     // warp-uniform queue fill
+    for (int kb = warp; kb * kTC < A.TD; kb += kThreads / 32) {
+        const int dc = d0 + kb * kTC;                // diagonal of pixel (0, 0) of the block; warp-uniform
+        if (dc - 3 > A.dhi) break;
+        unsigned lvp[4];                             // levels of the 16 pixels, one byte each, [i] = row
+        int last = -1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            unsigned pk = 0;
+#pragma unroll
+            for (int j = 0; j < kTC; ++j) {
+                const int rr = r + i, d = dc + j - i;
+                unsigned lv = kLvlNone;
+                if (d >= A.dlo && d <= A.dhi && rr < A.n && rr + d < A.n) lv = A.lvl[(size_t)d * A.pitch + rr];
+                pk |= lv << (8 * j);
+                if (lv < kLvlNever) {
+                    const int k = d - A.dlo < dspan ? d - A.dlo : dspan;
+                    const int rs = c_prog.last_need[k][lv];
+                    if (rs != kNoStep && rs > last) last = rs;
+                }
+            }
+            lvp[i] = pk;
+        }
+        const int wlast = __reduce_max_sync(0xffffffffu, last);
+        if (wlast < 0) continue;
+        double aK[4][kTC], aY[4][kTC];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < kTC; ++j) { aK[i][j] = 0.0; aY[i][j] = 0.0; }
+        const double* base = sh.tile + (size_t)(dc - plane0) * 4 * kNQ + (lane + kHR / 4);
+#pragma unroll 1
+        for (int s = 0; s <= wlast; ++s) {
+            spec_dispatch<PG, 0>(s, base, aK, aY);
+            // pixels whose level lies in (previous executed step of this pair, s] resolve the pair now
+            const int pi = c_prog.step_pi[s], lo = c_prog.step_lo[s], wmin = c_prog.ww[pi];
+            unsigned em = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < kTC; ++j) {
+                    const int lv = (lvp[i] >> (8 * j)) & 0xff;
+                    if (lv >= lo && lv <= s && (dc + j - i) >= wmin) em |= 1u << (i * kTC + j);
+                }
+            if (!__any_sync(0xffffffffu, em != 0u)) continue;
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+                const unsigned emr = (em >> (i * kTC)) & ((1u << kTC) - 1u);
+                if (!__any_sync(0xffffffffu, emr != 0u)) continue;
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii)
+                    if (ii == i) {
+#pragma unroll
+                        for (int j = 0; j < kTC; ++j) {
+                            const bool e = (emr >> j) & 1u;
+                            const unsigned m = __ballot_sync(0xffffffffu, e);
+                            if (e) {
+                                const int slot = cnt + __popc(m & lt);
+                                qs[slot] = make_double2(aK[ii][j], aY[ii][j]);
+                                qm[slot] = make_int2(r + ii, ((dc + j - ii) << 16) | (s << 8) | pi);
+                            }
+                            cnt += __popc(m);
+                        }
+                    }
+                __syncwarp();
+                while (cnt >= 32) {
+                    cnt -= 32;
+                    const double2 v = qs[cnt + lane];
+                    const int2 mt = qm[cnt + lane];
+                    emit_record<PG::npw>(A, sh, true, v.x, v.y, mt.x, mt.y >> 16, (mt.y >> 8) & 0xff, mt.y & 0xff, lane);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    if (cnt > 0) {                                    // leftover records of this warp
+        const bool act = lane < cnt;
+        const double2 v = act ? qs[lane] : make_double2(0.0, 0.0);
+        const int2 mt = act ? qm[lane] : make_int2(0, 0);
+        emit_record<PG::npw>(A, sh, act, v.x, v.y, mt.x, mt.y >> 16, (mt.y >> 8) & 0xff, mt.y & 0xff, lane);
+    }
+    score_epilogue(A, sh, sh_bins);
+}
+
+// ---- host side: does a run-time program (a prefix of it) equal the compiled one? ----------------
+template <class PG>
+inline bool spec_matches(const Prog& G, int nexec, const signed char* opa, const signed char* opb, const unsigned char* opy) {
+    if (G.npw != PG::npw || nexec > PG::nsteps() || nexec > G.nsteps) return false;
+    for (int i = 0; i < PG::npw; ++i)
+        if (G.pw[i] != PG::pw(i) || G.ww[i] != PG::ww(i)) return false;
+    int k = 0;
+    for (int s = 0; s < nexec; ++s) {
+        if (G.step_pi[s] != PG::step_pi(s) || G.step_w[s] != PG::step_w(s)) return false;
+        const unsigned m = PG::mask(s);
+        const int w = G.step_w[s];
+        for (int a = -w; a <= w; ++a)
+            for (int b = -w; b <= w; ++b) {
+                if (a == 0 || b == 0) continue;
+                const int g = abs(a) > abs(b) ? abs(a) : abs(b);
+                if (!((m >> g) & 1u)) continue;
+                if (k >= G.op_end[s] || opa[k] != a || opb[k] != b || opy[k] != (unsigned char)(a > 0 && b < 0)) return false;
+                ++k;
+            }
+        if (k != G.op_end[s]) return false;
+    }
+    return true;
+}
+
+}  // namespace hp

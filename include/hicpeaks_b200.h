@@ -88,8 +88,10 @@ typedef struct hp_hiccups_params {
     int64_t maxapart_bins;       /* maxapart // res  (callers.py:102)                          */
     double sig;                  /* callers.py:273,279                                         */
     int32_t dump;                /* !=0: keep per-pixel bS/bE/E planes for hp_dump_plane (tests) */
-    int32_t reserved;
+    int32_t flags;               /* HP_PF_*                                                    */
 } hp_hiccups_params;
+#define HP_PF_GENERIC_KERNEL 1   /* use the table-driven score kernel even when a compiled-in sweep
+                                    program matches (tests exercise both kernels)               */
 
 typedef struct hp_step_stat {    /* one executed sweep step, callers.py:203-232                 */
     int32_t p, w;
@@ -116,7 +118,7 @@ typedef struct hp_hiccups_summary {
     int64_t n_survivors;         /* records available to hp_get_survivors                       */
     float ms_levels, ms_score, ms_fdr, ms_total; /* device time (CUDA events on the ctx stream) */
     int32_t launches;            /* kernels launched by this call                               */
-    int32_t reserved;
+    int32_t spec_kernel;         /* 1: the score kernel specialised for this sweep program ran   */
 } hp_hiccups_summary;
 
 /* sweep (levels + adaptive width) + expected values + lambda-chunk histograms            */
@@ -144,7 +146,8 @@ typedef struct hp_survivor {     /* a pixel with q <= sig for K or Y of one pair
 #define HP_SF_CEMY_NONZERO 16u   /* reference's cEM[ci,cj] != 0 for the Y background (callers.py:330) */
 int hp_get_survivors(hp_ctx* ctx, hp_survivor* buf, int64_t capacity, int64_t* count);
 
-/* rows of cM whose stored band is all zero ('gaps', callers.py:238): out[r] = 1 if row r is a gap */
+/* rows of cM whose stored band is all zero ('gaps', callers.py:238): out[r] = 1 if row r is a gap
+ * (available after hp_band_upload) */
 int hp_get_gaps(hp_ctx* ctx, uint8_t* out, int64_t n);
 
 /* ---- inspection (parity tests) --------------------------------------------------------------- */

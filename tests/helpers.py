@@ -15,23 +15,24 @@ def engine_inputs(inp):
     return Diags, cDiags, ir
 
 
-def run_engine(ctx, inp, pw, ww, maxww, sig, maxapart_bins, min_local_reads, dump=True):
+def run_engine(ctx, inp, pw, ww, maxww, sig, maxapart_bins, min_local_reads, dump=True, generic_kernel=False):
     Diags, cDiags, ir = engine_inputs(inp)
     ctx.upload(inp["n"], inp["num"], inp["min_ww"], Diags, cDiags, ir, inp["biases"], inp["biases"])
-    P = ctx.make_params(pw, ww, maxww, sig, maxapart_bins, min_local_reads, dump=dump)
+    P = ctx.make_params(pw, ww, maxww, sig, maxapart_bins, min_local_reads, dump=dump, generic_kernel=generic_kernel)
     S1 = ctx.score(P)
     S = ctx.fdr()
     return S1, S
 
 
-def compare_with_oracle(ctx, inp, pw, ww, maxww, sig, maxapart_bins, min_local_reads, q_tol=1e-6):
+def compare_with_oracle(ctx, inp, pw, ww, maxww, sig, maxapart_bins, min_local_reads, q_tol=1e-6, generic_kernel=False):
     """Full cut-point comparison (levels, bS/bE/E bit-exact, histograms exact, p/q within q_tol,
     survivor coordinates exact).  Returns a dict of small statistics."""
     sw, res = ho.score(inp, pw, ww, maxww=maxww, sig=sig, maxapart_bins=maxapart_bins,
                        min_local_reads=min_local_reads)
-    S1, S = run_engine(ctx, inp, pw, ww, maxww, sig, maxapart_bins, min_local_reads, dump=True)
+    S1, S = run_engine(ctx, inp, pw, ww, maxww, sig, maxapart_bins, min_local_reads, dump=True,
+                       generic_kernel=generic_kernel)
+    stats = {"spec_kernel": int(S1.spec_kernel)}
     vx, vd = sw["vx"], sw["vd"]
-    stats = {}
     # --- levels (a-4) ---
     assert S.n_pixels == sw["total"]
     assert S.frozen_w == sw["frozen"], (S.frozen_w, sw["frozen"])

@@ -9,6 +9,9 @@ from helpers import compare_with_oracle
 
 pytestmark = pytest.mark.gpu
 
+# sweep programs compiled into the library (hp_api.cu g_specs): these must take the specialised kernel
+COMPILED = {((2,), (5,)), ((1,), (3,)), ((4,), (7,)), ((1, 2, 4), (3, 5, 7))}
+
 CASES = [
     # n, band, pw, ww, maxww, scale, decay, thr, seed
     (600, 60, [2], [5], 8, 300.0, 1.08, 16, 1),          # dense: freezes at the first level
@@ -19,6 +22,8 @@ CASES = [
     (300, 40, [4], [7], 12, 60.0, 1.2, 30, 4),           # (4,7)
     (129, 30, [2], [5], 7, 80.0, 1.1, 16, 5),            # ragged: n just above one tile
     (1000, 200, [2], [5], 10, 300.0, 1.08, 16, 7),       # several tiles in both directions
+    (777, 150, [2], [5], 10, 12.0, 1.0, 16, 9),          # sparse: deep levels, many zero pixels
+    (515, 100, [1, 2, 4], [3, 5, 7], 10, 15.0, 1.0, 16, 10),  # union, sparse
 ]
 
 
@@ -29,13 +34,18 @@ def ctx():
     c.close()
 
 
+@pytest.mark.parametrize("kernel", ["spec", "generic"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "n%d_b%d_%s" % (c[0], c[1], "-".join(map(str, c[2]))))
-def test_cutpoints_match_oracle(ctx, case):
+def test_cutpoints_match_oracle(ctx, case, kernel):
     n, band, pw, ww, maxww, scale, decay, thr, seed = case
     inp = synth_chromosome(n, band, min(ww), maxww=maxww, seed=seed, scale=scale, decay=decay)
-    st = compare_with_oracle(ctx, inp, pw, ww, maxww, 0.1, band, thr)
+    st = compare_with_oracle(ctx, inp, pw, ww, maxww, 0.1, band, thr, generic_kernel=(kernel == "generic"))
     print(case, st)
     assert st["n_pixels"] > 0
+    if kernel == "generic":
+        assert st["spec_kernel"] == 0
+    elif (tuple(pw), tuple(ww)) in COMPILED and st["frozen"] <= 10:
+        assert st["spec_kernel"] == 1, "a compiled-in sweep program fell back to the generic kernel"
 
 
 def test_poisson_tail_matches_scipy(ctx):
