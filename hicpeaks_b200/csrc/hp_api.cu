@@ -111,6 +111,9 @@ static int build_chunks(hp_ctx* ctx, int max_chunks, const double* edges) {
     for (int i = 1; i <= max_chunks; ++i) {
         C.rv[i] = edges ? edges[i - 1] : (i == 1 ? 1.0 : pow(2.0, (i - 1) / 3.0));
         if (!(C.rv[i] > C.rv[i - 1])) return fail(ctx, HP_ERR_INVALID, "chunk edges must increase");
+        // the kernels locate a chunk from the binary exponent: every third edge must be 2^((i-1)/3) exactly
+        if (i % 3 == 1 && C.rv[i] != ldexp(1.0, (i - 1) / 3))
+            return fail(ctx, HP_ERR_INVALID, "chunk edge " + std::to_string(i) + " is not the exact power of two 2^((i-1)/3)");
         C.hoff[i] = off;
         C.hw[i] = (int)ceil(C.rv[i] + 12.0 * sqrt(C.rv[i]) + 40.0);
         off += C.hw[i];
@@ -346,7 +349,7 @@ struct SpecKernel {
 template <class PG>
 static int launch_spec(hp_ctx* ctx, const CUtensorMap& tm, const ScoreArgs& A, dim3 grid, size_t smem, cudaStream_t st) {
     CK(cudaFuncSetAttribute(k_score_spec<PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_score_spec<PG><<<grid, kThreads, smem, st>>>(tm, A);
+    k_score_spec<PG><<<grid, kSpecThreads, smem, st>>>(tm, A);
     return HP_OK;
 }
 #define HP_SPEC(name, ...) {spec_matches<SProg<__VA_ARGS__>>, launch_spec<SProg<__VA_ARGS__>>, name}
@@ -496,16 +499,16 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
         // 4x4 register-block kernel: one CTA per SM (all 8 warps share one big tile), TD diagonals per CTA
         A.HR = kHR; A.NQ = kNQ;
         int TD = 64;
-        while (TD > 8 && score_smem_bytes(TD + 3 + 4 * F, kNQ, sh_pairs, true) > 200 * 1024) TD /= 2;
+        while (TD > 8 && score_smem_bytes(TD + 3 + 4 * F, kNQ, sh_pairs, kSpecThreads / 32, kQCap) > 224 * 1024) TD /= 2;
         A.TD = TD; A.BD = TD + 3 + 4 * F;
-        smem = score_smem_bytes(A.BD, kNQ, sh_pairs, true);
+        smem = score_smem_bytes(A.BD, kNQ, sh_pairs, kSpecThreads / 32, kQCap);
         grid = dim3((n + kTR - 1) / kTR, (dhi - dlo + 3 + TD) / TD);
     } else {
         A.HR = (F + 7) & ~7; A.NQ = (kTR + 2 * A.HR) / 4;
         int TD = 32;
-        while (TD > 8 && score_smem_bytes(TD + 4 * F, A.NQ, sh_pairs, false) > 110 * 1024) TD /= 2;   // two CTAs per SM where possible
+        while (TD > 8 && score_smem_bytes(TD + 4 * F, A.NQ, sh_pairs, 0, 0) > 110 * 1024) TD /= 2;   // two CTAs per SM where possible
         A.TD = TD; A.BD = TD + 4 * F;
-        smem = score_smem_bytes(A.BD, A.NQ, sh_pairs, false);
+        smem = score_smem_bytes(A.BD, A.NQ, sh_pairs, 0, 0);
         grid = dim3((n + kTR - 1) / kTR, (dhi - dlo + TD) / TD);
     }
     if (smem > 227 * 1024) return fail(ctx, HP_ERR_INVALID, "tile does not fit shared memory");

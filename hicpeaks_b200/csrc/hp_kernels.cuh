@@ -146,67 +146,78 @@ struct ScoreSmem {                     // carve-up of the dynamic shared memory 
     uint64_t* bar;
     unsigned int* cnt;                 // staged candidate count
     unsigned int* base;
+    unsigned int* next;                // next unclaimed column block of the CTA (k_score_spec)
     unsigned long long* emax;          // [16]
     unsigned int* nval;                // [16]
-    double* rv;                        // [kMaxChunk + 2] chunk edges (copy of c_chunks.rv: per-lane indexing)
-    int4* cinfo;                       // [kMaxChunk + 2] {hoff, hw, kcand, 0}
+    double* rv;                        // [kChunkTab] chunk edges (copy of c_chunks.rv: per-lane indexing)
+    int4* cinfo;                       // [kChunkTab] {hoff, hw, kcand, 0}
     Cand* stage;                       // [kStage]
     double2* qsum;                     // [warps][kQCap] resolved (bS_K, bS_Y) waiting for the tail (k_score_spec only)
     int2* qmeta;                       // [warps][kQCap] {r, d << 16 | step << 8 | pair}
     unsigned int* hist;                // [sh_pairs*2][kShI][kShK]
 };
-constexpr int kQCap = 160;             // per-warp queue: < 32 left over + one pixel row of a block (4 x 32)
-constexpr int kQueueBytes = (kThreads / 32) * kQCap * 24;
-constexpr int kChunkTabBytes = (kMaxChunk + 2) * 24;
-__host__ __device__ __forceinline__ size_t score_smem_bytes(int BD, int NQ, int sh_pairs, bool queue) {
-    return (size_t)BD * 4 * NQ * 8 + 16 + 128 + 64 + kChunkTabBytes + (size_t)kStage * sizeof(Cand) + (queue ? kQueueBytes : 0) +
+constexpr int kChunkTab = kMaxChunk + 4;   // shared-memory copies of the chunk tables, +inf padded
+constexpr int kChunkTabBytes = kChunkTab * 24;
+// qwarps: warps that own a tail queue (0: none), qcap: records per queue
+__host__ __device__ __forceinline__ size_t score_smem_bytes(int BD, int NQ, int sh_pairs, int qwarps, int qcap) {
+    return (size_t)BD * 4 * NQ * 8 + 32 + 128 + 64 + kChunkTabBytes + (size_t)kStage * sizeof(Cand) + (size_t)qwarps * qcap * 24 +
            (size_t)sh_pairs * 2 * kShI * kShK * 4;
 }
-__device__ __forceinline__ ScoreSmem score_smem(unsigned char* smem, int BD, int NQ, bool queue) {
+__device__ __forceinline__ ScoreSmem score_smem(unsigned char* smem, int BD, int NQ, int qwarps, int qcap) {
     ScoreSmem S;
     unsigned char* p = smem;
     S.tile = reinterpret_cast<double*>(p); p += (size_t)BD * 4 * NQ * 8;
     S.bar = reinterpret_cast<uint64_t*>(p);
     S.cnt = reinterpret_cast<unsigned int*>(p + 8);
-    S.base = reinterpret_cast<unsigned int*>(p + 12); p += 16;
+    S.base = reinterpret_cast<unsigned int*>(p + 12);
+    S.next = reinterpret_cast<unsigned int*>(p + 16); p += 32;
     S.emax = reinterpret_cast<unsigned long long*>(p); p += 128;
     S.nval = reinterpret_cast<unsigned int*>(p); p += 64;
-    S.cinfo = reinterpret_cast<int4*>(p); p += (kMaxChunk + 2) * 16;
-    S.rv = reinterpret_cast<double*>(p); p += (kMaxChunk + 2) * 8;
+    S.cinfo = reinterpret_cast<int4*>(p); p += kChunkTab * 16;
+    S.rv = reinterpret_cast<double*>(p); p += kChunkTab * 8;
     S.stage = reinterpret_cast<Cand*>(p); p += (size_t)kStage * sizeof(Cand);
     S.qsum = reinterpret_cast<double2*>(p);
-    S.qmeta = reinterpret_cast<int2*>(p + (queue ? (kThreads / 32) * kQCap * 16 : 0));
-    if (queue) p += kQueueBytes;
+    S.qmeta = reinterpret_cast<int2*>(p + (size_t)qwarps * qcap * 16);
+    p += (size_t)qwarps * qcap * 24;
     S.hist = reinterpret_cast<unsigned int*>(p);
     return S;
 }
 
 // lambda-chunk of E > 0: smallest i >= 1 with E < rv[i]; member iff rv[i-1] < E (strict, callers.py:38).
-// rv[3e+1] <= 2^e <= E < 2^(e+1) <= rv[3e+4] up to the rounding of the edge table, hence the two fix-up loops
-// (they almost never iterate).  Returns maxchunk + 1 when E is beyond the last edge.
+// hp_ctx_create checks that every third edge is an exact power of two (rv[3e+1] = 2^e, as numpy and the C
+// library both give), so for 2^e <= E < 2^(e+1) the chunk is 3e+2, 3e+3 or 3e+4: two compares, no search.
+// rv[] is padded with +inf beyond maxchunk.  Returns maxchunk + 1 when E is beyond the last edge.
 __device__ __forceinline__ int find_chunk(const double* __restrict__ rv, int mc, double E, bool& member) {
     int i = 1;
+    double lower = 0.0;
     if (E >= 1.0) {
         const int e = (int)((__double2hiint(E) >> 20) & 0x7ff) - 1023;
-        i = (e > 40) ? mc + 1 : 3 * e + 2;
-        if (i > mc + 1) i = mc + 1;
-        if (i <= mc && E >= rv[i]) { ++i; if (i <= mc && E >= rv[i]) ++i; }
+        int i0 = 3 * e + 2;
+        if (i0 > mc + 1) i0 = mc + 1;
+        const double e0 = rv[i0], e1 = rv[i0 + 1];
+        lower = rv[i0 - 1];
+        i = i0;
+        if (E >= e0) { lower = e0; i = i0 + 1; }
+        if (E >= e1) { lower = e1; i = i0 + 2; }
     }
-    while (i <= mc && E >= rv[i]) ++i;
-    while (i > 1 && E < rv[i - 1]) --i;
-    member = (i <= mc) && (E > rv[i - 1]);
+    member = (i <= mc) && (E > lower);
     return i;
 }
 
+struct TailAcc {                       // per-thread running totals of a single-pair kernel (merged at the end)
+    unsigned long long emax[2];
+    unsigned int nval[2];
+};
+
 // Per-pixel tail (callers.py:244-256 + chunk id + histograms), called by every lane of a converged warp.
 // `act`: this lane holds a pixel (r, r + d) that resolves pair `pi` at executed step `s` with donut /
-// lower-left sums SK, SY; s and pi may differ between lanes.  NPW > 0: compile-time pair count.
+// lower-left sums SK, SY; s and pi may differ between lanes.  NPW == 1: single pair, totals kept in `acc`.
 template <int NPW>
-__device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem& sh, bool act, double SK, double SY,
+__device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem& sh, TailAcc& acc, bool act, double SK, double SY,
                                             int r, int d, int s, int pi, int lane) {
     const int nexec = c_prog.nsteps_exec;
-    const int total_bins = c_chunks.total_bins;
     const int mc = c_chunks.maxchunk;
+    if (NPW == 1) pi = 0;
     bool cand = false;
     unsigned flags = 0, chk[2] = {0, 0};
     double Ev[2] = {0.0, 0.0};
@@ -245,7 +256,12 @@ __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem&
                 flags |= (fl ? HP_SF_VALID_Y : HP_SF_VALID_K);
                 Ev[fl] = E;
                 const unsigned long long eb = (unsigned long long)__double_as_longlong(E);
-                if (eb > sh.emax[pi * 2 + fl]) atomicMax(&sh.emax[pi * 2 + fl], eb);
+                if (NPW == 1) {
+                    acc.emax[fl] = eb > acc.emax[fl] ? eb : acc.emax[fl];
+                    ++acc.nval[fl];
+                } else {
+                    if (eb > sh.emax[pi * 2 + fl]) atomicMax(&sh.emax[pi * 2 + fl], eb);
+                }
                 bool member;
                 const int ci = find_chunk(sh.rv, mc, E, member);
                 if (ci > mc) atomicAdd(&A.cand_count[2], 1u);
@@ -256,21 +272,18 @@ __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem&
                     if (pi < A.sh_pairs && ci <= kShI && kb < kShK)
                         atomicAdd(&sh.hist[((pi * 2 + fl) * kShI + (ci - 1)) * kShK + kb], 1u);
                     else
-                        atomicAdd(&A.hist[(size_t)(pi * 2 + fl) * total_bins + inf.x + kb], 1u);
+                        atomicAdd(&A.hist[(size_t)(pi * 2 + fl) * c_chunks.total_bins + inf.x + kb], 1u);
                     cand |= (obs >= inf.z);
                 }
             }
         }
     }
     // warp-converged bookkeeping: valid counts per (pair, background), candidate staging
-    const int npw = NPW > 0 ? NPW : c_prog.npw;
+    if (NPW != 1) {
+        const int npw = NPW > 0 ? NPW : c_prog.npw;
 #pragma unroll
-    for (int fl = 0; fl < 2; ++fl) {
-        const bool v = (flags & (fl ? HP_SF_VALID_Y : HP_SF_VALID_K)) != 0;
-        if (NPW == 1) {
-            const unsigned mv = __ballot_sync(0xffffffffu, v);
-            if (mv && lane == 0) atomicAdd(&sh.nval[fl], (unsigned)__popc(mv));
-        } else {
+        for (int fl = 0; fl < 2; ++fl) {
+            const bool v = (flags & (fl ? HP_SF_VALID_Y : HP_SF_VALID_K)) != 0;
             for (int k = 0; k < npw; ++k) {
                 const unsigned mv = __ballot_sync(0xffffffffu, v && pi == k);
                 if (mv && lane == 0) atomicAdd(&sh.nval[k * 2 + fl], (unsigned)__popc(mv));
@@ -297,6 +310,22 @@ __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem&
         }
     }
 }
+// merge the per-thread totals of a single-pair kernel into the CTA totals (before score_epilogue)
+__device__ __forceinline__ void tail_acc_flush(const ScoreSmem& sh, const TailAcc& acc) {
+#pragma unroll
+    for (int fl = 0; fl < 2; ++fl) {
+        const unsigned nv = __reduce_add_sync(0xffffffffu, acc.nval[fl]);
+        unsigned hi = (unsigned)(acc.emax[fl] >> 32);
+        const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned lo = hi == mhi ? (unsigned)acc.emax[fl] : 0u;
+        const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
+        if ((threadIdx.x & 31) == 0) {
+            if (nv) atomicAdd(&sh.nval[fl], nv);
+            const unsigned long long m = ((unsigned long long)mhi << 32) | mlo;
+            if (m) atomicMax(&sh.emax[fl], m);
+        }
+    }
+}
 
 __device__ __forceinline__ void score_prologue(const ScoreSmem& sh, const CUtensorMap* tm, int tile_bytes, int q0, int plane0,
                                                int sh_bins) {
@@ -306,12 +335,14 @@ __device__ __forceinline__ void score_prologue(const ScoreSmem& sh, const CUtens
         mbar_expect_tx(sh.bar, (uint32_t)tile_bytes);
         tma_load_3d(sh.tile, tm, q0, 0, plane0, sh.bar);
         *sh.cnt = 0;
+        *sh.next = 0;
     }
-    for (int i = threadIdx.x; i < sh_bins; i += kThreads) sh.hist[i] = 0;
+    for (int i = threadIdx.x; i < sh_bins; i += blockDim.x) sh.hist[i] = 0;
     if (threadIdx.x < 16) { sh.emax[threadIdx.x] = 0ull; sh.nval[threadIdx.x] = 0u; }
-    for (int i = threadIdx.x; i < kMaxChunk + 2; i += kThreads) {
-        sh.rv[i] = c_chunks.rv[i];
-        sh.cinfo[i] = make_int4(c_chunks.hoff[i], c_chunks.hw[i], c_chunks.kcand[i], 0);
+    for (int i = threadIdx.x; i < kChunkTab; i += blockDim.x) {
+        const bool in = i <= c_chunks.maxchunk;
+        sh.rv[i] = in ? c_chunks.rv[i] : INFINITY;
+        sh.cinfo[i] = in ? make_int4(c_chunks.hoff[i], c_chunks.hw[i], c_chunks.kcand[i], 0) : make_int4(0, 1, 0x7fffffff, 0);
     }
     __syncthreads();
     mbar_wait(sh.bar, 0);
@@ -321,7 +352,7 @@ __device__ __forceinline__ void score_prologue(const ScoreSmem& sh, const CUtens
 __device__ __forceinline__ void score_epilogue(const ScoreArgs& A, const ScoreSmem& sh, int sh_bins) {
     __syncthreads();
     const int total_bins = c_chunks.total_bins;
-    for (int i = threadIdx.x; i < sh_bins; i += kThreads) {
+    for (int i = threadIdx.x; i < sh_bins; i += blockDim.x) {
         const unsigned v = sh.hist[i];
         if (v) {
             const int kb = i % kShK, ci = (i / kShK) % kShI + 1, lf = i / (kShK * kShI);
@@ -338,7 +369,7 @@ __device__ __forceinline__ void score_epilogue(const ScoreArgs& A, const ScoreSm
         if (threadIdx.x == 0) *sh.base = atomicAdd(&A.cand_count[0], staged);
         __syncthreads();
         const unsigned base = *sh.base;
-        for (unsigned i = threadIdx.x; i < staged; i += kThreads) {
+        for (unsigned i = threadIdx.x; i < staged; i += blockDim.x) {
             if (base + i < A.cand_cap) A.cand[base + i] = sh.stage[i];
             else atomicAdd(&A.cand_count[1], 1u);
         }
@@ -348,7 +379,7 @@ __device__ __forceinline__ void score_epilogue(const ScoreArgs& A, const ScoreSm
 // generic kernel: walks the op table of the sweep program, one pixel per thread per diagonal
 __global__ void __launch_bounds__(kThreads) k_score(const __grid_constant__ CUtensorMap tm_bal, ScoreArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const ScoreSmem sh = score_smem(smem, A.BD, A.NQ, false);
+    const ScoreSmem sh = score_smem(smem, A.BD, A.NQ, 0, 0);
     const int sh_bins = A.sh_pairs * 2 * kShI * kShK;
     const int r0 = blockIdx.x * kTR;
     const int d0 = A.dlo + blockIdx.y * A.TD;
@@ -359,6 +390,7 @@ __global__ void __launch_bounds__(kThreads) k_score(const __grid_constant__ CUte
     const int rl = threadIdx.x & (kTR - 1);
     const int r = r0 + rl;
     const int rho = rl + A.HR;                       // row inside the tile
+    TailAcc tacc{};                                  // unused by the multi-pair tail
 
     for (int dl = threadIdx.x >> 7; dl < A.TD; dl += kThreads / kTR) {
         const int d = d0 + dl;                       // warp-uniform
@@ -391,7 +423,7 @@ __global__ void __launch_bounds__(kThreads) k_score(const __grid_constant__ CUte
             }
             const int pi = c_prog.step_pi[s];
             const bool em = (s <= last) && (d >= c_prog.ww[pi]) && (c_prog.next_step[pi][lv] == s);
-            if (__any_sync(0xffffffffu, em)) emit_record<0>(A, sh, em, SK, SY, r, d, s, pi, lane);
+            if (__any_sync(0xffffffffu, em)) emit_record<0>(A, sh, tacc, em, SK, SY, r, d, s, pi, lane);
         }
     }
     score_epilogue(A, sh, sh_bins);

@@ -84,7 +84,9 @@ __host__ __device__ constexpr int hp_top_ring(unsigned m) {
     return w;
 }
 
-constexpr int kTC = 4;     // pixel block: 4 rows x kTC columns per thread
+constexpr int kTC = 2;              // pixel block: 4 rows x kTC columns per thread
+constexpr int kSpecThreads = 512;   // 16 warps share one tile (one CTA per SM)
+constexpr int kQCap = 32 + kTC * 32;   // per-warp tail queue: < 32 left over + one pixel row of every lane's block
 
 // offset (in doubles) of matrix element (row r + rho, column c + kappa) from the thread's base
 // pointer &tile[d'(c - r)][0][quad(r)]
@@ -110,7 +112,7 @@ __host__ __device__ constexpr bool hp_cell_in(unsigned mask, int a, int b) {
 // does matrix element (rho, kappa) of the block's window feed any of the 16 pixels under MASK / W?
 __host__ __device__ constexpr bool hp_strip_used(unsigned mask, int W, int rho, int kappa) {
     for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kTC; ++j) {
             const int a = rho - i, b = kappa - j;
             if (a >= -W && a <= W && b >= -W && b <= W && hp_cell_in(mask, a, b)) return true;
         }
@@ -173,12 +175,13 @@ __device__ __forceinline__ void spec_dispatch(int s, const double* base, double 
 #define HP_SPEC_MINB 1
 #endif
 template <class PG>
-__global__ void __launch_bounds__(kThreads, HP_SPEC_MINB) k_score_spec(const __grid_constant__ CUtensorMap tm_bal, ScoreArgs A) {
+__global__ void __launch_bounds__(kSpecThreads, HP_SPEC_MINB) k_score_spec(const __grid_constant__ CUtensorMap tm_bal, ScoreArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const ScoreSmem sh = score_smem(smem, A.BD, kNQ, true);
+    const ScoreSmem sh = score_smem(smem, A.BD, kNQ, kSpecThreads / 32, kQCap);
     const int sh_bins = A.sh_pairs * 2 * kShI * kShK;
     const int r0 = blockIdx.x * kTR;
-    const int d0 = A.dlo + blockIdx.y * A.TD;
+    // far diagonals first: they run the deepest levels, so the cheap tiles fill the tail of the grid
+    const int d0 = A.dlo + (int)(gridDim.y - 1 - blockIdx.y) * A.TD;
     const int plane0 = d0 - 3 - 2 * A.F;
     score_prologue(sh, &tm_bal, A.BD * 4 * kNQ * 8, (r0 - kHR) / 4, plane0, sh_bins);
 
@@ -189,9 +192,13 @@ __global__ void __launch_bounds__(kThreads, HP_SPEC_MINB) k_score_spec(const __g
     double2* qs = sh.qsum + warp * kQCap;
     int2* qm = sh.qmeta + warp * kQCap;
     int cnt = 0;                                     // warp-uniform queue fill
-    for (int kb = warp; kb * kTC < A.TD; kb += kThreads / 32) {
+    TailAcc tacc{};
+    for (;;) {
+        int kb = 0;                                  // column blocks are claimed dynamically: deep (sparse) blocks take longer
+        if (lane == 0) kb = (int)atomicAdd(sh.next, 1u);
+        kb = __shfl_sync(0xffffffffu, kb, 0);
         const int dc = d0 + kb * kTC;                // diagonal of pixel (0, 0) of the block; warp-uniform
-        if (dc - 3 > A.dhi) break;
+        if (kb * kTC >= A.TD || dc - 3 > A.dhi) break;
         unsigned lvp[4];                             // levels of the 16 pixels, one byte each, [i] = row
         int last = -1;
 #pragma unroll
@@ -257,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, HP_SPEC_MINB) k_score_spec(const __g
                     cnt -= 32;
                     const double2 v = qs[cnt + lane];
                     const int2 mt = qm[cnt + lane];
-                    emit_record<PG::npw>(A, sh, true, v.x, v.y, mt.x, mt.y >> 16, (mt.y >> 8) & 0xff, mt.y & 0xff, lane);
+                    emit_record<PG::npw>(A, sh, tacc, true, v.x, v.y, mt.x, mt.y >> 16, (mt.y >> 8) & 0xff, mt.y & 0xff, lane);
                 }
                 __syncwarp();
             }
@@ -267,8 +274,9 @@ __global__ void __launch_bounds__(kThreads, HP_SPEC_MINB) k_score_spec(const __g
         const bool act = lane < cnt;
         const double2 v = act ? qs[lane] : make_double2(0.0, 0.0);
         const int2 mt = act ? qm[lane] : make_int2(0, 0);
-        emit_record<PG::npw>(A, sh, act, v.x, v.y, mt.x, mt.y >> 16, (mt.y >> 8) & 0xff, mt.y & 0xff, lane);
+        emit_record<PG::npw>(A, sh, tacc, act, v.x, v.y, mt.x, mt.y >> 16, (mt.y >> 8) & 0xff, mt.y & 0xff, lane);
     }
+    if (PG::npw == 1) tail_acc_flush(sh, tacc);
     score_epilogue(A, sh, sh_bins);
 }
 
