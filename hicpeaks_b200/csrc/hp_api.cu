@@ -17,16 +17,15 @@
 using namespace hp;
 
 static thread_local std::string g_err;
-// the sweep program and chunk tables live in __constant__ memory (one copy per device): calls that
-// upload and use them are serialised per device
-static std::mutex g_dev_mutex[64];
 
 struct hp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};
     std::string err;
-    // chunk tables
+    // sweep program + chunk tables: pinned host mirror and the device copy the kernels read
+    Tables* h_tab = nullptr;
+    Tables* d_tab = nullptr;
     Chunks chunks{};
     std::vector<double> h_ptab;
     double* d_ptab = nullptr;
@@ -40,7 +39,7 @@ struct hp_ctx {
     unsigned char* d_lvl = nullptr;
     double *d_ir = nullptr, *d_b1 = nullptr, *d_b2 = nullptr;
     unsigned int* d_rownz = nullptr;
-    double* d_tmp = nullptr;          // plain-layout landing zone of the balanced upload
+    double* d_tmp = nullptr;          // plain-layout landing zone of the uploads (re-laid out on the device)
     void* h_stage = nullptr;          // pinned staging for uploads
     size_t cap_stage = 0;
     bool have_band = false;
@@ -49,6 +48,7 @@ struct hp_ctx {
     Prog prog{};
     std::vector<signed char> opa, opb;
     std::vector<unsigned char> opy, opr;
+    std::vector<unsigned short> ropi;
     bool scored = false, fdr_done = false;
     hp_hiccups_summary sum{};
     int dlo = 0, dhi = -1;
@@ -151,6 +151,8 @@ extern "C" int hp_ctx_create(int device, int max_chunks, const double* edges, hp
     if (rc) { g_err = ctx->err; return bail(rc); }
     const size_t tb = ctx->chunks.total_bins;
     bool ok = cudaMalloc(&ctx->d_ptab, tb * sizeof(double)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_tab, sizeof(Tables)) == cudaSuccess &&
+              cudaHostAlloc(&ctx->h_tab, sizeof(Tables), cudaHostAllocDefault) == cudaSuccess &&
               cudaMalloc(&ctx->d_lhist, (HP_MAX_STEPS + 2) * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&ctx->d_small, 48 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&ctx->d_cnt, 8 * sizeof(unsigned int)) == cudaSuccess &&
@@ -158,10 +160,11 @@ extern "C" int hp_ctx_create(int device, int max_chunks, const double* edges, hp
     if (!ok) return bail(fail(nullptr, HP_ERR_CUDA, "device allocation failed"));
     // Poisson table (universal): p[i][k] = 1 - pdtr(k, rv_i)
     for (int i = 1; i <= max_chunks; ++i) ctx->chunks.kcand[i] = 0;
-    std::lock_guard<std::mutex> lock(g_dev_mutex[device & 63]);
-    if (cudaMemcpyToSymbolAsync(c_chunks, &ctx->chunks, sizeof(Chunks), 0, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
-        return bail(fail(nullptr, HP_ERR_CUDA, "constant upload failed"));
-    k_ptab<<<(unsigned)((tb + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_ptab);
+    memset(ctx->h_tab, 0, sizeof(Tables));
+    ctx->h_tab->chunks = ctx->chunks;
+    if (cudaMemcpyAsync(ctx->d_tab, ctx->h_tab, sizeof(Tables), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+        return bail(fail(nullptr, HP_ERR_CUDA, "table upload failed"));
+    k_ptab<<<(unsigned)((tb + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_tab, ctx->d_ptab);
     ctx->h_ptab.resize(tb);
     cudaMemcpyAsync(ctx->h_ptab.data(), ctx->d_ptab, tb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -179,9 +182,10 @@ extern "C" void hp_ctx_destroy(hp_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_ptab, ctx->d_raw, ctx->d_bal, ctx->d_lvl, ctx->d_ir, ctx->d_b1, ctx->d_b2, ctx->d_rownz,
                     ctx->d_lhist, ctx->d_betab, ctx->d_hist, ctx->d_qtab, ctx->d_small, ctx->d_cnt, ctx->d_numbin,
-                    ctx->d_cand, ctx->d_surv, ctx->d_dump, ctx->d_tmp};
+                    ctx->d_cand, ctx->d_surv, ctx->d_dump, ctx->d_tmp, ctx->d_tab};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -260,9 +264,11 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
     for (int d = 0; d < num; ++d) hir[d] = d >= bf ? b->ir[d - bf] : 0.0;
     CK(cudaMemcpyAsync(ctx->d_tmp, hbal, plane * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_rownz, 0, (size_t)n * sizeof(unsigned int), ctx->stream));
-    k_relayout<<<dim3((pitch + 255) / 256, num), 256, 0, ctx->stream>>>(ctx->d_tmp, ctx->d_bal, ctx->d_rownz, pitch, num);
+    k_relayout<double><<<dim3((pitch + 255) / 256, num), 256, 0, ctx->stream>>>(ctx->d_tmp, ctx->d_bal, ctx->d_rownz, pitch, num);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(ctx->d_raw, hraw, plane * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_tmp, hraw, plane * 4, cudaMemcpyHostToDevice, ctx->stream));
+    k_relayout<int><<<dim3((pitch + 255) / 256, num), 256, 0, ctx->stream>>>((const int*)ctx->d_tmp, ctx->d_raw, nullptr, pitch, num);
+    CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->d_ir, hir, (size_t)num * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_b1, b->b1, n * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_b2, b->b2, n * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -277,7 +283,7 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
 static int build_program(hp_ctx* ctx, const hp_hiccups_params& P) {
     Prog& G = ctx->prog;
     memset(&G, 0, sizeof(G));
-    ctx->opa.clear(); ctx->opb.clear(); ctx->opy.clear(); ctx->opr.clear();
+    ctx->opa.clear(); ctx->opb.clear(); ctx->opy.clear(); ctx->opr.clear(); ctx->ropi.clear();
     G.npw = P.npw; G.thr = P.min_local_reads;
     int minp = P.pw[0];
     for (int i = 0; i < P.npw; ++i) { G.pw[i] = P.pw[i]; G.ww[i] = P.ww[i]; minp = std::min(minp, P.pw[i]); }
@@ -301,6 +307,7 @@ static int build_program(hp_ctx* ctx, const hp_hiccups_params& P) {
                 if (abs(a) <= p && abs(b) <= p) continue;
                 const bool isy = a > 0 && b < 0;
                 const bool isr = isy && (!limit || (p == minp && g > last_w));
+                if (isr) ctx->ropi.push_back((unsigned short)ctx->opa.size());
                 ctx->opa.push_back((signed char)a); ctx->opb.push_back((signed char)b);
                 ctx->opy.push_back(isy); ctx->opr.push_back(isr);
                 nr += isr;
@@ -315,44 +322,38 @@ static int build_program(hp_ctx* ctx, const hp_hiccups_params& P) {
     return HP_OK;
 }
 
-static int make_map(hp_ctx* ctx, CUtensorMap* map, CUtensorMapDataType dt, int esize, void* base, int box_r, int box_d) {
-    cuuint64_t dims[2] = {(cuuint64_t)ctx->pitch, (cuuint64_t)ctx->num};
-    cuuint64_t strides[1] = {(cuuint64_t)ctx->pitch * esize};
-    cuuint32_t box[2] = {(cuuint32_t)box_r, (cuuint32_t)box_d};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = ctx->encode(map, dt, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(ctx, HP_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
-    return HP_OK;
-}
-
-// quad-interleaved balanced plane: dims (row quad, row & 3, diagonal)
-static int make_map_bal(hp_ctx* ctx, CUtensorMap* map, int box_q, int box_d) {
+// quad-interleaved plane: dims (row quad, row & 3, diagonal)
+static int make_map_plane(hp_ctx* ctx, CUtensorMap* map, CUtensorMapDataType dt, int esize, void* base, int box_q, int box_d) {
     cuuint64_t dims[3] = {(cuuint64_t)ctx->pitch / 4, 4, (cuuint64_t)ctx->num};
-    cuuint64_t strides[2] = {(cuuint64_t)ctx->pitch / 4 * 8, (cuuint64_t)ctx->pitch * 8};
+    cuuint64_t strides[2] = {(cuuint64_t)ctx->pitch / 4 * esize, (cuuint64_t)ctx->pitch * esize};
     cuuint32_t box[3] = {(cuuint32_t)box_q, 4, (cuuint32_t)box_d};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, ctx->d_bal, dims, strides, box, es,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(ctx, HP_ERR_CUDA, "cuTensorMapEncodeTiled (balanced plane) failed: " + std::to_string((int)r));
+    CUresult r = ctx->encode(map, dt, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, HP_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
     return HP_OK;
 }
 
 // ---- specialised score kernels: sweep programs compiled in (hp_score_spec.cuh) --------------------
 struct SpecKernel {
-    bool (*matches)(const Prog&, int, const signed char*, const signed char*, const unsigned char*);
+    bool (*matches)(const Prog&, int, const signed char*, const signed char*, const unsigned char*, const unsigned char*);
     int (*launch)(hp_ctx*, const CUtensorMap&, const ScoreArgs&, dim3, size_t, cudaStream_t);
+    int (*launch_levels)(hp_ctx*, const CUtensorMap&, const LevelArgs&, dim3, size_t, cudaStream_t);
     const char* name;
 };
+template <class PG>
+static int launch_levels_spec(hp_ctx* ctx, const CUtensorMap& tm, const LevelArgs& A, dim3 grid, size_t smem, cudaStream_t st) {
+    CK(cudaFuncSetAttribute(k_levels_spec<PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_levels_spec<PG><<<grid, kThreads, smem, st>>>(tm, A);
+    return HP_OK;
+}
 template <class PG>
 static int launch_spec(hp_ctx* ctx, const CUtensorMap& tm, const ScoreArgs& A, dim3 grid, size_t smem, cudaStream_t st) {
     CK(cudaFuncSetAttribute(k_score_spec<PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_score_spec<PG><<<grid, kSpecThreads, smem, st>>>(tm, A);
     return HP_OK;
 }
-#define HP_SPEC(name, ...) {spec_matches<SProg<__VA_ARGS__>>, launch_spec<SProg<__VA_ARGS__>>, name}
+#define HP_SPEC(name, ...) {spec_matches<SProg<__VA_ARGS__>>, launch_spec<SProg<__VA_ARGS__>>, launch_levels_spec<SProg<__VA_ARGS__>>, name}
 static const SpecKernel g_specs[] = {
     HP_SPEC("p2w5", 10, 1, 2, 5),
 #ifndef HP_FAST_BUILD       // development builds compile one program only (each takes about a minute)
@@ -363,7 +364,7 @@ static const SpecKernel g_specs[] = {
 };
 static const SpecKernel* find_spec(hp_ctx* ctx, int nexec) {
     for (const SpecKernel& k : g_specs)
-        if (k.matches(ctx->prog, nexec, ctx->opa.data(), ctx->opb.data(), ctx->opy.data())) return &k;
+        if (k.matches(ctx->prog, nexec, ctx->opa.data(), ctx->opb.data(), ctx->opy.data(), ctx->opr.data())) return &k;
     return nullptr;
 }
 
@@ -389,7 +390,6 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     if (minww != ctx->bal_first) return fail(ctx, HP_ERR_INVALID, "band was uploaded with bal_first != min(ww)");
     if (!(P.sig >= 0.0)) return fail(ctx, HP_ERR_INVALID, "sig must be >= 0");
     CK(cudaSetDevice(ctx->device));
-    std::lock_guard<std::mutex> lock(g_dev_mutex[ctx->device & 63]);
     ctx->scored = false; ctx->fdr_done = false;
     ctx->prm = P;
     int rc = build_program(ctx, P);
@@ -407,31 +407,45 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     const int nops = (int)ctx->opa.size();
     int launches = 0;
 
+    // ---- tables (program, cell list) -> device ------------------------------------------------------
+    const bool force_generic = (P.flags & HP_PF_GENERIC_KERNEL) != 0;
+    const bool spec_ok = !force_generic && num <= 32767;
+    Tables& HT = *ctx->h_tab;
+    G.nsteps_exec = G.nsteps;
+    HT.prog = G;
+    memcpy(HT.opa, ctx->opa.data(), nops);
+    memcpy(HT.opb, ctx->opb.data(), nops);
+    memcpy(HT.opy, ctx->opy.data(), nops);
+    memcpy(HT.ropi, ctx->ropi.data(), ctx->ropi.size() * sizeof(unsigned short));
+    CK(cudaMemcpyAsync(ctx->d_tab, &HT, sizeof(Tables), cudaMemcpyHostToDevice, st));
+
     // ---- K1: levels --------------------------------------------------------------------------
-    const int F1 = P.maxww, TD1 = 32;
-    const int BR1 = (kTR + F1 + 3) / 4 * 4, BD1 = TD1 + 2 * F1;
-    {
-        std::vector<int> roff;
-        for (int i = 0; i < nops; ++i)
-            if (ctx->opr[i]) roff.push_back((ctx->opb[i] - ctx->opa[i]) * BR1 + ctx->opa[i]);
-        G.nsteps_exec = G.nsteps;
-        CK(cudaMemcpyToSymbolAsync(c_prog, &G, sizeof(Prog), 0, cudaMemcpyHostToDevice, st));
-        if (!roff.empty()) CK(cudaMemcpyToSymbolAsync(c_roff, roff.data(), roff.size() * sizeof(int), 0, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyToSymbolAsync(c_opa, ctx->opa.data(), nops, 0, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyToSymbolAsync(c_opb, ctx->opb.data(), nops, 0, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyToSymbolAsync(c_opy, ctx->opy.data(), nops, 0, cudaMemcpyHostToDevice, st));
-    }
-    CUtensorMap tm_raw;
-    rc = make_map(ctx, &tm_raw, CU_TENSOR_MAP_DATA_TYPE_INT32, 4, ctx->d_raw, BR1, BD1);
-    if (rc) return rc;
+    const int F1 = P.maxww;
     CK(cudaEventRecord(ctx->ev[0], st));
     CK(cudaMemsetAsync(ctx->d_lhist, 0, (HP_MAX_STEPS + 2) * sizeof(unsigned long long), st));
     {
-        LevelArgs A{ctx->d_lvl, ctx->d_lhist, n, pitch, dlo, dhi, F1, BR1, BD1, TD1};
-        const size_t smem = (size_t)BR1 * BD1 * 4 + 16 + (G.nsteps + 2) * 4;
-        CK(cudaFuncSetAttribute(k_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((n + kTR - 1) / kTR, (dhi - dlo + TD1) / TD1);
-        k_levels<<<grid, kThreads, smem, st>>>(tm_raw, A);
+        const SpecKernel* lspec = spec_ok ? find_spec(ctx, G.nsteps) : nullptr;
+        LevelArgs A{};
+        A.tab = ctx->d_tab; A.lvl = ctx->d_lvl; A.hist = ctx->d_lhist;
+        A.n = n; A.pitch = pitch; A.dlo = dlo; A.dhi = dhi; A.F = F1;
+        CUtensorMap tm_raw;
+        if (lspec) {
+            A.TD = 64; A.BD = A.TD + 3 + 2 * F1; A.NQ = kNQL;
+            rc = make_map_plane(ctx, &tm_raw, CU_TENSOR_MAP_DATA_TYPE_INT32, 4, ctx->d_raw, A.NQ, A.BD);
+            if (rc) return rc;
+            const size_t smem = (size_t)A.BD * 4 * A.NQ * 4 + 16 + (G.nsteps + 2) * 4;
+            dim3 grid((n + kTR - 1) / kTR, (dhi - dlo + 3 + A.TD) / A.TD);
+            rc = lspec->launch_levels(ctx, tm_raw, A, grid, smem, st);
+            if (rc) return rc;
+        } else {
+            A.TD = 32; A.BD = A.TD + 2 * F1; A.NQ = ((kTR + F1 + 3) / 4 + 3) & ~3;   // box rows: a multiple of 16 bytes
+            rc = make_map_plane(ctx, &tm_raw, CU_TENSOR_MAP_DATA_TYPE_INT32, 4, ctx->d_raw, A.NQ, A.BD);
+            if (rc) return rc;
+            const size_t smem = (size_t)A.BD * 4 * A.NQ * 4 + 16 + (G.nsteps + 2) * 4;
+            CK(cudaFuncSetAttribute(k_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dim3 grid((n + kTR - 1) / kTR, (dhi - dlo + A.TD) / A.TD);
+            k_levels<<<grid, kThreads, smem, st>>>(tm_raw, A);
+        }
         ++launches;
         CK(cudaGetLastError());
     }
@@ -491,7 +505,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     // ---- tables for K2 ------------------------------------------------------------------------
     const int F = frozen;
     const int sh_pairs = std::min(P.npw, kShPairs);
-    const SpecKernel* spec = (P.flags & HP_PF_GENERIC_KERNEL) ? nullptr : (num <= 32767 ? find_spec(ctx, nexec) : nullptr);   // reserved bit 0: force the generic kernel
+    const SpecKernel* spec = spec_ok ? find_spec(ctx, nexec) : nullptr;
     ScoreArgs A{};
     size_t smem = 0;
     dim3 grid;
@@ -513,7 +527,6 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     }
     if (smem > 227 * 1024) return fail(ctx, HP_ERR_INVALID, "tile does not fit shared memory");
     {
-        CK(cudaMemcpyToSymbolAsync(c_prog, &G, sizeof(Prog), 0, cudaMemcpyHostToDevice, st));
         // candidate thresholds for this sig (host copy of the universal Poisson table)
         Chunks& C = ctx->chunks;
         const double lim = P.sig * (1.0 + 1e-9) + 1e-300;
@@ -523,10 +536,12 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
             while (k < C.hw[i] && !(p[k] <= lim)) ++k;
             C.kcand[i] = k;
         }
-        CK(cudaMemcpyToSymbolAsync(c_chunks, &C, sizeof(Chunks), 0, cudaMemcpyHostToDevice, st));
+        HT.prog = G;                       // now with the executed steps and the resolve tables
+        HT.chunks = C;
+        CK(cudaMemcpyAsync(ctx->d_tab, &HT, offsetof(Tables, opa), cudaMemcpyHostToDevice, st));
     }
     const size_t tb = ctx->chunks.total_bins;
-    CK(ensure(&ctx->d_betab, &ctx->cap_betab, (size_t)2 * nexec * num));
+    CK(ensure(&ctx->d_betab, &ctx->cap_betab, (size_t)(1 + 2 * F) * 2 * nexec * num));
     CK(ensure(&ctx->d_hist, &ctx->cap_hist, (size_t)P.npw * 2 * tb));
     CK(ensure(&ctx->d_qtab, &ctx->cap_qtab, (size_t)P.npw * 2 * tb));
     if (P.dump) {
@@ -538,10 +553,10 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     size_t want = std::min<size_t>((size_t)total * P.npw, (size_t)((double)total * P.npw * std::max(0.15, 1.5 * P.sig)) + 65536);
     want = std::max<size_t>(want, 65536);
     CUtensorMap tm_bal;
-    rc = make_map_bal(ctx, &tm_bal, A.NQ, A.BD);
+    rc = make_map_plane(ctx, &tm_bal, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, ctx->d_bal, A.NQ, A.BD);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev[2], st));
-    k_betab<<<dim3((num + 127) / 128, nexec), 128, 0, st>>>(ctx->d_ir, ctx->d_betab, num, ctx->bal_first, nexec);
+    k_betab<<<dim3((num + 127) / 128, nexec, 1 + 2 * F), 128, 0, st>>>(ctx->d_tab, ctx->d_ir, ctx->d_betab, num, ctx->bal_first, nexec, F);
     ++launches;
     unsigned int cnt[4] = {0, 0, 0, 0};
     unsigned long long small[48];
@@ -550,13 +565,17 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
         CK(cudaMemsetAsync(ctx->d_hist, 0, (size_t)P.npw * 2 * tb * sizeof(unsigned int), st));
         CK(cudaMemsetAsync(ctx->d_small, 0, 48 * sizeof(unsigned long long), st));
         CK(cudaMemsetAsync(ctx->d_cnt, 0, 8 * sizeof(unsigned int), st));
-        A.raw = ctx->d_raw; A.lvl = ctx->d_lvl; A.ir = ctx->d_ir; A.b1 = ctx->d_b1; A.b2 = ctx->d_b2;
+        A.tab = ctx->d_tab; A.raw = ctx->d_raw; A.lvl = ctx->d_lvl; A.ir = ctx->d_ir; A.b1 = ctx->d_b1; A.b2 = ctx->d_b2;
         A.betab = ctx->d_betab; A.hist = ctx->d_hist; A.emax_bits = ctx->d_small; A.nvalid = ctx->d_small + 16;
         A.cand = ctx->d_cand; A.cand_count = ctx->d_cnt;
         A.cand_cap = (unsigned)std::min<size_t>(ctx->cap_cand, 0xffffffffu);
         A.dump = P.dump ? ctx->d_dump : nullptr; A.plane = (long long)ctx->plane;
         A.n = n; A.num = num; A.pitch = pitch; A.dlo = dlo; A.dhi = dhi; A.F = F;
         A.bal_first = ctx->bal_first; A.sh_pairs = sh_pairs;
+        A.nexec = nexec; A.npw = P.npw; A.dspan = G.dspan; A.maxchunk = ctx->chunks.maxchunk; A.total_bins = ctx->chunks.total_bins;
+        for (int i = 0; i < P.npw; ++i) A.ww[i] = P.ww[i];
+        for (int k = 0; k < nexec; ++k) { A.step_pi[k] = (unsigned char)G.step_pi[k]; A.step_lo[k] = G.step_lo[k]; }
+        memcpy(A.last_need, G.last_need, sizeof(A.last_need));
         if (spec) {
             rc = spec->launch(ctx, tm_bal, A, grid, smem, st);
             if (rc) return rc;
@@ -617,14 +636,12 @@ extern "C" int hp_hiccups_fdr(hp_ctx* ctx, const int32_t* numbin_override, hp_hi
             nb[i * 2 + fl] = v;
             maxnb = std::max(maxnb, v);
         }
-    std::lock_guard<std::mutex> lock(g_dev_mutex[ctx->device & 63]);
-    CK(cudaMemcpyToSymbolAsync(c_chunks, &ctx->chunks, sizeof(Chunks), 0, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(ctx->ev[4], st));
     CK(cudaMemcpyAsync(ctx->d_numbin, nb, sizeof(nb), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctx->d_small + 32, 0, 16 * sizeof(unsigned long long), st));
     int launches = 0;
     if (maxnb > 0) {
-        k_bh<<<dim3(maxnb, P.npw * 2), kThreads, 0, st>>>(ctx->d_hist, ctx->d_ptab, ctx->d_qtab, ctx->d_numbin);
+        k_bh<<<dim3(maxnb, P.npw * 2), kThreads, 0, st>>>(ctx->d_tab, ctx->d_hist, ctx->d_ptab, ctx->d_qtab, ctx->d_numbin);
         ++launches;
         CK(cudaGetLastError());
     }
@@ -635,7 +652,7 @@ extern "C" int hp_hiccups_fdr(hp_ctx* ctx, const int32_t* numbin_override, hp_hi
         CK(cudaMemsetAsync(ctx->d_cnt + 4, 0, 4 * sizeof(unsigned int), st));
         CK(cudaMemsetAsync(ctx->d_small + 32, 0, 16 * sizeof(unsigned long long), st));
         FilterArgs A{};
-        A.cand = ctx->d_cand; A.ncand = ctx->ncand; A.ptab = ctx->d_ptab; A.qtab = ctx->d_qtab; A.numbin = ctx->d_numbin;
+        A.tab = ctx->d_tab; A.cand = ctx->d_cand; A.ncand = ctx->ncand; A.ptab = ctx->d_ptab; A.qtab = ctx->d_qtab; A.numbin = ctx->d_numbin;
         A.bal = ctx->d_bal; A.out = ctx->d_surv; A.out_count = ctx->d_cnt + 4;
         A.out_cap = (unsigned)std::min<size_t>(ctx->cap_surv, 0xffffffffu);
         A.nreject = ctx->d_small + 32; A.sig = P.sig; A.pitch = ctx->pitch;
@@ -705,10 +722,14 @@ extern "C" int hp_dump_levels(hp_ctx* ctx, uint8_t* out, int64_t capacity) {
     if (capacity < (int64_t)ctx->num * ctx->n) return fail(ctx, HP_ERR_CAPACITY, "level buffer too small");
     CK(cudaSetDevice(ctx->device));
     memset(out, kLvlNone, (size_t)ctx->num * ctx->n);
-    const int rows = ctx->dhi - ctx->dlo + 1;
-    CK(cudaMemcpy2DAsync(out + (size_t)ctx->dlo * ctx->n, ctx->n, ctx->d_lvl + (size_t)ctx->dlo * ctx->pitch, ctx->pitch,
-                         ctx->n, rows, cudaMemcpyDeviceToHost, ctx->stream));
+    const int rows = ctx->dhi - ctx->dlo + 1, pitch = ctx->pitch;
+    std::vector<unsigned char> tmp((size_t)rows * pitch);
+    CK(cudaMemcpyAsync(tmp.data(), ctx->d_lvl + (size_t)ctx->dlo * pitch, tmp.size(), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < rows; ++k) {
+        uint8_t* o = out + (size_t)(ctx->dlo + k) * ctx->n;
+        for (int64_t r = 0; r < ctx->n; ++r) o[r] = tmp[qidx(k, (int)r, pitch)];
+    }
     return HP_OK;
 }
 

@@ -14,6 +14,7 @@ constexpr int kThreads = 256;
 constexpr int kHR = 16;           // row halo of a balanced tile: >= maxww of the specialised kernels and a multiple of 8
                                   // (a TMA box must start on a 16-byte boundary: an even row quad)
 constexpr int kNQ = (kTR + 2 * kHR) / 4;   // row quads of a balanced tile (40)
+constexpr int kNQL = (kTR + 16) / 4;       // row quads of a raw tile of the specialised level kernel (rows r .. r + maxww + 3)
 constexpr int kMaxOps = 6144;     // stencil offsets of one whole sweep program
 constexpr int kMaxROps = 512;     // offsets that feed Reads (<= maxww^2)
 constexpr int kMaxChunk = 64;     // lambda-chunk cap
@@ -44,16 +45,26 @@ struct Chunks {                   // lambda-chunk geometry (callers.py:30-38) + 
     int maxchunk, total_bins;
 };
 
+struct Tables {                   // per-context tables in global memory (one H2D copy per upload)
+    Prog prog;
+    Chunks chunks;
+    signed char opa[kMaxOps];     // row / column offset of every cell the sweep adds, in fp64 addition order
+    signed char opb[kMaxOps];
+    unsigned char opy[kMaxOps];   // the cell also feeds the lower-left (Y) sums
+    unsigned short ropi[kMaxROps];  // indices of the cells that feed Reads
+};
+
 struct Cand {                     // 32 B: a pixel whose Poisson p can pass sig for K or Y
     int r, d, obs;
     unsigned char pair, flags, chunk_k, chunk_y;
     double e_k, e_y;
 };
 
-// Balanced plane in HBM: "quad-interleaved" diagonal planes.  Element (r, r + d) lives at
-// [d][r & 3][r >> 2] (sub-plane pitch = pitch / 4): a thread that owns four consecutive matrix rows
-// then reads consecutive shared-memory words across the lanes of a warp for every row offset.
-__host__ __device__ __forceinline__ size_t bal_index(int d, int r, int pitch) {
+// Band planes in HBM (raw counts, balanced values, levels): "quad-interleaved" diagonal planes.
+// Element (r, r + d) lives at [d][r & 3][r >> 2] (sub-plane pitch = pitch / 4): a thread that owns four
+// consecutive matrix rows then reads consecutive shared-memory words across the lanes of a warp for
+// every row offset, and a 3-D TMA box (row quads, 4, diagonals) lands a tile in that order.
+__host__ __device__ __forceinline__ size_t qidx(int d, int r, int pitch) {
     return (size_t)d * pitch + (size_t)(r & 3) * (pitch >> 2) + (r >> 2);
 }
 

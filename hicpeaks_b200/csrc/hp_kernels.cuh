@@ -7,66 +7,69 @@
 
 namespace hp {
 
-__constant__ Prog c_prog;
-__constant__ Chunks c_chunks;
-__constant__ signed char c_opa[kMaxOps];
-__constant__ signed char c_opb[kMaxOps];
-__constant__ unsigned char c_opy[kMaxOps];
-__constant__ int c_roff[kMaxROps];           // level kernel: tile offsets of the Reads ops
-
 // ============================================================================================
-// K1  level kernel -- callers.py:197-198 (Reads accumulation) + :203-206 (Reads >= min_local_reads)
+// K1  level kernel (generic) -- callers.py:197-198 (Reads accumulation) + :203-206 (Reads >= min_local_reads)
 // For every non-zero band pixel: the first sweep step s* after which the raw lower-left sum reaches
 // the threshold.  Integer work on the raw plane only; one TMA tile (+ lower-left halo) per CTA.
+// The specialised version for compiled-in sweep programs is k_levels_spec (hp_score_spec.cuh).
 // ============================================================================================
 struct LevelArgs {
-    unsigned char* lvl;            // [num][pitch]
+    const Tables* tab;
+    unsigned char* lvl;            // quad-interleaved [num][pitch]
     unsigned long long* hist;      // [nsteps + 1]   (index nsteps = never)
-    int n, pitch, dlo, dhi, F, BR, BD, TD;
+    int n, pitch, dlo, dhi, F, BD, TD, NQ;
 };
+
+__device__ __forceinline__ void level_prologue(int* tile, uint64_t* bar, const CUtensorMap* tm, int tile_bytes, int q0, int plane0) {
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, (uint32_t)tile_bytes);
+        tma_load_3d(tile, tm, q0, 0, plane0, bar);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+}
 
 __global__ void __launch_bounds__(kThreads) k_levels(const __grid_constant__ CUtensorMap tm_raw, LevelArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    int* tile = reinterpret_cast<int*>(smem);
-    const int tile_bytes = A.BR * A.BD * 4;
+    const Tables& T = *A.tab;
+    int* tile = reinterpret_cast<int*>(smem);                       // [BD][4][NQ], rows r0.., planes d0 - 2F..
+    const int tile_bytes = A.BD * 4 * A.NQ * 4;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + tile_bytes);
     unsigned int* sh_hist = reinterpret_cast<unsigned int*>(smem + tile_bytes + 16);
 
     const int r0 = blockIdx.x * kTR;
     const int d0 = A.dlo + blockIdx.y * A.TD;
-    const int nsteps = c_prog.nsteps;
+    const int nsteps = T.prog.nsteps;
     for (int i = threadIdx.x; i <= nsteps; i += kThreads) sh_hist[i] = 0;
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, (uint32_t)tile_bytes);
-        tma_load_2d(tile, &tm_raw, r0, d0 - 2 * A.F, bar);
-    }
-    __syncthreads();
-    mbar_wait(bar, 0);
+    level_prologue(tile, bar, &tm_raw, tile_bytes, r0 / 4, d0 - 2 * A.F);
 
     const int rl = threadIdx.x & (kTR - 1);
     const int r = r0 + rl;
-    const long long thr = c_prog.thr;
+    const long long thr = T.prog.thr;
     for (int dl = threadIdx.x >> 7; dl < A.TD; dl += kThreads / kTR) {
         const int d = d0 + dl;
         if (d > A.dhi || r >= A.n) continue;
-        const int* ctr = tile + (dl + 2 * A.F) * A.BR + rl;
         unsigned char out = kLvlNone;
-        if (r + d < A.n && *ctr != 0) {
+        if (r + d < A.n && tile[((dl + 2 * A.F) * 4 + (rl & 3)) * A.NQ + (rl >> 2)] != 0) {
             long long R = 0;
             int opi = 0;
             out = kLvlNever;
             for (int s = 0; s < nsteps; ++s) {
-                const int e = c_prog.rop_end[s];
-                for (; opi < e; ++opi) R += ctr[c_roff[opi]];
+                const int e = T.prog.rop_end[s];
+                for (; opi < e; ++opi) {
+                    const int k = T.ropi[opi];
+                    const int a = T.opa[k], b = T.opb[k], rr = rl + a;
+                    R += tile[((dl + 2 * A.F + b - a) * 4 + (rr & 3)) * A.NQ + (rr >> 2)];
+                }
                 if (R >= thr) { out = (unsigned char)s; break; }
             }
             const int slot = (out == kLvlNever) ? nsteps : out;
             const unsigned m = __match_any_sync(__activemask(), slot);
             if ((threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&sh_hist[slot], __popc(m));
         }
-        A.lvl[(size_t)d * A.pitch + r] = out;
+        A.lvl[qidx(d, r, A.pitch)] = out;
     }
     __syncthreads();
     for (int i = threadIdx.x; i <= nsteps; i += kThreads)
@@ -78,38 +81,45 @@ __global__ void __launch_bounds__(kThreads) k_levels(const __grid_constant__ CUt
 // up to and including step s (callers.py:178,182,189-191).  Away from the chromosome ends the sum
 // only depends on the diagonal, so it never touches the band.
 // ============================================================================================
-__global__ void k_betab(const double* __restrict__ ir, double* __restrict__ betab, int num, int bal_first,
-                        int nsteps_exec) {
+// Layout betab[z][fl][s][d]: z = 0 interior pixels; z = 1 + r for the rows r < F next to the start of the
+// chromosome (cells with row < 0 or column < 0 drop out); z = 1 + F + e for the columns c = n - 1 - e, e < F,
+// next to its end (cells with row >= n or column >= n drop out).  Pixels near both ends take edge_be().
+__global__ void k_betab(const Tables* __restrict__ tab, const double* __restrict__ ir, double* __restrict__ betab, int num,
+                        int bal_first, int nsteps_exec, int F) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
-    const int s = blockIdx.y;
+    const int s = blockIdx.y, z = blockIdx.z;
     if (d >= num || s >= nsteps_exec) return;
+    int amin = -128, bmin = -128, amax = 127, bmax = 127;
+    if (z >= 1 && z <= F) { const int r = z - 1; amin = -r; bmin = -(r + d); }
+    if (z > F) { const int e = z - F - 1; amax = e + d; bmax = e; }
     double ek = 0.0, ey = 0.0;
-    const int e = c_prog.op_end[s];
+    const int e = tab->prog.op_end[s];
     for (int i = 0; i < e; ++i) {
-        const int dd = d + c_opb[i] - c_opa[i];
-        if (dd >= bal_first && dd < num) {
+        const int a = tab->opa[i], b = tab->opb[i];
+        const int dd = d + b - a;
+        if (dd >= bal_first && dd < num && a >= amin && a <= amax && b >= bmin && b <= bmax) {
             const double v = ir[dd];
             ek = __dadd_rn(ek, v);
-            if (c_opy[i]) ey = __dadd_rn(ey, v);
+            if (tab->opy[i]) ey = __dadd_rn(ey, v);
         }
     }
-    betab[(size_t)s * num + d] = ek;
-    betab[(size_t)(nsteps_exec + s) * num + d] = ey;
+    betab[((size_t)(z * 2 + 0) * nsteps_exec + s) * num + d] = ek;
+    betab[((size_t)(z * 2 + 1) * nsteps_exec + s) * num + d] = ey;
 }
 
 // same sum for a pixel next to a chromosome end (some offsets fall outside [0, n)^2)
-__device__ __noinline__ void edge_be(const double* __restrict__ ir, int r, int d, int n, int num, int bal_first,
-                                     int s, double& ek, double& ey) {
+__device__ __noinline__ void edge_be(const Tables* __restrict__ tab, const double* __restrict__ ir, int r, int d, int n, int num,
+                                     int bal_first, int s, double& ek, double& ey) {
     ek = 0.0; ey = 0.0;
-    const int e = c_prog.op_end[s];
+    const int e = tab->prog.op_end[s];
     const int c = r + d;
     for (int i = 0; i < e; ++i) {
-        const int a = c_opa[i], b = c_opb[i];
+        const int a = tab->opa[i], b = tab->opb[i];
         const int dd = d + b - a, rr = r + a, cc = c + b;
         if (rr >= 0 && rr < n && cc >= 0 && cc < n && dd >= bal_first && dd < num) {
             const double v = ir[dd];
             ek = __dadd_rn(ek, v);
-            if (c_opy[i]) ey = __dadd_rn(ey, v);
+            if (tab->opy[i]) ey = __dadd_rn(ey, v);
         }
     }
 }
@@ -123,12 +133,13 @@ __device__ __noinline__ void edge_be(const double* __restrict__ ir, int r, int d
 // (hp_score_spec.cuh: compile-time unrolled sweep programs, 4x4 register blocks).
 // ============================================================================================
 struct ScoreArgs {
-    const int* raw;
-    const unsigned char* lvl;
+    const Tables* tab;
+    const int* raw;                    // quad-interleaved
+    const unsigned char* lvl;          // quad-interleaved
     const double* ir;
     const double* b1;
     const double* b2;
-    const double* betab;               // [2][nsteps_exec][num]
+    const double* betab;               // [1 + 2F][2][nsteps_exec][num], see k_betab
     unsigned int* hist;                // [npw*2][total_bins]
     unsigned long long* emax_bits;     // [npw*2]
     unsigned long long* nvalid;        // [npw*2]
@@ -138,7 +149,12 @@ struct ScoreArgs {
     double* dump;                      // optional [npw*2][3][num*pitch]
     long long plane;
     int n, num, pitch, dlo, dhi, F, BD, TD, bal_first, sh_pairs;
-    int HR, NQ;                        // row halo (multiple of 4) and row quads of the tile: NQ = (kTR + 2 HR) / 4
+    int HR, NQ;                        // row halo (multiple of 8) and row quads of the tile: NQ = (kTR + 2 HR) / 4
+    // hot scalars and step tables of the program, in the kernel parameter (constant) bank
+    int nexec, npw, dspan, maxchunk, total_bins;
+    int ww[HP_MAX_PW];
+    unsigned char step_pi[HP_MAX_STEPS], step_lo[HP_MAX_STEPS];
+    unsigned char last_need[HP_MAX_WW + 1][HP_MAX_STEPS + 2];
 };
 
 struct ScoreSmem {                     // carve-up of the dynamic shared memory of a score CTA
@@ -215,22 +231,24 @@ struct TailAcc {                       // per-thread running totals of a single-
 template <int NPW>
 __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem& sh, TailAcc& acc, bool act, double SK, double SY,
                                             int r, int d, int s, int pi, int lane) {
-    const int nexec = c_prog.nsteps_exec;
-    const int mc = c_chunks.maxchunk;
+    const int nexec = A.nexec;
+    const int mc = A.maxchunk;
     if (NPW == 1) pi = 0;
     bool cand = false;
     unsigned flags = 0, chk[2] = {0, 0};
     double Ev[2] = {0.0, 0.0};
     int obs = 0;
     if (act) {
-        obs = A.raw[(size_t)d * A.pitch + r];
+        obs = A.raw[qidx(d, r, A.pitch)];
         double be[2];
-        const bool edge = (r < A.F) || (r + d >= A.n - A.F);
-        if (edge) {
-            edge_be(A.ir, r, d, A.n, A.num, A.bal_first, s, be[0], be[1]);
+        const bool top = r < A.F, end = r + d >= A.n - A.F;
+        if (top && end) {                      // chromosome shorter than the band + two windows: walk the cell list
+            edge_be(A.tab, A.ir, r, d, A.n, A.num, A.bal_first, s, be[0], be[1]);
         } else {
-            be[0] = A.betab[(size_t)s * A.num + d];
-            be[1] = A.betab[(size_t)(nexec + s) * A.num + d];
+            const int z = top ? 1 + r : end ? 1 + A.F + (A.n - 1 - r - d) : 0;
+            const double* bt = A.betab + ((size_t)(z * 2) * nexec + s) * A.num + d;
+            be[0] = bt[0];
+            be[1] = bt[(size_t)nexec * A.num];
         }
         const double ird = A.ir[d], bb1 = A.b1[r], bb2 = A.b2[r + d];
 #pragma unroll
@@ -272,7 +290,7 @@ __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem&
                     if (pi < A.sh_pairs && ci <= kShI && kb < kShK)
                         atomicAdd(&sh.hist[((pi * 2 + fl) * kShI + (ci - 1)) * kShK + kb], 1u);
                     else
-                        atomicAdd(&A.hist[(size_t)(pi * 2 + fl) * c_chunks.total_bins + inf.x + kb], 1u);
+                        atomicAdd(&A.hist[(size_t)(pi * 2 + fl) * A.total_bins + inf.x + kb], 1u);
                     cand |= (obs >= inf.z);
                 }
             }
@@ -280,7 +298,7 @@ __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem&
     }
     // warp-converged bookkeeping: valid counts per (pair, background), candidate staging
     if (NPW != 1) {
-        const int npw = NPW > 0 ? NPW : c_prog.npw;
+        const int npw = NPW > 0 ? NPW : A.npw;
 #pragma unroll
         for (int fl = 0; fl < 2; ++fl) {
             const bool v = (flags & (fl ? HP_SF_VALID_Y : HP_SF_VALID_K)) != 0;
@@ -327,8 +345,9 @@ __device__ __forceinline__ void tail_acc_flush(const ScoreSmem& sh, const TailAc
     }
 }
 
-__device__ __forceinline__ void score_prologue(const ScoreSmem& sh, const CUtensorMap* tm, int tile_bytes, int q0, int plane0,
-                                               int sh_bins) {
+__device__ __forceinline__ void score_prologue(const ScoreArgs& A, const ScoreSmem& sh, const CUtensorMap* tm, int tile_bytes, int q0,
+                                               int plane0, int sh_bins) {
+    const Chunks& C = A.tab->chunks;
     if (threadIdx.x == 0) {
         mbar_init(sh.bar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -340,9 +359,9 @@ __device__ __forceinline__ void score_prologue(const ScoreSmem& sh, const CUtens
     for (int i = threadIdx.x; i < sh_bins; i += blockDim.x) sh.hist[i] = 0;
     if (threadIdx.x < 16) { sh.emax[threadIdx.x] = 0ull; sh.nval[threadIdx.x] = 0u; }
     for (int i = threadIdx.x; i < kChunkTab; i += blockDim.x) {
-        const bool in = i <= c_chunks.maxchunk;
-        sh.rv[i] = in ? c_chunks.rv[i] : INFINITY;
-        sh.cinfo[i] = in ? make_int4(c_chunks.hoff[i], c_chunks.hw[i], c_chunks.kcand[i], 0) : make_int4(0, 1, 0x7fffffff, 0);
+        const bool in = i <= C.maxchunk;
+        sh.rv[i] = in ? C.rv[i] : INFINITY;
+        sh.cinfo[i] = in ? make_int4(C.hoff[i], C.hw[i], C.kcand[i], 0) : make_int4(0, 1, 0x7fffffff, 0);
     }
     __syncthreads();
     mbar_wait(sh.bar, 0);
@@ -351,15 +370,15 @@ __device__ __forceinline__ void score_prologue(const ScoreSmem& sh, const CUtens
 // flush: privatised histogram, counters, staged candidates
 __device__ __forceinline__ void score_epilogue(const ScoreArgs& A, const ScoreSmem& sh, int sh_bins) {
     __syncthreads();
-    const int total_bins = c_chunks.total_bins;
+    const int total_bins = A.total_bins;
     for (int i = threadIdx.x; i < sh_bins; i += blockDim.x) {
         const unsigned v = sh.hist[i];
         if (v) {
             const int kb = i % kShK, ci = (i / kShK) % kShI + 1, lf = i / (kShK * kShI);
-            atomicAdd(&A.hist[(size_t)lf * total_bins + c_chunks.hoff[ci] + kb], v);
+            atomicAdd(&A.hist[(size_t)lf * total_bins + sh.cinfo[ci].x + kb], v);
         }
     }
-    if (threadIdx.x < 2 * c_prog.npw) {
+    if (threadIdx.x < 2 * A.npw) {
         if (sh.nval[threadIdx.x]) atomicAdd(&A.nvalid[threadIdx.x], (unsigned long long)sh.nval[threadIdx.x]);
         if (sh.emax[threadIdx.x]) atomicMax(&A.emax_bits[threadIdx.x], sh.emax[threadIdx.x]);
     }
@@ -383,8 +402,9 @@ __global__ void __launch_bounds__(kThreads) k_score(const __grid_constant__ CUte
     const int sh_bins = A.sh_pairs * 2 * kShI * kShK;
     const int r0 = blockIdx.x * kTR;
     const int d0 = A.dlo + blockIdx.y * A.TD;
-    const int npw = c_prog.npw;
-    score_prologue(sh, &tm_bal, A.BD * 4 * A.NQ * 8, (r0 - A.HR) / 4, d0 - 2 * A.F, sh_bins);
+    const Tables& T = *A.tab;
+    const int npw = T.prog.npw;
+    score_prologue(A, sh, &tm_bal, A.BD * 4 * A.NQ * 8, (r0 - A.HR) / 4, d0 - 2 * A.F, sh_bins);
 
     const int lane = threadIdx.x & 31;
     const int rl = threadIdx.x & (kTR - 1);
@@ -397,12 +417,12 @@ __global__ void __launch_bounds__(kThreads) k_score(const __grid_constant__ CUte
         if (d > A.dhi) break;
         const bool inside = (r < A.n) && (r + d < A.n);
         unsigned char lv = kLvlNone;
-        if (inside) lv = A.lvl[(size_t)d * A.pitch + r];
+        if (inside) lv = A.lvl[qidx(d, r, A.pitch)];
         int last = -1;
         if (lv < kLvlNever) {
             for (int pi = 0; pi < npw; ++pi) {
-                if (d < c_prog.ww[pi]) continue;
-                const int rs = c_prog.next_step[pi][lv];
+                if (d < T.prog.ww[pi]) continue;
+                const int rs = T.prog.next_step[pi][lv];
                 if (rs != kNoStep && rs > last) last = rs;
             }
         }
@@ -411,18 +431,18 @@ __global__ void __launch_bounds__(kThreads) k_score(const __grid_constant__ CUte
         double SK = 0.0, SY = 0.0;
         int opi = 0;
         for (int s = 0; s <= wlast; ++s) {
-            const int oe = c_prog.op_end[s];
+            const int oe = T.prog.op_end[s];
             if (s <= last) {
                 for (; opi < oe; ++opi) {
-                    const int a = c_opa[opi], b = c_opb[opi];
+                    const int a = T.opa[opi], b = T.opb[opi];
                     const int rr = rho + a;
                     const double v = sh.tile[((dl + 2 * A.F + b - a) * 4 + (rr & 3)) * A.NQ + (rr >> 2)];
                     SK = __dadd_rn(SK, v);
-                    if (c_opy[opi]) SY = __dadd_rn(SY, v);
+                    if (T.opy[opi]) SY = __dadd_rn(SY, v);
                 }
             }
-            const int pi = c_prog.step_pi[s];
-            const bool em = (s <= last) && (d >= c_prog.ww[pi]) && (c_prog.next_step[pi][lv] == s);
+            const int pi = T.prog.step_pi[s];
+            const bool em = (s <= last) && (d >= T.prog.ww[pi]) && (T.prog.next_step[pi][lv] == s);
             if (__any_sync(0xffffffffu, em)) emit_record<0>(A, sh, tacc, em, SK, SY, r, d, s, pi, lane);
         }
     }
@@ -433,28 +453,29 @@ __global__ void __launch_bounds__(kThreads) k_score(const __grid_constant__ CUte
 // upload helper: plain diagonal-major staging plane -> quad-interleaved balanced plane, plus the
 // "row has a non-zero stored balanced value" flags behind the gap mask (callers.py:238)
 // ============================================================================================
-__global__ void k_relayout(const double* __restrict__ src, double* __restrict__ dst, unsigned int* __restrict__ rownz,
-                           int pitch, int num) {
+template <typename T>
+__global__ void k_relayout(const T* __restrict__ src, T* __restrict__ dst, unsigned int* __restrict__ rownz, int pitch, int num) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const int d = blockIdx.y;
     if (r >= pitch || d >= num) return;
-    const double v = src[(size_t)d * pitch + r];
-    dst[bal_index(d, r, pitch)] = v;
-    if (v != 0.0) rownz[r] = 1u;
+    const T v = src[(size_t)d * pitch + r];
+    dst[qidx(d, r, pitch)] = v;
+    if (rownz && v != T(0)) rownz[r] = 1u;
 }
 
 // ============================================================================================
 // Poisson tables: p[i][k] = 1 - pdtr(k, rv_i)  (callers.py:268-270); universal, built once per ctx
 // ============================================================================================
-__global__ void k_ptab(double* __restrict__ ptab) {
+__global__ void k_ptab(const Tables* __restrict__ tab, double* __restrict__ ptab) {
+    const Chunks& C = tab->chunks;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= c_chunks.total_bins) return;
-    int lo = 1, hi = c_chunks.maxchunk;          // chunk containing flat bin idx
+    if (idx >= C.total_bins) return;
+    int lo = 1, hi = C.maxchunk;          // chunk containing flat bin idx
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (c_chunks.hoff[mid] <= idx) lo = mid; else hi = mid - 1;
+        if (C.hoff[mid] <= idx) lo = mid; else hi = mid - 1;
     }
-    ptab[idx] = poisson_sf((double)(idx - c_chunks.hoff[lo]), c_chunks.rv[lo]);
+    ptab[idx] = poisson_sf((double)(idx - C.hoff[lo]), C.rv[lo]);
 }
 
 // ============================================================================================
@@ -496,8 +517,10 @@ __device__ __forceinline__ double block_scan_min(double v, double* sh, double& t
     return fmin(x, pre);
 }
 
-__global__ void __launch_bounds__(kThreads) k_bh(const unsigned int* __restrict__ hist, const double* __restrict__ ptab,
-                                                  double* __restrict__ qtab, const int* __restrict__ numbin) {
+__global__ void __launch_bounds__(kThreads) k_bh(const Tables* __restrict__ tab, const unsigned int* __restrict__ hist,
+                                                  const double* __restrict__ ptab, double* __restrict__ qtab,
+                                                  const int* __restrict__ numbin) {
+    const Chunks& c_chunks = tab->chunks;
     __shared__ unsigned long long sh_u[kThreads / 32];
     __shared__ double sh_d[kThreads / 32];
     const int ci = blockIdx.x + 1, lf = blockIdx.y;
@@ -545,6 +568,7 @@ __global__ void __launch_bounds__(kThreads) k_bh(const unsigned int* __restrict_
 // survivor selection: q <= sig for K or Y (callers.py:279-287), over the candidate list only
 // ============================================================================================
 struct FilterArgs {
+    const Tables* tab;
     const Cand* cand;
     unsigned int ncand;
     const double* ptab;
@@ -562,6 +586,7 @@ struct FilterArgs {
 __global__ void k_filter(FilterArgs A) {
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= A.ncand) return;
+    const Chunks& c_chunks = A.tab->chunks;
     const Cand c = A.cand[idx];
     hp_survivor sv;
     sv.r = c.r; sv.c = c.r + c.d; sv.pair = c.pair; sv.flags = c.flags;
@@ -588,7 +613,7 @@ __global__ void k_filter(FilterArgs A) {
         }
     }
     if (any) {
-        sv.ice = A.bal[bal_index(c.d, c.r, A.pitch)];
+        sv.ice = A.bal[qidx(c.d, c.r, A.pitch)];
         const unsigned g = atomicAdd(&A.out_count[0], 1u);
         if (g < A.out_cap) A.out[g] = sv; else atomicAdd(&A.out_count[1], 1u);
     }

@@ -69,6 +69,21 @@ struct SProg {
         }
         return m;
     }
+    __host__ __device__ static constexpr int min_pw() {
+        int m = pw(0);
+        for (int i = 1; i < npw; ++i) m = pw(i) < m ? pw(i) : m;
+        return m;
+    }
+    // rings whose lower-left cells step s also adds to Reads (callers.py:197-198: the first step, then
+    // only steps of the smallest p and only rings beyond the previous step's w)
+    __host__ __device__ static constexpr unsigned rmask(int s) {
+        const unsigned m = mask(s);
+        if (s == 0) return m;
+        if (step_p(s) != min_pw()) return 0u;
+        unsigned out = 0;
+        for (int g = step_w(s - 1) + 1; g < 32; ++g) out |= m & (1u << g);
+        return out;
+    }
     // previous step of the same pair, -1 if none: pixels with level in (prev, s] resolve the pair at s
     __host__ __device__ static constexpr int prev_same_pair(int s) {
         const int pi = step_pi(s);
@@ -175,7 +190,8 @@ __device__ __forceinline__ void spec_dispatch(int s, const double* base, double 
 #define HP_SPEC_MINB 1
 #endif
 template <class PG>
-__global__ void __launch_bounds__(kSpecThreads, HP_SPEC_MINB) k_score_spec(const __grid_constant__ CUtensorMap tm_bal, ScoreArgs A) {
+__global__ void __launch_bounds__(kSpecThreads, HP_SPEC_MINB) k_score_spec(const __grid_constant__ CUtensorMap tm_bal,
+                                                                            const __grid_constant__ ScoreArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     const ScoreSmem sh = score_smem(smem, A.BD, kNQ, kSpecThreads / 32, kQCap);
     const int sh_bins = A.sh_pairs * 2 * kShI * kShK;
@@ -183,12 +199,12 @@ __global__ void __launch_bounds__(kSpecThreads, HP_SPEC_MINB) k_score_spec(const
     // far diagonals first: they run the deepest levels, so the cheap tiles fill the tail of the grid
     const int d0 = A.dlo + (int)(gridDim.y - 1 - blockIdx.y) * A.TD;
     const int plane0 = d0 - 3 - 2 * A.F;
-    score_prologue(sh, &tm_bal, A.BD * 4 * kNQ * 8, (r0 - kHR) / 4, plane0, sh_bins);
+    score_prologue(A, sh, &tm_bal, A.BD * 4 * kNQ * 8, (r0 - kHR) / 4, plane0, sh_bins);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = r0 + 4 * lane;
     const unsigned lt = (1u << lane) - 1u;
-    const int dspan = c_prog.dspan;
+    const int dspan = A.dspan;
     double2* qs = sh.qsum + warp * kQCap;
     int2* qm = sh.qmeta + warp * kQCap;
     int cnt = 0;                                     // warp-uniform queue fill
@@ -208,11 +224,11 @@ __global__ void __launch_bounds__(kSpecThreads, HP_SPEC_MINB) k_score_spec(const
             for (int j = 0; j < kTC; ++j) {
                 const int rr = r + i, d = dc + j - i;
                 unsigned lv = kLvlNone;
-                if (d >= A.dlo && d <= A.dhi && rr < A.n && rr + d < A.n) lv = A.lvl[(size_t)d * A.pitch + rr];
+                if (d >= A.dlo && d <= A.dhi && rr < A.n && rr + d < A.n) lv = A.lvl[qidx(d, rr, A.pitch)];
                 pk |= lv << (8 * j);
                 if (lv < kLvlNever) {
                     const int k = d - A.dlo < dspan ? d - A.dlo : dspan;
-                    const int rs = c_prog.last_need[k][lv];
+                    const int rs = A.last_need[k][lv];
                     if (rs != kNoStep && rs > last) last = rs;
                 }
             }
@@ -230,7 +246,7 @@ __global__ void __launch_bounds__(kSpecThreads, HP_SPEC_MINB) k_score_spec(const
         for (int s = 0; s <= wlast; ++s) {
             spec_dispatch<PG, 0>(s, base, aK, aY);
             // pixels whose level lies in (previous executed step of this pair, s] resolve the pair now
-            const int pi = c_prog.step_pi[s], lo = c_prog.step_lo[s], wmin = c_prog.ww[pi];
+            const int pi = A.step_pi[s], lo = A.step_lo[s], wmin = A.ww[pi];
             unsigned em = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -280,9 +296,137 @@ __global__ void __launch_bounds__(kSpecThreads, HP_SPEC_MINB) k_score_spec(const
     score_epilogue(A, sh, sh_bins);
 }
 
+// ============================================================================================
+// k_levels_spec -- K1 for compiled-in sweep programs: the raw lower-left ring sums (integers, so any
+// order) with the same 4-row register blocks, 4 columns per thread.  Output: per non-zero band pixel
+// the first step s* with Reads >= min_local_reads (callers.py:203-206) and the histogram of s*.
+// ============================================================================================
+constexpr int kTCL = 4;
+
+template <unsigned RMASK>
+__device__ __forceinline__ void level_accumulate(const int* __restrict__ base, int (&R)[4][kTCL]) {
+    constexpr int W = hp_top_ring(RMASK);
+    static_for<1, W + 4>([&](auto RHO) {                   // rows below the block's first row
+        constexpr int rho = decltype(RHO)::value;
+        int strip[W + kTCL];                               // columns c - W .. c + kTCL - 1
+        static_for<0, W + kTCL>([&](auto KK) {
+            constexpr int k = decltype(KK)::value;
+            strip[k] = base[((k - W - rho) * 4 + (rho & 3)) * kNQL + (rho >> 2)];
+        });
+        static_for<0, 4>([&](auto II) {
+            constexpr int i = decltype(II)::value;
+            constexpr int a = rho - i;
+            if constexpr (a >= 1 && a <= W) {
+                static_for<0, kTCL>([&](auto JJ) {
+                    constexpr int j = decltype(JJ)::value;
+                    static_for<-W, 0>([&](auto BB) {
+                        constexpr int b = decltype(BB)::value;
+                        if constexpr (hp_cell_in(RMASK, a, b)) R[i][j] += strip[j + b + W];
+                    });
+                });
+            }
+        });
+    });
+}
+
+template <class PG, int S>
+__device__ __forceinline__ void level_dispatch(int s, const int* base, int (&R)[4][kTCL]) {
+    if constexpr (S < PG::nsteps()) {
+        if (s == S) {
+            constexpr unsigned M = PG::rmask(S);
+            if constexpr (M != 0u) level_accumulate<M>(base, R);
+        } else {
+            level_dispatch<PG, S + 1>(s, base, R);
+        }
+    }
+}
+
+// tile: rows [r0, r0 + 4 kNQL), planes [d0 - 3 - 2F, d0 + TD); thread = rows 4l..4l+3 x 4 columns
+template <class PG>
+__global__ void __launch_bounds__(kThreads) k_levels_spec(const __grid_constant__ CUtensorMap tm_raw, LevelArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const Tables& T = *A.tab;
+    int* tile = reinterpret_cast<int*>(smem);
+    const int tile_bytes = A.BD * 4 * kNQL * 4;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + tile_bytes);
+    unsigned int* next = reinterpret_cast<unsigned int*>(smem + tile_bytes + 8);
+    unsigned int* sh_hist = reinterpret_cast<unsigned int*>(smem + tile_bytes + 16);
+    const int r0 = blockIdx.x * kTR;
+    const int d0 = A.dlo + (int)(gridDim.y - 1 - blockIdx.y) * A.TD;
+    const int plane0 = d0 - 3 - 2 * A.F;
+    const int nsteps = T.prog.nsteps;
+    for (int i = threadIdx.x; i <= nsteps; i += kThreads) sh_hist[i] = 0;
+    if (threadIdx.x == 0) *next = 0;
+    level_prologue(tile, bar, &tm_raw, tile_bytes, r0 / 4, plane0);
+
+    const int lane = threadIdx.x & 31;
+    const int r = r0 + 4 * lane;
+    const int thr = T.prog.thr;
+    for (;;) {
+        int kb = 0;
+        if (lane == 0) kb = (int)atomicAdd(next, 1u);
+        kb = __shfl_sync(0xffffffffu, kb, 0);
+        const int dc = d0 + kb * kTCL;
+        if (kb * kTCL >= A.TD || dc - 3 > A.dhi) break;
+        const int* base = tile + (size_t)(dc - plane0) * 4 * kNQL + lane;
+        int R[4][kTCL];
+        unsigned lvp[4];                                   // one byte per pixel: kLvlNone / kLvlNever / step
+        bool open = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            unsigned pk = 0;
+#pragma unroll
+            for (int j = 0; j < kTCL; ++j) {
+                R[i][j] = 0;
+                const int rr = r + i, d = dc + j - i;
+                unsigned lv = kLvlNone;
+                if (d >= A.dlo && d <= A.dhi && rr < A.n && rr + d < A.n && base[((j - i) * 4 + i) * kNQL] != 0) lv = kLvlNever;
+                pk |= lv << (8 * j);
+            }
+            lvp[i] = pk;
+            open |= __vcmpeq4(pk, 0xFEFEFEFEu) != 0u;
+        }
+        int never = 0;
+        for (int s = 0; s < nsteps && __any_sync(0xffffffffu, open); ++s) {
+            level_dispatch<PG, 0>(s, base, R);
+            int hit = 0;
+            open = false;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int j = 0; j < kTCL; ++j) {
+                    const unsigned sh8 = 8 * j;
+                    if (((lvp[i] >> sh8) & 0xffu) == kLvlNever && R[i][j] >= thr) {
+                        lvp[i] = (lvp[i] & ~(0xffu << sh8)) | ((unsigned)s << sh8);
+                        ++hit;
+                    }
+                }
+                open |= __vcmpeq4(lvp[i], 0xFEFEFEFEu) != 0u;
+            }
+            hit = __reduce_add_sync(0xffffffffu, hit);
+            if (lane == 0 && hit) atomicAdd(&sh_hist[s], (unsigned)hit);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            never += __popc(__vcmpeq4(lvp[i], 0xFEFEFEFEu)) >> 3;
+#pragma unroll
+            for (int j = 0; j < kTCL; ++j) {
+                const int rr = r + i, d = dc + j - i;
+                if (d >= A.dlo && d <= A.dhi && rr < A.n) A.lvl[qidx(d, rr, A.pitch)] = (unsigned char)(lvp[i] >> (8 * j));
+            }
+        }
+        never = __reduce_add_sync(0xffffffffu, never);
+        if (lane == 0 && never) atomicAdd(&sh_hist[nsteps], (unsigned)never);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= nsteps; i += kThreads)
+        if (sh_hist[i]) atomicAdd(&A.hist[i], (unsigned long long)sh_hist[i]);
+}
+
 // ---- host side: does a run-time program (a prefix of it) equal the compiled one? ----------------
 template <class PG>
-inline bool spec_matches(const Prog& G, int nexec, const signed char* opa, const signed char* opb, const unsigned char* opy) {
+inline bool spec_matches(const Prog& G, int nexec, const signed char* opa, const signed char* opb, const unsigned char* opy,
+                         const unsigned char* opr) {
     if (G.npw != PG::npw || nexec > PG::nsteps() || nexec > G.nsteps) return false;
     for (int i = 0; i < PG::npw; ++i)
         if (G.pw[i] != PG::pw(i) || G.ww[i] != PG::ww(i)) return false;
@@ -297,6 +441,7 @@ inline bool spec_matches(const Prog& G, int nexec, const signed char* opa, const
                 const int g = abs(a) > abs(b) ? abs(a) : abs(b);
                 if (!((m >> g) & 1u)) continue;
                 if (k >= G.op_end[s] || opa[k] != a || opb[k] != b || opy[k] != (unsigned char)(a > 0 && b < 0)) return false;
+                if (opr[k] != (unsigned char)(a > 0 && b < 0 && ((PG::rmask(s) >> g) & 1u))) return false;
                 ++k;
             }
         if (k != G.op_end[s]) return false;
