@@ -34,7 +34,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 SYMBOLS = [
     "hp_abi_version", "hp_device_count", "hp_ctx_create", "hp_ctx_destroy", "hp_last_error",
     "hp_band_upload", "hp_hiccups_score", "hp_hiccups_fdr", "hp_hiccups", "hp_get_survivors",
-    "hp_get_gaps", "hp_dump_levels", "hp_dump_plane", "hp_get_chunk_table", "hp_poisson_sf",
+    "hp_hist_bins", "hp_hist_export", "hp_hist_import", "hp_get_gaps", "hp_dump_levels", "hp_dump_plane", "hp_get_chunk_table", "hp_poisson_sf",
 ]
 
 
@@ -105,6 +105,9 @@ def load_library(path: str | None = None):
     lib.hp_hiccups_fdr.argtypes = [vp, vp, C.POINTER(HiccupsSummary)]
     lib.hp_hiccups.argtypes = [vp, C.POINTER(HiccupsParams), C.POINTER(HiccupsSummary)]
     lib.hp_get_survivors.argtypes = [vp, vp, i64, C.POINTER(i64)]
+    lib.hp_hist_bins.argtypes = [vp, C.POINTER(i64)]
+    lib.hp_hist_export.argtypes = [vp, vp, i64]
+    lib.hp_hist_import.argtypes = [vp, vp, i64]
     lib.hp_get_gaps.argtypes = [vp, vp, i64]
     lib.hp_dump_levels.argtypes = [vp, vp, i64]
     lib.hp_dump_plane.argtypes = [vp, i32, i32, i32, vp, i64]
@@ -234,6 +237,18 @@ class Context:
         if cnt.value:
             self._check(self.lib.hp_get_survivors(self._h, _ptr(out), cnt.value, C.byref(cnt)))
         return out
+
+    def hist_export(self):
+        """(npw * 2, total_bins) int64 histograms of the last score() call."""
+        tb = C.c_int64()
+        self._check(self.lib.hp_hist_bins(self._h, C.byref(tb)))
+        out = np.zeros((self.params.npw * 2, tb.value), dtype=np.int64)
+        self._check(self.lib.hp_hist_export(self._h, _ptr(out), out.size))
+        return out
+
+    def hist_import(self, hist):
+        h = np.ascontiguousarray(hist, dtype=np.int64)
+        self._check(self.lib.hp_hist_import(self._h, _ptr(h), h.size))
 
     def gaps(self):
         out = np.zeros(self.n, dtype=np.uint8)

@@ -704,6 +704,42 @@ extern "C" int hp_get_survivors(hp_ctx* ctx, hp_survivor* buf, int64_t capacity,
     return HP_OK;
 }
 
+extern "C" int hp_hist_bins(hp_ctx* ctx, int64_t* total_bins) {
+    if (!ctx || !total_bins) return fail(ctx, HP_ERR_INVALID, "NULL argument");
+    *total_bins = ctx->chunks.total_bins;
+    return HP_OK;
+}
+
+extern "C" int hp_hist_export(hp_ctx* ctx, int64_t* out, int64_t capacity) {
+    if (!ctx || !out) return fail(ctx, HP_ERR_INVALID, "NULL argument");
+    if (!ctx->scored) return fail(ctx, HP_ERR_STATE, "hp_hiccups_score must come first");
+    const size_t cnt = (size_t)ctx->prm.npw * 2 * ctx->chunks.total_bins;
+    if ((size_t)capacity < cnt) return fail(ctx, HP_ERR_CAPACITY, "histogram buffer too small");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<unsigned int> h(cnt);
+    CK(cudaMemcpyAsync(h.data(), ctx->d_hist, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < cnt; ++i) out[i] = h[i];
+    return HP_OK;
+}
+
+extern "C" int hp_hist_import(hp_ctx* ctx, const int64_t* in, int64_t count) {
+    if (!ctx || !in) return fail(ctx, HP_ERR_INVALID, "NULL argument");
+    if (!ctx->scored) return fail(ctx, HP_ERR_STATE, "hp_hiccups_score must come first");
+    const size_t cnt = (size_t)ctx->prm.npw * 2 * ctx->chunks.total_bins;
+    if ((size_t)count != cnt) return fail(ctx, HP_ERR_INVALID, "histogram size mismatch");
+    std::vector<unsigned int> h(cnt);
+    for (size_t i = 0; i < cnt; ++i) {
+        if (in[i] < 0 || in[i] > 0xffffffffll) return fail(ctx, HP_ERR_INVALID, "histogram count out of range");
+        h[i] = (unsigned int)in[i];
+    }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->d_hist, h.data(), cnt * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->fdr_done = false;
+    return HP_OK;
+}
+
 extern "C" int hp_get_gaps(hp_ctx* ctx, uint8_t* out, int64_t n) {
     if (!ctx || !out) return fail(ctx, HP_ERR_INVALID, "NULL argument");
     if (!ctx->have_band) return fail(ctx, HP_ERR_STATE, "hp_band_upload must come first");

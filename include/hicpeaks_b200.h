@@ -146,6 +146,14 @@ typedef struct hp_survivor {     /* a pixel with q <= sig for K or Y of one pair
 #define HP_SF_CEMY_NONZERO 16u   /* reference's cEM[ci,cj] != 0 for the Y background (callers.py:330) */
 int hp_get_survivors(hp_ctx* ctx, hp_survivor* buf, int64_t capacity, int64_t* count);
 
+/* ---- genome-wide FDR (optional; NOT the reference's behaviour, which corrects per chromosome) ------
+ * Between hp_hiccups_score and hp_hiccups_fdr the (pair, background, lambda-chunk, observed) histograms can
+ * be exported, summed over chromosomes / GPUs by the caller (one all-reduce), and imported back, so that BH
+ * runs on the merged counts.  Layout: [npw * 2][total_bins] int64, total_bins from hp_hist_bins().       */
+int hp_hist_bins(hp_ctx* ctx, int64_t* total_bins);
+int hp_hist_export(hp_ctx* ctx, int64_t* out, int64_t capacity);
+int hp_hist_import(hp_ctx* ctx, const int64_t* in, int64_t count);
+
 /* rows of cM whose stored band is all zero ('gaps', callers.py:238): out[r] = 1 if row r is a gap
  * (available after hp_band_upload) */
 int hp_get_gaps(hp_ctx* ctx, uint8_t* out, int64_t n);

@@ -52,3 +52,36 @@ def test_survivors_match_reference(name):
                 assert np.abs(s["q"][:, fl] - exp[5]).max() <= Q_TOL
             assert S.lf[pi][fl].n_valid == int(z["p%d%s_n_valid" % (p, nm)])
             assert S.lf[pi][fl].numbin == int(z["p%d%s_numbin" % (p, nm)])
+
+
+@pytest.mark.parametrize("scope", ["chrom", "genome"])
+def test_genome_runner_matches_hiccups(scope):
+    """The dispatcher (chromosome sharding; optional merged-histogram FDR) on one rank: with a single chromosome both
+    scopes must reproduce the drop-in hiccups() table, i.e. the reference's."""
+    from hicpeaks_b200 import dispatch
+    name = "chr21_25k_p1w3"
+    z, inp, kw, res = gu.load(name)
+    runner = dispatch.GenomeRunner(engine=dispatch.CudaEngine(0), fdr_scope=scope)
+    out = runner.run({"21": lambda: inp}, {"21": (inp["n"], inp["num"])}, res=res, **kw)
+    got, exp = gu.table_rows(out["21"]), z["table"]
+    assert got.shape == exp.shape
+    assert np.array_equal(got[:, :6], exp[:, :6])
+    for col in (7, 8, 10, 11):
+        assert np.abs(got[:, col] - exp[:, col]).max() <= Q_TOL
+
+
+def test_genome_scope_merges_histograms():
+    """Two chromosomes, genome scope: every context runs BH on the summed histogram (checked through the chunk tables)."""
+    from hicpeaks_b200 import dispatch
+    from hicpeaks_b200.synth import synth_chromosome
+    inps = {c: synth_chromosome(500, 60, 5, maxww=10, seed=s, scale=60.0) for c, s in (("a", 3), ("b", 4))}
+    prm = dict(dispatch.DEFAULTS, pw=[2], ww=[5], maxww=10, sig=0.1, maxapart=60 * 10000, res=10000, min_local_reads=16)
+    eng = dispatch.CudaEngine(0)
+    hs = {c: eng.score(c, inps[c], prm) for c in inps}
+    hists = {c: eng.hist(hs[c]) for c in inps}
+    total = hists["a"] + hists["b"]
+    assert total.sum() == hists["a"].sum() + hists["b"].sum() > 0
+    hs["a"]["ctx"].hist_import(total)
+    assert np.array_equal(hs["a"]["ctx"].hist_export(), total)
+    for h in hs.values():
+        h["ctx"].close()
