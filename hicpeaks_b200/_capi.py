@@ -44,6 +44,10 @@ class BandDesc(C.Structure):
                 ("ir", C.c_void_p), ("b1", C.c_void_p), ("b2", C.c_void_p)]
 
 
+class ApaDesc(C.Structure):
+    _fields_ = [("n", C.c_int64), ("num", C.c_int32), ("reserved", C.c_int32), ("bal_diags", C.POINTER(C.c_void_p))]
+
+
 class HiccupsParams(C.Structure):
     _fields_ = [("npw", C.c_int32), ("pw", C.c_int32 * HP_MAX_PW), ("ww", C.c_int32 * HP_MAX_PW),
                 ("maxww", C.c_int32), ("min_local_reads", C.c_int32), ("maxapart_bins", C.c_int64),
@@ -113,6 +117,11 @@ def load_library(path: str | None = None):
     lib.hp_dump_plane.argtypes = [vp, i32, i32, i32, vp, i64]
     lib.hp_get_chunk_table.argtypes = [vp, i32, i32, C.POINTER(i32), vp, vp, vp, vp, i64]
     lib.hp_poisson_sf.argtypes = [vp, vp, vp, vp, i64]
+    lib.hp_apa_upload.argtypes = [vp, C.POINTER(ApaDesc)]
+    lib.hp_apa_windows.argtypes = [vp, vp, vp, i64, i32, vp, vp]
+    lib.hp_apa_load_windows.argtypes = [vp, vp, i64, i32, vp]
+    lib.hp_apa_accumulate.argtypes = [vp, vp, i64, vp, i32]
+    lib.hp_apa_get_windows.argtypes = [vp, vp, i64, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("hp_ctx_destroy", "hp_last_error"):
@@ -150,9 +159,10 @@ class Context:
         self.params = None
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
-            self.lib.hp_ctx_destroy(self._h)
-            self._h = C.c_void_p()
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._h = None
+            self.lib.hp_ctx_destroy(h)
 
     __del__ = close
 
@@ -280,6 +290,45 @@ class Context:
                                                     _ptr(p), _ptr(q), tot))
         off = np.concatenate([[0], np.cumsum(widths)]).astype(np.int64)
         return nb.value, widths, off, hist, p, q
+
+    # -- APA ----------------------------------------------------------------------------------
+    def apa_upload(self, n, diags):
+        """diags[d]: balanced diagonal d (float64, length n - d, NaN kept), d = 0 .. len(diags) - 1."""
+        num = len(diags)
+        keep = [np.ascontiguousarray(a, dtype=np.float64) for a in diags]
+        ptrs = (C.c_void_p * num)()
+        for d, a in enumerate(keep):
+            if a.size != n - d:
+                raise ValueError("diagonal %d must have %d entries" % (d, n - d))
+            ptrs[d] = a.ctypes.data
+        desc = ApaDesc(n, num, 0, C.cast(ptrs, C.POINTER(C.c_void_p)))
+        self._check(self.lib.hp_apa_upload(self._h, C.byref(desc)))
+
+    def apa_windows(self, pos_i, pos_j, w):
+        pi = np.ascontiguousarray(pos_i, dtype=np.int32)
+        pj = np.ascontiguousarray(pos_j, dtype=np.int32)
+        valid = np.zeros(pi.size, dtype=np.uint8)
+        mean = np.zeros(pi.size, dtype=np.float64)
+        self._check(self.lib.hp_apa_windows(self._h, _ptr(pi), _ptr(pj), pi.size, int(w), _ptr(valid), _ptr(mean)))
+        return valid.astype(bool), mean
+
+    def apa_load_windows(self, wins, w):
+        a = np.ascontiguousarray(wins, dtype=np.float64)
+        mean = np.zeros(a.shape[0], dtype=np.float64)
+        self._check(self.lib.hp_apa_load_windows(self._h, _ptr(a), a.shape[0], int(w), _ptr(mean)))
+        return mean
+
+    def apa_accumulate(self, sel, acc, init):
+        sel = np.ascontiguousarray(sel, dtype=np.int64)
+        self._check(self.lib.hp_apa_accumulate(self._h, _ptr(sel), sel.size, _ptr(acc), int(bool(init))))
+
+    def apa_get_windows(self, sel, w):
+        sel = np.ascontiguousarray(sel, dtype=np.int64)
+        side = 2 * w + 1
+        out = np.empty((sel.size, side, side), dtype=np.float64)
+        if sel.size:
+            self._check(self.lib.hp_apa_get_windows(self._h, _ptr(sel), sel.size, _ptr(out)))
+        return out
 
     def poisson_sf(self, k, mu):
         k = np.ascontiguousarray(k, dtype=np.float64)

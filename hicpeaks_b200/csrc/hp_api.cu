@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -13,6 +14,7 @@
 
 #include "hp_kernels.cuh"
 #include "hp_score_spec.cuh"
+#include "hp_apa.cuh"
 
 using namespace hp;
 
@@ -66,6 +68,17 @@ struct hp_ctx {
     unsigned int ncand = 0, nsurv = 0;
     bool spec_used = false;
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    // APA (hp_apa.cuh)
+    double* d_apa_bal = nullptr; size_t cap_apa_bal = 0;
+    int64_t apa_n = 0; int apa_num = 0;
+    ApaPlan* d_apa_plan = nullptr;
+    int* d_apa_pos = nullptr; size_t cap_apa_pos = 0;
+    double* d_apa_wins = nullptr; size_t cap_apa_wins = 0;
+    unsigned char* d_apa_valid = nullptr; size_t cap_apa_valid = 0;
+    double* d_apa_mean = nullptr; size_t cap_apa_mean = 0;
+    long long* d_apa_sel = nullptr; size_t cap_apa_sel = 0;
+    double* d_apa_avg = nullptr; size_t cap_apa_avg = 0;
+    int64_t apa_npos = 0; int apa_w = 0;
 };
 
 static int fail(hp_ctx* c, int code, const std::string& msg) {
@@ -182,7 +195,8 @@ extern "C" void hp_ctx_destroy(hp_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_ptab, ctx->d_raw, ctx->d_bal, ctx->d_lvl, ctx->d_ir, ctx->d_b1, ctx->d_b2, ctx->d_rownz,
                     ctx->d_lhist, ctx->d_betab, ctx->d_hist, ctx->d_qtab, ctx->d_small, ctx->d_cnt, ctx->d_numbin,
-                    ctx->d_cand, ctx->d_surv, ctx->d_dump, ctx->d_tmp, ctx->d_tab};
+                    ctx->d_cand, ctx->d_surv, ctx->d_dump, ctx->d_tmp, ctx->d_tab, ctx->d_apa_bal, ctx->d_apa_plan, ctx->d_apa_pos,
+                    ctx->d_apa_wins, ctx->d_apa_valid, ctx->d_apa_mean, ctx->d_apa_sel, ctx->d_apa_avg};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
@@ -208,7 +222,7 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
         ctx->d_raw = nullptr; ctx->d_bal = nullptr; ctx->d_lvl = nullptr; ctx->d_tmp = nullptr; ctx->cap_plane = 0;
         CK(cudaMalloc(&ctx->d_raw, plane * sizeof(int)));
         CK(cudaMalloc(&ctx->d_bal, plane * sizeof(double)));
-        CK(cudaMalloc(&ctx->d_tmp, plane * sizeof(double)));
+        CK(cudaMalloc(&ctx->d_tmp, plane * 12));
         CK(cudaMalloc(&ctx->d_lvl, plane));
         ctx->cap_plane = plane;
     }
@@ -248,26 +262,49 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
             }
         }
     };
-    unsigned nthreads = std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
+    // chunks of diagonals: worker threads pack chunk k + 1 .. while the copy engine uploads chunk k
+    for (int d = 0; d < num; ++d) hir[d] = d >= bf ? b->ir[d - bf] : 0.0;
+    double* tbal = ctx->d_tmp;
+    int* traw = (int*)((char*)ctx->d_tmp + plane * 8);
+    const int per = std::max(1, (int)((size_t)(8u << 20) / ((size_t)pitch * 12)));     // ~8 MB per chunk
+    const int nchunk = (num + per - 1) / per;
+    unsigned nthreads = std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
     if (plane < (1u << 20)) nthreads = 1;
+    cudaError_t cerr = cudaSuccess;
+    auto send = [&](int k) {
+        const int d0 = k * per, d1 = std::min(num, d0 + per);
+        const size_t off = (size_t)d0 * pitch, cnt = (size_t)(d1 - d0) * pitch;
+        cudaError_t e = cudaMemcpyAsync(tbal + off, hbal + off, cnt * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(traw + off, hraw + off, cnt * 4, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess && cerr == cudaSuccess) cerr = e;
+    };
     if (nthreads == 1) {
-        pack(0, num);
+        for (int k = 0; k < nchunk; ++k) { pack(k * per, std::min(num, (k + 1) * per)); send(k); }
     } else {
+        std::atomic<int> next{0};
+        std::vector<std::atomic<int>> done(nchunk);
+        for (auto& f : done) f.store(0, std::memory_order_relaxed);
         std::vector<std::thread> th;
-        const int per = (num + nthreads - 1) / nthreads;
-        for (unsigned t = 0; t < nthreads; ++t) {
-            const int a = t * per, e = std::min(num, a + per);
-            if (a < e) th.emplace_back(pack, a, e);
+        for (unsigned t = 0; t < nthreads; ++t)
+            th.emplace_back([&]() {
+                for (;;) {
+                    const int k = next.fetch_add(1);
+                    if (k >= nchunk) break;
+                    pack(k * per, std::min(num, (k + 1) * per));
+                    done[k].store(1, std::memory_order_release);
+                }
+            });
+        for (int k = 0; k < nchunk; ++k) {
+            while (!done[k].load(std::memory_order_acquire)) std::this_thread::yield();
+            send(k);
         }
         for (auto& t : th) t.join();
     }
-    for (int d = 0; d < num; ++d) hir[d] = d >= bf ? b->ir[d - bf] : 0.0;
-    CK(cudaMemcpyAsync(ctx->d_tmp, hbal, plane * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (cerr != cudaSuccess) return fail(ctx, HP_ERR_CUDA, std::string("band upload: ") + cudaGetErrorString(cerr));
     CK(cudaMemsetAsync(ctx->d_rownz, 0, (size_t)n * sizeof(unsigned int), ctx->stream));
-    k_relayout<double><<<dim3((pitch + 255) / 256, num), 256, 0, ctx->stream>>>(ctx->d_tmp, ctx->d_bal, ctx->d_rownz, pitch, num);
+    k_relayout<double><<<dim3((pitch + 255) / 256, num), 256, 0, ctx->stream>>>(tbal, ctx->d_bal, ctx->d_rownz, pitch, num);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(ctx->d_tmp, hraw, plane * 4, cudaMemcpyHostToDevice, ctx->stream));
-    k_relayout<int><<<dim3((pitch + 255) / 256, num), 256, 0, ctx->stream>>>((const int*)ctx->d_tmp, ctx->d_raw, nullptr, pitch, num);
+    k_relayout<int><<<dim3((pitch + 255) / 256, num), 256, 0, ctx->stream>>>(traw, ctx->d_raw, nullptr, pitch, num);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->d_ir, hir, (size_t)num * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_b1, b->b1, n * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -826,5 +863,150 @@ extern "C" int hp_poisson_sf(hp_ctx* ctx, const double* k, const double* mu, dou
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d);
     if (e != cudaSuccess) return fail(ctx, HP_ERR_CUDA, cudaGetErrorString(e));
+    return HP_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// APA -- /root/reference/hicpeaks/apa.py
+static int apa_rec(ApaPlan& P, int start, int n) {
+    if (n <= 128) {
+        const int l = P.nleaf++;
+        P.leaf_start[l] = start; P.leaf_len[l] = n;
+        return l;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    const int a = apa_rec(P, start, n2), b = apa_rec(P, start + n2, n - n2);
+    P.comb_dst[P.ncomb] = (short)a; P.comb_src[P.ncomb] = (short)b; ++P.ncomb;
+    return a;
+}
+
+extern "C" int hp_apa_upload(hp_ctx* ctx, const hp_apa_desc* b) {
+    if (!ctx || !b || !b->bal_diags) return fail(ctx, HP_ERR_INVALID, "NULL argument");
+    if (b->n <= 0 || b->n > (1ll << 30) || b->num <= 0 || b->num > b->n) return fail(ctx, HP_ERR_INVALID, "bad band geometry");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t n = b->n;
+    const int num = b->num;
+    const size_t cells = (size_t)n * num;
+    CK(ensure(&ctx->d_apa_bal, &ctx->cap_apa_bal, cells));
+    if (cells * 8 > ctx->cap_stage) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr; ctx->cap_stage = 0;
+        CK(cudaHostAlloc(&ctx->h_stage, cells * 8, cudaHostAllocDefault));
+        ctx->cap_stage = cells * 8;
+    }
+    double* h = (double*)ctx->h_stage;                 // row-major [r][d], zero where r + d >= n
+    for (int d = 0; d < num; ++d) {
+        const double* src = b->bal_diags[d];
+        for (int64_t r = 0; r < n - d; ++r) h[(size_t)r * num + d] = src[r];
+        for (int64_t r = n - d; r < n; ++r) h[(size_t)r * num + d] = 0.0;
+    }
+    CK(cudaMemcpyAsync(ctx->d_apa_bal, h, cells * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->apa_n = n; ctx->apa_num = num; ctx->apa_npos = 0;
+    return HP_OK;
+}
+
+static int apa_plan(hp_ctx* ctx, int cells);
+extern "C" int hp_apa_windows(hp_ctx* ctx, const int32_t* pos_i, const int32_t* pos_j, int64_t npos, int32_t w, uint8_t* valid,
+                              double* mean_arr) {
+    if (!ctx || !pos_i || !pos_j || !valid || !mean_arr || npos < 0) return fail(ctx, HP_ERR_INVALID, "bad argument");
+    if (!ctx->apa_num) return fail(ctx, HP_ERR_STATE, "hp_apa_upload must come first");
+    const int side = 2 * w + 1, cells = side * side;
+    if (w < 0 || cells > 128 * kApaMaxLeaves / 2) return fail(ctx, HP_ERR_INVALID, "window too large");
+    for (int64_t k = 0; k < npos; ++k) {
+        const int64_t i = pos_i[k], j = pos_j[k];
+        const bool inside = i - w >= 0 && i + w + 1 <= ctx->apa_n && j - w >= 0 && j + w + 1 <= ctx->apa_n;
+        if (inside && llabs(j - i) + 2 * w >= ctx->apa_num)
+            return fail(ctx, HP_ERR_INVALID, "anchor " + std::to_string(k) + " needs diagonals beyond the uploaded band");
+    }
+    ctx->apa_npos = 0;
+    if (npos == 0) { ctx->apa_w = w; return HP_OK; }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int rcp = apa_plan(ctx, cells);
+    if (rcp) return rcp;
+    CK(ensure(&ctx->d_apa_pos, &ctx->cap_apa_pos, (size_t)2 * npos));
+    CK(ensure(&ctx->d_apa_wins, &ctx->cap_apa_wins, (size_t)npos * cells));
+    CK(ensure(&ctx->d_apa_valid, &ctx->cap_apa_valid, (size_t)npos));
+    CK(ensure(&ctx->d_apa_mean, &ctx->cap_apa_mean, (size_t)npos));
+    CK(cudaMemcpyAsync(ctx->d_apa_pos, pos_i, npos * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_apa_pos + npos, pos_j, npos * 4, cudaMemcpyHostToDevice, st));
+    const size_t smem = (size_t)cells * 8 + (size_t)kApaMaxLeaves * 9 * 8;
+    CK(cudaFuncSetAttribute(k_apa_windows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_apa_windows<<<(unsigned)npos, kApaThreads, smem, st>>>(ctx->d_apa_plan, ctx->d_apa_bal, ctx->apa_n, ctx->apa_num, ctx->d_apa_pos,
+                                                             ctx->d_apa_pos + npos, w, ctx->d_apa_wins, ctx->d_apa_valid, ctx->d_apa_mean);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(valid, ctx->d_apa_valid, npos, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(mean_arr, ctx->d_apa_mean, npos * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->apa_npos = npos; ctx->apa_w = w;
+    return HP_OK;
+}
+
+static int apa_plan(hp_ctx* ctx, int cells) {
+    if (!ctx->d_apa_plan) CK(cudaMalloc(&ctx->d_apa_plan, sizeof(ApaPlan)));
+    ApaPlan P{};
+    P.n = cells;
+    apa_rec(P, 0, cells);
+    CK(cudaMemcpyAsync(ctx->d_apa_plan, &P, sizeof(P), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));      // P lives on this stack frame
+    return HP_OK;
+}
+
+extern "C" int hp_apa_load_windows(hp_ctx* ctx, const double* wins, int64_t npos, int32_t w, double* mean_arr) {
+    if (!ctx || !wins || !mean_arr || npos <= 0) return fail(ctx, HP_ERR_INVALID, "bad argument");
+    const int side = 2 * w + 1, cells = side * side;
+    if (w < 0 || cells > 128 * kApaMaxLeaves / 2) return fail(ctx, HP_ERR_INVALID, "window too large");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->apa_npos = 0;
+    int rc = apa_plan(ctx, cells);
+    if (rc) return rc;
+    CK(ensure(&ctx->d_apa_wins, &ctx->cap_apa_wins, (size_t)npos * cells));
+    CK(ensure(&ctx->d_apa_mean, &ctx->cap_apa_mean, (size_t)npos));
+    CK(cudaMemcpyAsync(ctx->d_apa_wins, wins, (size_t)npos * cells * 8, cudaMemcpyHostToDevice, st));
+    const size_t smem = (size_t)cells * 8 + (size_t)kApaMaxLeaves * 9 * 8;
+    CK(cudaFuncSetAttribute(k_apa_means, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_apa_means<<<(unsigned)npos, kApaThreads, smem, st>>>(ctx->d_apa_plan, ctx->d_apa_wins, cells, ctx->d_apa_mean);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(mean_arr, ctx->d_apa_mean, npos * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->apa_npos = npos; ctx->apa_w = w;
+    return HP_OK;
+}
+
+extern "C" int hp_apa_accumulate(hp_ctx* ctx, const int64_t* sel, int64_t nsel, double* acc, int32_t init) {
+    if (!ctx || !acc || nsel < 0 || (nsel && !sel)) return fail(ctx, HP_ERR_INVALID, "bad argument");
+    if (!ctx->apa_npos) return fail(ctx, HP_ERR_STATE, "hp_apa_windows must come first");
+    for (int64_t k = 0; k < nsel; ++k)
+        if (sel[k] < 0 || sel[k] >= ctx->apa_npos) return fail(ctx, HP_ERR_INVALID, "window index out of range");
+    if (nsel == 0) return HP_OK;
+    const int side = 2 * ctx->apa_w + 1, cells = side * side;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(ensure(&ctx->d_apa_sel, &ctx->cap_apa_sel, (size_t)nsel));
+    CK(ensure(&ctx->d_apa_avg, &ctx->cap_apa_avg, (size_t)cells));
+    CK(cudaMemcpyAsync(ctx->d_apa_sel, sel, nsel * 8, cudaMemcpyHostToDevice, st));
+    if (!init) CK(cudaMemcpyAsync(ctx->d_apa_avg, acc, (size_t)cells * 8, cudaMemcpyHostToDevice, st));
+    k_apa_accumulate<<<(cells + 31) / 32, 32, 0, st>>>(ctx->d_apa_wins, ctx->d_apa_sel, nsel, cells, ctx->d_apa_avg, init ? 1 : 0);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(acc, ctx->d_apa_avg, (size_t)cells * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return HP_OK;
+}
+
+extern "C" int hp_apa_get_windows(hp_ctx* ctx, const int64_t* sel, int64_t nsel, double* out) {
+    if (!ctx || !out || nsel < 0 || (nsel && !sel)) return fail(ctx, HP_ERR_INVALID, "bad argument");
+    if (!ctx->apa_npos) return fail(ctx, HP_ERR_STATE, "hp_apa_windows must come first");
+    const int side = 2 * ctx->apa_w + 1, cells = side * side;
+    CK(cudaSetDevice(ctx->device));
+    for (int64_t k = 0; k < nsel; ++k) {
+        if (sel[k] < 0 || sel[k] >= ctx->apa_npos) return fail(ctx, HP_ERR_INVALID, "window index out of range");
+        CK(cudaMemcpyAsync(out + (size_t)k * cells, ctx->d_apa_wins + (size_t)sel[k] * cells, (size_t)cells * 8, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
     return HP_OK;
 }

@@ -171,6 +171,31 @@ int hp_get_chunk_table(hp_ctx* ctx, int32_t pair, int32_t background, int32_t* n
 /* device Poisson tail exactly as used for the tables: out[i] = 1 - pdtr(k[i], mu[i])           */
 int hp_poisson_sf(hp_ctx* ctx, const double* k, const double* mu, double* out, int64_t count);
 
+/* ---- APA pileup: /root/reference/hicpeaks/apa.py --------------------------------------------------- */
+/* The balanced matrix of one chromosome as its upper diagonals 0 .. num-1 (bal_diags[d] has n - d doubles, NaN
+ * kept: apa_submatrix rejects windows that hold a NaN, apa.py:20-22); the matrix is symmetric (cooler fetch). */
+typedef struct hp_apa_desc {
+    int64_t n;
+    int32_t num;
+    int32_t reserved;
+    const double* const* bal_diags;   /* [num] */
+} hp_apa_desc;
+int hp_apa_upload(hp_ctx* ctx, const hp_apa_desc* band);
+/* apa_submatrix (apa.py:11-28) + the per-window means of apa_analysis (apa.py:33): for anchor k the
+ * (2w+1)^2 window around (pos_i[k], pos_j[k]) is gathered, rejected (valid[k] = 0) when it leaves the matrix,
+ * holds a NaN or has mean 0, else divided by its mean and kept on the device; mean_arr[k] = mean of the
+ * normalised window, bit-identical to numpy's.  Every anchor needs |j - i| + 2w < num. */
+int hp_apa_windows(hp_ctx* ctx, const int32_t* pos_i, const int32_t* pos_j, int64_t npos, int32_t w, uint8_t* valid,
+                   double* mean_arr);
+/* the same means for caller-supplied normalised windows (apa_analysis on a host array): wins is
+ * npos * (2w+1)^2 doubles; the windows stay on the device for hp_apa_accumulate */
+int hp_apa_load_windows(hp_ctx* ctx, const double* wins, int64_t npos, int32_t w, double* mean_arr);
+/* the axis-0 sum of apa[mask].mean(axis=0) (apa.py:37): acc[(2w+1)^2] = (init ? 0 : acc) + windows sel[0..nsel)
+ * added one by one in that order (numpy's order); the caller divides by the total count */
+int hp_apa_accumulate(hp_ctx* ctx, const int64_t* sel, int64_t nsel, double* acc, int32_t init);
+/* download normalised windows (apa_submatrix's return value), out is nsel * (2w+1)^2 doubles */
+int hp_apa_get_windows(hp_ctx* ctx, const int64_t* sel, int64_t nsel, double* out);
+
 #ifdef __cplusplus
 }
 #endif

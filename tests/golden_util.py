@@ -42,3 +42,12 @@ def load(name):
 def table_rows(table):
     rows = [list(k) + [float(v) for v in table[k]] for k in sorted(table)]
     return np.array(rows, dtype=np.float64).reshape(len(rows), 12)
+
+
+def load_apa(name):
+    """(z, n, raw diagonals, weights) of an APA fixture (oracle/make_golden_apa.py)."""
+    z = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    n, num = int(z["n"]), int(z["num"])
+    off = np.concatenate([[0], np.cumsum([n - d for d in range(num)])])
+    Diags = [z["raw"][off[d]:off[d + 1]] for d in range(num)]
+    return z, n, Diags, z["weights"]

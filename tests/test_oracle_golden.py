@@ -38,3 +38,21 @@ def test_oracle_reproduces_reference(name):
     final = glue_oracle.finish_hiccups(inp, sw, out, pw, ww, res, kw["sumq"], kw["double_fold"], kw["single_fold"],
                                        kw["use_raw"], kw["min_marginal_peaks"], kw["onlyanchor"])
     assert np.array_equal(gu.table_rows(final), z["table"])
+
+
+@pytest.mark.parametrize("name", gu.names("apa"))
+def test_apa_oracle_reproduces_reference(name):
+    from oracle import apa_oracle as ao
+    z, n, Diags, weights = gu.load_apa(name)
+    w, cw = int(z["w"]), int(z["cw"])
+    diags = ao.balanced_diags(Diags, weights)
+    apa, valid = ao.apa_submatrix(diags, n, [tuple(p) for p in z["pos"]], w=w)
+    assert len(apa) == int(z["n_windows"]) == int(valid.sum())
+    assert np.array_equal(apa[0], z["win_first"]) and np.array_equal(apa[-1], z["win_last"])
+    avg, score, zz, p, maxi, mean_arr, mask = ao.apa_analysis(apa, w=w, cw=cw)
+    assert np.array_equal(mean_arr, z["mean_arr"])                      # bit-exact: the outlier cut selects on these
+    assert np.array_equal(avg, z["avg"])
+    assert np.array_equal(np.array([score, zz, p, maxi]), z["stats"])
+    # the explicit pairwise model the CUDA kernel follows equals numpy's mean on these windows
+    for a in (apa[0], apa[len(apa) // 2], apa[-1]):
+        assert ao.pairwise_sum(a.ravel()) / a.size == a.mean()
