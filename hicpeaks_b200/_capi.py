@@ -25,6 +25,7 @@ HP_ERR_CHUNK_OVERFLOW = -6
 HP_ERR_CAPACITY = -7
 
 PF_GENERIC_KERNEL = 1
+PF_BHFDR = 2
 SF_VALID_K, SF_VALID_Y, SF_REJECT_K, SF_REJECT_Y, SF_CEMY_NONZERO = 1, 2, 4, 8, 16
 
 LIB_NAME = "libhicpeaks_b200.so"
@@ -208,7 +209,7 @@ class Context:
 
     # -- scoring -------------------------------------------------------------------------------
     @staticmethod
-    def make_params(pw, ww, maxww, sig, maxapart_bins, min_local_reads, dump=False, generic_kernel=False):
+    def make_params(pw, ww, maxww, sig, maxapart_bins, min_local_reads, dump=False, generic_kernel=False, bhfdr=False):
         if len(pw) != len(ww) or not 1 <= len(pw) <= HP_MAX_PW:
             raise ValueError("need 1..%d (pw, ww) pairs" % HP_MAX_PW)
         P = HiccupsParams()
@@ -217,7 +218,7 @@ class Context:
             P.pw[i], P.ww[i] = int(p), int(w)
         P.maxww, P.min_local_reads = int(maxww), int(min_local_reads)
         P.maxapart_bins, P.sig, P.dump = int(maxapart_bins), float(sig), int(bool(dump))
-        P.flags = PF_GENERIC_KERNEL if generic_kernel else 0
+        P.flags = (PF_GENERIC_KERNEL if generic_kernel else 0) | (PF_BHFDR if bhfdr else 0)
         return P
 
     def score(self, P):

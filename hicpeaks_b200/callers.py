@@ -139,6 +139,67 @@ def hiccups(M, cM, B1, B2, IR, chromLen, Diags, cDiags, num, chrom, pw=[2], ww=[
                           min_marginal_peaks, onlyanchor)
 
 
+def bh_adjust(p, n, alpha):
+    """statsmodels ``multipletests(method='fdr_bh')`` restricted to the ``p.size`` smallest of ``n`` p-values
+    (all p-values that are not passed are larger than every one that is).  Returns (reject, q)."""
+    order = np.argsort(p)
+    ps = np.take(p, order)
+    ecdf = np.arange(1, ps.size + 1) / float(n)
+    rej = ps <= ecdf * alpha
+    if rej.any():
+        rej[:np.max(np.nonzero(rej)[0])] = True
+    q = np.minimum.accumulate((ps / ecdf)[::-1])[::-1]
+    q[q > 1] = 1
+    reject = np.empty_like(rej)
+    qv = np.empty_like(q)
+    reject[order] = rej
+    qv[order] = q
+    return reject, qv
+
+
+def bhfdr(M, cM, B1, B2, IR, chromLen, Diags, cDiags, num, chrom, pw=2, ww=5, sig=0.05,
+          maxww=20, maxapart=2000000, res=10000, min_marginal_peaks=3, onlyanchor=False, device=0):
+    """BH-FDR peak calling for one chromosome -- same contract as the reference's ``bhfdr``
+    (/root/reference/hicpeaks/callers.py:364-590).  Returns ``{(x_bp, y_bp): (cx_bp, cy_bp, radius_bp, O, fold, p, q)}``.
+
+    GPU: the donut sweep with the hard-coded ``Reads >= 16`` rule (:490), ``E`` (:526-535) and the per-pixel Poisson
+    tail (:536-540) for every pixel that can still pass ``sig``.  Host (a few thousand records): the chromosome-wide
+    Benjamini-Hochberg step (:545-547), gap filter (:557-577), clustering (:580-582) and ``fold > 2`` (:587)."""
+    ctx = get_context(device)
+    raw, bal, ir = _as_diags(Diags, cDiags, IR, chromLen, num, ww)
+    ctx.upload(chromLen, num, ww, raw, bal, ir, B1, B2)
+    P = ctx.make_params([pw], [ww], maxww, sig, maxapart // res, 16, bhfdr=True)
+    try:
+        S = ctx.score(P)
+    except _capi.EngineError as e:
+        if e.code == _capi.HP_ERR_EMPTY_REFIDX:
+            raise ValueError(str(e)) from None
+        raise
+    _log_sweep(chrom, S)
+    S = ctx.fdr()
+    n_tests = int(S.lf[0][0].n_valid)
+    logger.info('Chrom:{0}, Number of Poisson Models: {1}'.format(chrom, n_tests))
+    sv = ctx.survivors()
+    sv = sv[np.lexsort((sv["c"], sv["r"]))]
+    table = {}
+    if sv.size == 0:
+        return table
+    p = np.ascontiguousarray(sv["p"][:, 0])
+    reject, q = bh_adjust(p, n_tests, sig)
+    sv, p, q = sv[reject], p[reject], q[reject]
+    keep = gap_filter(sv["r"], sv["c"], ctx.gaps(), ww, chromLen)
+    sv, p, q = sv[keep], p[keep], q[keep]
+    x, y = sv["r"].astype(np.int64), sv["c"].astype(np.int64)
+    fold = sv["obs"] / sv["e"][:, 0]
+    Donuts = {(int(a), int(b)): (o, f, pp, qq) for a, b, o, f, pp, qq in zip(x, y, sv["obs"], fold, p, q)}
+    for pixel, cen, radius in local_clustering(Donuts, None, res, min_count=min_marginal_peaks, r=2 * res,
+                                               onlysummit=onlyanchor):
+        donut = Donuts[pixel]
+        if donut[1] > 2:
+            table[(pixel[0] * res, pixel[1] * res)] = (cen[0] * res, cen[1] * res) + (radius * res,) + donut
+    return table
+
+
 def assemble_table(sv, gaps, chromLen, pw, ww, res, sumq, double_fold, single_fold, use_raw,
                    min_marginal_peaks, onlyanchor):
     """callers.py:289-362 on the engine's survivor records (``_capi.SURVIVOR_DTYPE``) and gap mask."""

@@ -446,6 +446,8 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
 
     // ---- tables (program, cell list) -> device ------------------------------------------------------
     const bool force_generic = (P.flags & HP_PF_GENERIC_KERNEL) != 0;
+    const bool bhfdr = (P.flags & HP_PF_BHFDR) != 0;
+    if (bhfdr && P.npw != 1) return fail(ctx, HP_ERR_INVALID, "the BH-FDR caller takes one (pw, ww) pair");
     const bool spec_ok = !force_generic && num <= 32767;
     Tables& HT = *ctx->h_tab;
     G.nsteps_exec = G.nsteps;
@@ -573,6 +575,10 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
             while (k < C.hw[i] && !(p[k] <= lim)) ++k;
             C.kcand[i] = k;
         }
+        if (bhfdr) {   // per-pixel rates: the tail at the LOWER edge of the chunk bounds p from below
+            for (int i = C.maxchunk; i >= 2; --i) C.kcand[i] = C.kcand[i - 1];
+            C.kcand[1] = 0;
+        }
         HT.prog = G;                       // now with the executed steps and the resolve tables
         HT.chunks = C;
         CK(cudaMemcpyAsync(ctx->d_tab, &HT, offsetof(Tables, opa), cudaMemcpyHostToDevice, st));
@@ -609,6 +615,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
         A.dump = P.dump ? ctx->d_dump : nullptr; A.plane = (long long)ctx->plane;
         A.n = n; A.num = num; A.pitch = pitch; A.dlo = dlo; A.dhi = dhi; A.F = F;
         A.bal_first = ctx->bal_first; A.sh_pairs = sh_pairs;
+        A.bhfdr = bhfdr ? 1 : 0;
         A.nexec = nexec; A.npw = P.npw; A.dspan = G.dspan; A.maxchunk = ctx->chunks.maxchunk; A.total_bins = ctx->chunks.total_bins;
         for (int i = 0; i < P.npw; ++i) A.ww[i] = P.ww[i];
         for (int k = 0; k < nexec; ++k) { A.step_pi[k] = (unsigned char)G.step_pi[k]; A.step_lo[k] = G.step_lo[k]; }
@@ -693,6 +700,7 @@ extern "C" int hp_hiccups_fdr(hp_ctx* ctx, const int32_t* numbin_override, hp_hi
         A.bal = ctx->d_bal; A.out = ctx->d_surv; A.out_count = ctx->d_cnt + 4;
         A.out_cap = (unsigned)std::min<size_t>(ctx->cap_surv, 0xffffffffu);
         A.nreject = ctx->d_small + 32; A.sig = P.sig; A.pitch = ctx->pitch;
+        A.bhfdr = (P.flags & HP_PF_BHFDR) ? 1 : 0;
         k_filter<<<(ctx->ncand + 255) / 256, 256, 0, st>>>(A);
         ++launches;
         CK(cudaGetLastError());

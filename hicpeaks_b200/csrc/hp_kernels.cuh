@@ -152,6 +152,7 @@ struct ScoreArgs {
     int HR, NQ;                        // row halo (multiple of 8) and row quads of the tile: NQ = (kTR + 2 HR) / 4
     // hot scalars and step tables of the program, in the kernel parameter (constant) bank
     int nexec, npw, dspan, maxchunk, total_bins;
+    int bhfdr;                         // BH-FDR caller (callers.py:364-553): donut only, per-pixel Poisson rate, no histograms
     int ww[HP_MAX_PW];
     unsigned char step_pi[HP_MAX_STEPS], step_lo[HP_MAX_STEPS];
     unsigned char last_need[HP_MAX_WW + 1][HP_MAX_STEPS + 2];
@@ -253,6 +254,7 @@ __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem&
         const double ird = A.ir[d], bb1 = A.b1[r], bb2 = A.b2[r + d];
 #pragma unroll
         for (int fl = 0; fl < 2; ++fl) {
+            if (fl == 1 && A.bhfdr) break;
             const double bs = fl ? SY : SK;
             double E = 0.0;
             bool valid = false;
@@ -283,7 +285,11 @@ __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem&
                 bool member;
                 const int ci = find_chunk(sh.rv, mc, E, member);
                 if (ci > mc) atomicAdd(&A.cand_count[2], 1u);
-                if (member) {
+                if (A.bhfdr) {
+                    // p = 1 - pdtr(O, E) grows with E: with E in [rv[ci-1], rv[ci]) it can only pass sig if the tail at
+                    // the chunk's lower edge does; kcand was built from the lower edges (hp_hiccups_score)
+                    cand |= (ci <= mc) && (obs >= sh.cinfo[ci].z);
+                } else if (member) {
                     chk[fl] = (unsigned)ci;
                     const int4 inf = sh.cinfo[ci];
                     const int kb = obs < inf.y - 1 ? obs : inf.y - 1;
@@ -581,6 +587,7 @@ struct FilterArgs {
     unsigned long long* nreject;    // [npw*2]
     double sig;
     int pitch;
+    int bhfdr;
 };
 
 __global__ void k_filter(FilterArgs A) {
@@ -593,6 +600,17 @@ __global__ void k_filter(FilterArgs A) {
     sv.obs = (double)c.obs;
     sv.e[0] = c.e_k; sv.e[1] = c.e_y;
     bool any = false;
+    if (A.bhfdr) {
+        // per-pixel Poisson rate (callers.py:536-540); BH over the whole chromosome is finished by the caller on the
+        // pixels with p <= sig (every rejected pixel has p <= sig), q is filled in there
+        const double p = poisson_sf((double)c.obs, c.e_k);
+        sv.p[0] = p; sv.q[0] = 1.0; sv.p[1] = 1.0; sv.q[1] = 1.0;
+        if (p <= A.sig * (1.0 + 1e-9)) {
+            sv.flags |= HP_SF_REJECT_K;
+            atomicAdd(&A.nreject[c.pair * 2], 1ull);
+            any = true;
+        }
+    } else {
 #pragma unroll
     for (int fl = 0; fl < 2; ++fl) {
         const int lf = c.pair * 2 + fl;
@@ -611,6 +629,7 @@ __global__ void k_filter(FilterArgs A) {
             atomicAdd(&A.nreject[lf], 1ull);
             any = true;
         }
+    }
     }
     if (any) {
         sv.ice = A.bal[qidx(c.d, c.r, A.pitch)];

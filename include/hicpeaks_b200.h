@@ -90,6 +90,10 @@ typedef struct hp_hiccups_params {
     int32_t dump;                /* !=0: keep per-pixel bS/bE/E planes for hp_dump_plane (tests) */
     int32_t flags;               /* HP_PF_*                                                    */
 } hp_hiccups_params;
+#define HP_PF_BHFDR 2            /* the BH-FDR caller, callers.py:364-553: one pair, donut background only, Poisson
+                                    rate = the pixel's own E, no lambda-chunks.  hp_hiccups_fdr then returns the
+                                    pixels with p <= sig (flags REJECT_K, q = 1): the chromosome-wide BH over them and
+                                    summary.lf[0][0].n_valid tests is finished by the caller (<= 1e5 records)      */
 #define HP_PF_GENERIC_KERNEL 1   /* use the table-driven score kernel even when a compiled-in sweep
                                     program matches (tests exercise both kernels)               */
 

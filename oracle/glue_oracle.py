@@ -155,3 +155,20 @@ def finish_hiccups(inp, sw, res_by_pf, pw, ww, res, sumq, double_fold, single_fo
         key = (pixel[0] * res, pixel[1] * res)
         final[key] = (cen[0] * res, cen[1] * res) + (rad * res,) + table[key][4:]
     return final
+
+
+def finish_bhfdr(inp, sw, r, ww, res, min_marginal_peaks, onlyanchor):
+    """callers.py:555-590: gap filter with m = ww, clustering without the lower-left table, fold > 2."""
+    rej = r["reject"]
+    x, y = r["x"][rej], r["y"][rej]
+    vals = [r[k][rej] for k in ("O", "fold", "p", "q")]
+    keep = gap_keep(x, y, gaps_of(sw["bal"]), ww, inp["n"])
+    x, y = x[keep], y[keep]
+    vals = [v[keep] for v in vals]
+    Donuts = dict(zip(zip(x, y), zip(*vals)))
+    table = {}
+    for pixel, cen, radius in clustering(Donuts, None, res, onlyanchor, min_marginal_peaks, 2 * res, 1):
+        donut = Donuts[pixel]
+        if donut[1] > 2:
+            table[(pixel[0] * res, pixel[1] * res)] = (cen[0] * res, cen[1] * res) + (radius * res,) + donut
+    return table

@@ -221,3 +221,36 @@ def score(inp, pw, ww, maxww=20, sig=0.1, maxapart_bins=200, min_local_reads=25)
         for fl in (K, Y):
             res[(p, fl)] = expected_and_fdr(inp, sw, p, w0, fl, sig)
     return sw, res
+
+
+def score_bhfdr(inp, pw, ww, maxww=20, sig=0.05, maxapart_bins=200):
+    """callers.py:364-553 (``bhfdr``): the donut sweep of one (pw, ww) pair with the hard-coded Reads >= 16 rule (:490)
+    and ``break`` on valid < 0.3 or left < 0.03 (:505-511) -- for a single pair the same executed steps as ``sweep`` --
+    then per-pixel Poisson tails with the pixel's own rate (:536-540) and one BH over the chromosome (:545-547)."""
+    sw = sweep(inp, [pw], [ww], maxww, 16, maxapart_bins)
+    vx, vy, vd = sw["vx"], sw["vy"], sw["vd"]
+    B = inp["biases"]
+    ir = np.zeros(inp["num"])
+    for d, v in inp["IR"].items():
+        ir[d] = v
+    bs, be = sw["bSV"][pw][K], sw["bEV"][pw][K]
+    m = be != 0
+    x, y, d = vx[m], vy[m], vd[m]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ratio = bs[m] / be[m]
+        cem = ir[d] * ratio
+        E = cem * B[x] * B[y]
+        keep = (cem != 0) & (ratio != 0) & (E > 0)
+    x, y, d, E = x[keep], y[keep], d[keep], E[keep]
+    O = sw["raw"][d, x].astype(np.float64)
+    p = 1 - pdtr(np.floor(O), E)
+    n = p.size
+    order = np.argsort(p)
+    ps = np.take(p, order)
+    ecdf = np.arange(1, n + 1) / float(n)
+    rej = ps <= ecdf * sig
+    if rej.any():
+        rej[:np.max(np.nonzero(rej)[0])] = True
+    reject = np.empty(n, dtype=bool)
+    reject[order] = rej
+    return sw, dict(x=x, y=y, E=E, O=O, p=p, q=bh_fdr(p) if n else p, reject=reject, fold=O / E)

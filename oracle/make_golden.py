@@ -109,6 +109,30 @@ def make_hiccups(name, inp, res, kw):
           {k[:-5]: out[k].shape[1] for k in out if k.endswith("_surv")})
 
 
+def table_rows_bh(table):
+    rows = [list(k) + [float(v) for v in table[k]] for k in sorted(table)]
+    return np.array(rows, dtype=np.float64).reshape(len(rows), 9)
+
+
+def make_bhfdr(name, inp, res, kw):
+    out = pack_inputs(inp)
+    out["kind"] = "bhfdr"
+    out["res"] = res
+    for k, v in kw.items():
+        out["kw_" + k] = np.array(v)
+    table, c = ref_harness.run_bhfdr(inp, res, **kw)
+    out["n_tests"] = c["x"].size
+    out["sha_xy"] = sha(np.stack([c["x"], c["y"]]).astype(np.int64))
+    for key in ("E", "O", "p", "q"):
+        out["sha_" + key] = sha(c[key].astype(np.float64))
+    rej = c["reject"]
+    out["n_reject"] = int(rej.sum())
+    out["surv"] = np.stack([c["x"][rej], c["y"][rej], c["O"][rej], c["E"][rej], c["p"][rej], c["q"][rej]]).astype(np.float64)
+    out["table"] = table_rows_bh(table)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "tests", c["x"].size, "rejected", int(rej.sum()), "peaks", len(table))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     cli = dict(maxww=10, sig=0.05, sumq=0.01, double_fold=1.75, single_fold=2, use_raw=False,
@@ -132,5 +156,17 @@ def main():
     make_hiccups("synth_union_crash", inp, 10000, dict(cli, pw=[1, 2], ww=[3, 5], maxww=8, maxapart=600000, onlyanchor=False))
 
 
+def main_bhfdr():
+    inp = chr21_example(2000000 // 25000 + 10 + 1, 3)
+    make_bhfdr("bh_chr21_25k", inp, 25000, dict(pw=1, ww=3, sig=0.05, maxww=10, maxapart=2000000))
+    inp = synth_chromosome(500, 60, 5, maxww=10, seed=1, scale=40.0)
+    make_bhfdr("bh_synth_p2w5", inp, 10000, dict(pw=2, ww=5, sig=0.05, maxww=10, maxapart=600000))
+    inp = synth_chromosome(400, 70, 5, maxww=20, seed=3, scale=25.0, decay=1.0)
+    make_bhfdr("bh_synth_deep", inp, 10000, dict(pw=2, ww=5, sig=0.1, maxww=20, maxapart=700000, min_marginal_peaks=2,
+                                                 onlyanchor=True))
+
+
 if __name__ == "__main__":
-    main()
+    if "--bhfdr-only" not in sys.argv:
+        main()
+    main_bhfdr()

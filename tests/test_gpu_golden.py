@@ -85,3 +85,27 @@ def test_genome_scope_merges_histograms():
     assert np.array_equal(hs["a"]["ctx"].hist_export(), total)
     for h in hs.values():
         h["ctx"].close()
+
+
+@pytest.mark.parametrize("name", gu.names("bhfdr"))
+def test_bhfdr_matches_reference(name):
+    """pyBHFDR's operator: donut sweep + per-pixel Poisson tails on the GPU, chromosome-wide BH on the host."""
+    z, inp, kw, res = gu.load(name)
+    table = callers.bhfdr(None, None, inp["biases"], inp["biases"], dict(inp["IR"]), inp["n"], inp["Diags"], inp["cDiags"],
+                          inp["num"], "21", res=res, **kw)
+    got = np.array([list(k) + [float(v) for v in table[k]] for k in sorted(table)], dtype=np.float64).reshape(len(table), 9)
+    exp = z["table"]
+    assert got.shape == exp.shape, (got.shape, exp.shape)
+    assert np.array_equal(got[:, :6], exp[:, :6])                       # pixel, centroid, radius, O: exact
+    assert np.allclose(got[:, 6], exp[:, 6], rtol=1e-12, atol=0)        # fold (E is bit-exact)
+    assert np.abs(got[:, 7] - exp[:, 7]).max() <= Q_TOL and np.abs(got[:, 8] - exp[:, 8]).max() <= Q_TOL
+    # the rejected set before the gap filter / clustering
+    ctx = callers.get_context(0)
+    sv = ctx.survivors()
+    sv = sv[np.lexsort((sv["c"], sv["r"]))]
+    reject, q = callers.bh_adjust(np.ascontiguousarray(sv["p"][:, 0]), int(z["n_tests"]), kw["sig"])
+    s = sv[reject]
+    surv = z["surv"]
+    assert np.array_equal(s["r"], surv[0]) and np.array_equal(s["c"], surv[1])
+    assert np.array_equal(s["e"][:, 0], surv[3])
+    assert np.abs(s["p"][:, 0] - surv[4]).max() <= Q_TOL and np.abs(q[reject] - surv[5]).max() <= Q_TOL

@@ -56,3 +56,19 @@ def test_apa_oracle_reproduces_reference(name):
     # the explicit pairwise model the CUDA kernel follows equals numpy's mean on these windows
     for a in (apa[0], apa[len(apa) // 2], apa[-1]):
         assert ao.pairwise_sum(a.ravel()) / a.size == a.mean()
+
+
+@pytest.mark.parametrize("name", gu.names("bhfdr"))
+def test_bhfdr_oracle_reproduces_reference(name):
+    z, inp, kw, res = gu.load(name)
+    sw, r = ho.score_bhfdr(inp, kw["pw"], kw["ww"], maxww=kw["maxww"], sig=kw["sig"], maxapart_bins=kw["maxapart"] // res)
+    assert r["x"].size == int(z["n_tests"])
+    assert gu.sha(np.stack([r["x"], r["y"]]).astype(np.int64)) == str(z["sha_xy"])
+    for key in ("E", "O", "p", "q"):
+        assert gu.sha(r[key]) == str(z["sha_" + key]), key + " bits"
+    rej = r["reject"]
+    assert int(rej.sum()) == int(z["n_reject"])
+    assert np.array_equal(np.stack([r["x"][rej], r["y"][rej], r["O"][rej], r["E"][rej], r["p"][rej], r["q"][rej]]), z["surv"])
+    final = glue_oracle.finish_bhfdr(inp, sw, r, kw["ww"], res, kw.get("min_marginal_peaks", 3), kw.get("onlyanchor", False))
+    rows = np.array([list(k) + [float(v) for v in final[k]] for k in sorted(final)], dtype=np.float64).reshape(len(final), 9)
+    assert np.array_equal(rows, z["table"])
