@@ -1,0 +1,281 @@
+"""Command-line front ends with the reference's surface: ``pyHICCUPS`` (/root/reference/scripts/pyHICCUPS) and
+``pyBHFDR`` (/root/reference/scripts/pyBHFDR) -- same flags and defaults (:19-73 / :19-50), same log format
+(:89-105), same output lines (:200-207 / :169-176) -- on top of the CUDA engine.
+
+What replaces what:
+
+* ``prepare_chromosome``  <- the worker's input preparation, pyHICCUPS:142-166 (cooler fetch, band diagonals,
+                             per-distance expected ``IR``, biases).  Host side, numpy, same arithmetic.
+* ``run``                 <- ``Pool(nproc).map(worker, Params)`` (pyHICCUPS:184-198): one host thread per GPU
+                             (``--gpus``), chromosomes handed out longest first; ``--nproc`` is accepted as an alias.
+* extra flags: ``--gpus N`` and, for pyHICCUPS, ``--fdr-scope {chrom,genome}`` (``chrom`` = the reference).
+
+``cooler`` is imported lazily; anything with ``binsize``, ``chromnames``, ``matrix(balance=, sparse=True).fetch(c)``
+and ``bins().fetch(c)[name].values`` works (tests use an in-memory stand-in, the image has no cooler / h5py).
+"""
+from __future__ import annotations
+
+import argparse
+import logging
+import logging.handlers
+import sys
+import threading
+
+import numpy as np
+
+__version__ = "0.1.0"
+
+log = logging.getLogger("hicpeaks_b200.cli")
+
+
+# ---------------------------------------------------------------------------------------------------------
+def hiccups_parser(prog="pyHICCUPS"):
+    p = argparse.ArgumentParser(prog=prog, usage='%(prog)s <-O output> [options]',
+                                description='A B200 (CUDA) implementation of the HiCCUPS algorithm.',
+                                formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    p.add_argument('-v', '--version', action='version', version=' '.join(['%(prog)s', __version__]),
+                   help='Print version number and exit.')
+    p.add_argument('-O', '--output', help='Output file name.')
+    p.add_argument('--logFile', default='pyHICCUPS.log', help='Logging file name.')
+    g1 = p.add_argument_group(title='Relate to Hi-C data:')
+    g1.add_argument('-p', '--path', help='Cooler URI.')
+    g1.add_argument('-C', '--chroms', nargs='*', default=['#', 'X'],
+                    help='List of chromosome labels. "#" stands for chromosomes with numerical labels. '
+                         '"--chroms" with zero argument will include all chromosome data.')
+    g2 = p.add_argument_group(title='Algorithm Parameters:')
+    g2.add_argument('--pw', type=int, nargs='+', help='List of the peak widths.')
+    g2.add_argument('--ww', type=int, nargs='+', help='List of the donut widths.')
+    g2.add_argument('--maxww', type=int, default=10, help='Maximum donut width.')
+    g2.add_argument('--siglevel', type=float, default=0.05, help='Significant Level.')
+    g2.add_argument('--sumq', type=float, default=0.01,
+                    help='Isolated peak pixels are dropped when the sum of their 2 q-values exceeds this threshold.')
+    g2.add_argument('--double-fold', type=float, default=1.75, help='Minimum fold enrichment for both backgrounds.')
+    g2.add_argument('--single-fold', type=float, default=2, help='Minimum fold enrichment for either background.')
+    g2.add_argument('--clr-weight-name', default='weight', help='Name of the weight column in the Cooler URI.')
+    g2.add_argument('--use-raw', action='store_true', help='Sort peak pixels by raw signal during local clustering.')
+    g2.add_argument('--min-marginal-peaks', type=int, default=2,
+                    help='Minimum marginal number of peaks when detecting peak anchors.')
+    g2.add_argument('--min-local-reads', type=int, default=16,
+                    help='Minimum sum of contacts in the vicinity of a valid loop.')
+    g2.add_argument('--only-anchors', action='store_true', help='Either of the peak loci must be an anchor.')
+    g2.add_argument('--maxapart', type=int, default=10000000, help='Maximum genomic distance between two loci.')
+    g2.add_argument('--nproc', type=int, default=1, help='Accepted for compatibility (alias of --gpus when > 1).')
+    g3 = p.add_argument_group(title='GPU engine:')
+    g3.add_argument('--gpus', type=int, default=0, help='Number of GPUs (0 = all visible).')
+    g3.add_argument('--fdr-scope', choices=['chrom', 'genome'], default='chrom',
+                    help='"chrom": BH within lambda-chunks per chromosome (the reference). "genome": histograms merged '
+                         'over all chromosomes and GPUs before BH.')
+    return p
+
+
+def bhfdr_parser(prog="pyBHFDR"):
+    p = argparse.ArgumentParser(prog=prog, usage='%(prog)s <-O output> [options]',
+                                description='A B200 (CUDA) implementation of the BH-FDR algorithm.',
+                                formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    p.add_argument('-v', '--version', action='version', version=' '.join(['%(prog)s', __version__]),
+                   help='Print version number and exit.')
+    p.add_argument('-O', '--output', help='Output file name.')
+    p.add_argument('--logFile', default='pyBHFDR.log', help='Logging file name.')
+    g1 = p.add_argument_group(title='Relate to Hi-C data:')
+    g1.add_argument('-p', '--path', help='Cooler URI.')
+    g1.add_argument('-C', '--chroms', nargs='*', default=['#', 'X'], help='List of chromosome labels.')
+    g2 = p.add_argument_group(title='Algorithm Parameters:')
+    g2.add_argument('--pw', type=int, default=2, help='Width of the interaction region surrounding the peak.')
+    g2.add_argument('--ww', type=int, default=5, help='Width of the donut sampled.')
+    g2.add_argument('--maxww', type=int, default=10, help='Maximum donut width.')
+    g2.add_argument('--siglevel', type=float, default=0.05, help='Significant Level.')
+    g2.add_argument('--maxapart', type=int, default=2000000, help='Maximum genomic distance between two loci.')
+    g2.add_argument('--clr-weight-name', default='weight', help='Name of the weight column in the Cooler URI.')
+    g2.add_argument('--nproc', type=int, default=1, help='Accepted for compatibility (alias of --gpus when > 1).')
+    g3 = p.add_argument_group(title='GPU engine:')
+    g3.add_argument('--gpus', type=int, default=0, help='Number of GPUs (0 = all visible).')
+    return p
+
+
+def setup_logging(logfile, rotating=False):
+    """Root logger as the reference sets it up (pyHICCUPS:89-105; pyBHFDR uses a rotating file, :70-72)."""
+    root = logging.getLogger()
+    root.setLevel(10)
+    console = logging.StreamHandler()
+    if rotating:
+        filehandler = logging.handlers.RotatingFileHandler(logfile, maxBytes=200000, backupCount=5)
+    else:
+        filehandler = logging.FileHandler(logfile)
+    console.setLevel('INFO')
+    filehandler.setLevel('INFO')
+    formatter = logging.Formatter(fmt='%(name)-21s %(levelname)-7s @ %(asctime)s: %(message)s', datefmt='%m/%d/%y %H:%M:%S')
+    console.setFormatter(formatter)
+    filehandler.setFormatter(formatter)
+    root.addHandler(console)
+    root.addHandler(filehandler)
+    return console, filehandler
+
+
+# ---------------------------------------------------------------------------------------------------------
+def select_chromosomes(chromnames, chroms):
+    """pyHICCUPS:184-187."""
+    out = []
+    for key in chromnames:
+        label = key.lstrip('chr')
+        if (not chroms) or (label.isdigit() and '#' in chroms) or (label in chroms):
+            out.append(key)
+    return out
+
+
+def prepare_chromosome(Lib, key, weight_name, maxapart, maxww, min_ww, res):
+    """The containers the reference's worker hands to the caller (pyHICCUPS:142-166), without the two scipy
+    band matrices ``M`` / ``cM`` (the engine reads ``Diags`` / ``cDiags``)."""
+    H = Lib.matrix(balance=False, sparse=True).fetch(key)
+    cHeatMap = Lib.matrix(balance=weight_name, sparse=True).fetch(key)
+    chromLen = H.shape[0]
+    num = maxapart // res + maxww + 1
+    Diags = [np.asarray(H.diagonal(i)) for i in np.arange(num)]
+    IR = {}
+    cDiags = []
+    for i in np.arange(min_ww, num):
+        diag = np.array(cHeatMap.diagonal(i), dtype=np.float64)
+        mask = np.isnan(diag)
+        notnan = diag[np.logical_not(mask)]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            IR[int(i)] = notnan.mean()
+        diag[mask] = 0
+        cDiags.append(diag)
+    tmp = np.asarray(Lib.bins().fetch(key)[weight_name].values, dtype=np.float64)
+    mask = np.logical_not((tmp == 0) | np.isnan(tmp))
+    biases = np.zeros_like(tmp)
+    biases[mask] = 1 / tmp[mask]
+    return dict(n=int(chromLen), num=int(num), min_ww=int(min_ww), Diags=Diags, cDiags=cDiags, IR=IR, biases=biases)
+
+
+def _open_cooler(path):
+    try:
+        import cooler
+    except ImportError as e:                                    # pragma: no cover (no cooler in this image)
+        raise SystemExit("the 'cooler' package is needed to read %s (%s)" % (path, e))
+    return cooler.Cooler(path)
+
+
+def _n_gpus(args):
+    from . import _capi
+    have = _capi.device_count()
+    if have == 0:
+        raise _capi.EngineError(_capi.HP_ERR_NO_DEVICE, "no CUDA device (this engine has no CPU fallback)")
+    want = args.gpus or (args.nproc if args.nproc > 1 else 0) or have
+    return max(1, min(want, have))
+
+
+def _map_over_gpus(keys, sizes, ngpu, fn):
+    """Longest chromosome first, one host thread per GPU pulling from a shared list; returns {key: fn(key, gpu)}."""
+    order = sorted(keys, key=lambda k: -sizes[k])
+    lock = threading.Lock()
+    out, errors = {}, []
+
+    def loop(gpu):
+        while True:
+            with lock:
+                if not order or errors:
+                    return
+                key = order.pop(0)
+            try:
+                out[key] = fn(key, gpu)
+            except BaseException as e:                          # propagate like Pool.map does
+                errors.append(e)
+                return
+
+    threads = [threading.Thread(target=loop, args=(g,)) for g in range(ngpu)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return out
+
+
+HICCUPS_LINE = '{0}\t{1}\t{2}\t{3}\t{4}\t{5}\t{6}\t{7:.3g}\t{8}\t{9}\t{10:.3g}\t{11:.3g}\t{12:.3g}\t{13:.3g}\t{14:.3g}\t{15:.3g}\n'
+BHFDR_LINE = '{0}\t{1}\t{2}\t{3}\t{4}\t{5}\t{6}\t{7:.3g}\t{8}\t{9}\t{10:.3g}\t{11:.3g}\t{12:.3g}\n'
+
+
+def write_table(OF, fmt, key, pixel_table, res):
+    """pyHICCUPS:200-207 / pyBHFDR:169-176."""
+    for pixel in pixel_table:
+        tmp = pixel_table[pixel]
+        c = 'chr' + key.lstrip('chr')
+        content = (c, pixel[0], pixel[0] + res, c, pixel[1], pixel[1] + res, '.', tmp[3], '.', '.') + tuple(tmp[4:])
+        OF.write(fmt.format(*content))
+
+
+def run_hiccups(argv=None, Lib=None):
+    args = hiccups_parser().parse_args(argv if argv else ['-h'])
+    handlers = setup_logging(args.logFile)
+    try:
+        from . import callers, dispatch
+        for k in ('output', 'logFile', 'chroms', 'path', 'pw', 'ww', 'maxww', 'maxapart', 'siglevel', 'sumq', 'double_fold',
+                  'single_fold', 'clr_weight_name', 'min_local_reads', 'gpus', 'fdr_scope'):
+            log.info('# %s = %s', k, getattr(args, k))
+        log.info('Loading Hi-C data ...')
+        Lib = Lib if Lib is not None else _open_cooler(args.path)
+        res = Lib.binsize
+        keys = select_chromosomes(Lib.chromnames, args.chroms)
+        log.info('Calling Peaks ...')
+        kw = dict(pw=list(args.pw), ww=list(args.ww), sig=args.siglevel, sumq=args.sumq, maxww=args.maxww,
+                  maxapart=args.maxapart, double_fold=args.double_fold, single_fold=args.single_fold, res=res,
+                  use_raw=args.use_raw, min_marginal_peaks=args.min_marginal_peaks, onlyanchor=args.only_anchors,
+                  min_local_reads=args.min_local_reads)
+
+        def load(key):
+            return prepare_chromosome(Lib, key, args.clr_weight_name, args.maxapart, args.maxww, min(args.ww), res)
+
+        ngpu = _n_gpus(args)
+        if args.fdr_scope == 'genome':
+            sizes = {k: (1, 1) for k in keys}
+            runner = dispatch.GenomeRunner(engine=dispatch.CudaEngine(0), fdr_scope='genome')
+            tables = runner.run({k: (lambda k=k: load(k)) for k in keys}, sizes, **kw)
+        else:
+            def one(key, gpu):
+                b = load(key)
+                return callers.hiccups(None, None, b["biases"], b["biases"], b["IR"], b["n"], b["Diags"], b["cDiags"],
+                                       b["num"], key.lstrip('chr'), device=gpu, **kw)
+            sizes = {k: 1 for k in keys}
+            tables = _map_over_gpus(keys, sizes, ngpu, one)
+        with open(args.output, 'w') as OF:
+            for key in keys:
+                write_table(OF, HICCUPS_LINE, key.lstrip('chr'), tables[key], res)
+        log.info('Done!')
+    finally:
+        for h in handlers:
+            logging.getLogger().removeHandler(h)
+            h.close()
+
+
+def run_bhfdr(argv=None, Lib=None):
+    args = bhfdr_parser().parse_args(argv if argv else ['-h'])
+    handlers = setup_logging(args.logFile, rotating=True)
+    try:
+        from . import callers
+        log.info('Loading Hi-C data ...')
+        Lib = Lib if Lib is not None else _open_cooler(args.path)
+        res = Lib.binsize
+        keys = select_chromosomes(Lib.chromnames, args.chroms)
+        log.info('Calling Peaks ...')
+
+        def one(key, gpu):
+            b = prepare_chromosome(Lib, key, args.clr_weight_name, args.maxapart, args.maxww, args.ww, res)
+            return callers.bhfdr(None, None, b["biases"], b["biases"], b["IR"], b["n"], b["Diags"], b["cDiags"], b["num"],
+                                 key.lstrip('chr'), pw=args.pw, ww=args.ww, sig=args.siglevel, maxww=args.maxww,
+                                 maxapart=args.maxapart, res=res, device=gpu)
+
+        tables = _map_over_gpus(keys, {k: 1 for k in keys}, _n_gpus(args), one)
+        with open(args.output, 'w') as OF:
+            for key in keys:
+                write_table(OF, BHFDR_LINE, key.lstrip('chr'), tables[key], res)
+        log.info('Done!')
+    finally:
+        for h in handlers:
+            logging.getLogger().removeHandler(h)
+            h.close()
+
+
+if __name__ == "__main__":
+    (run_bhfdr if (len(sys.argv) > 1 and sys.argv[1] == "bhfdr") else run_hiccups)(sys.argv[2:] if len(sys.argv) > 1 and
+                                                                                   sys.argv[1] in ("bhfdr", "hiccups") else sys.argv[1:])

@@ -1,0 +1,80 @@
+"""Front ends: flags / chromosome selection / worker input preparation on CPU, the whole pyHICCUPS / pyBHFDR run
+(fake cooler in, BEDPE-like text out) on the GPU against the reference's golden peak tables."""
+import os
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+from fake_cooler import FakeCooler
+from hicpeaks_b200 import cli
+
+
+def test_flags_and_defaults_match_reference():
+    a = cli.hiccups_parser().parse_args(['-O', 'x', '-p', 'y', '--pw', '1', '2', '--ww', '3', '5'])
+    assert (a.maxww, a.siglevel, a.sumq, a.double_fold, a.single_fold) == (10, 0.05, 0.01, 1.75, 2)
+    assert (a.clr_weight_name, a.use_raw, a.min_marginal_peaks, a.min_local_reads, a.only_anchors) == ('weight', False, 2, 16, False)
+    assert (a.maxapart, a.nproc, a.chroms, a.logFile) == (10000000, 1, ['#', 'X'], 'pyHICCUPS.log')
+    b = cli.bhfdr_parser().parse_args(['-O', 'x', '-p', 'y'])
+    assert (b.pw, b.ww, b.maxww, b.siglevel, b.maxapart, b.logFile) == (2, 5, 10, 0.05, 2000000, 'pyBHFDR.log')
+
+
+def test_chromosome_selection():
+    names = ['chr1', 'chr2', 'chrX', 'chrY', 'chrM', 'chr10_random']
+    assert cli.select_chromosomes(names, ['#', 'X']) == ['chr1', 'chr2', 'chrX']
+    assert cli.select_chromosomes(names, []) == names
+    assert cli.select_chromosomes(names, ['Y']) == ['chrY']
+
+
+def test_prepare_chromosome_matches_worker_containers():
+    z, inp, kw, res = gu.load("synth_p2w5")
+    Lib = FakeCooler(res, {"chr7": (inp["Diags"], inp["weights"])})
+    b = cli.prepare_chromosome(Lib, "chr7", "weight", kw["maxapart"], kw["maxww"], min(kw["ww"]), res)
+    assert b["n"] == inp["n"] and b["num"] == inp["num"]
+    for d in range(inp["num"]):
+        assert np.array_equal(b["Diags"][d], inp["Diags"][d])
+    for i in range(inp["num"] - inp["min_ww"]):
+        assert np.array_equal(b["cDiags"][i], inp["cDiags"][i])
+    assert all(b["IR"][k] == inp["IR"][k] or (np.isnan(b["IR"][k]) and np.isnan(inp["IR"][k])) for k in inp["IR"])
+    assert np.array_equal(b["biases"], inp["biases"])
+
+
+def _expected_lines(table_rows, fmt, chrom, res, ncols):
+    lines = set()
+    for row in table_rows:
+        x, y = int(row[0]), int(row[1])
+        vals = tuple(row[5:5 + ncols])
+        c = 'chr' + chrom
+        lines.add(fmt.format(c, x, x + res, c, y, y + res, '.', vals[0], '.', '.', *vals[1:]))
+    return lines
+
+
+@pytest.mark.gpu
+def test_pyhiccups_end_to_end(tmp_path):
+    z, inp, kw, res = gu.load("chr21_25k_p1w3")
+    Lib = FakeCooler(res, {"chr21": (inp["Diags"], inp["weights"]), "chrM": (inp["Diags"], inp["weights"])})
+    out = tmp_path / "loops.txt"
+    cli.run_hiccups(['-O', str(out), '-p', 'fake.cool', '--logFile', str(tmp_path / 'log.txt'), '--pw', '1', '--ww', '3',
+                     '--maxapart', str(kw["maxapart"]), '-C', '21'], Lib=Lib)
+    got = set(open(out).read().splitlines(True))
+    exp = _expected_lines(z["table"], cli.HICCUPS_LINE, "21", res, 7)
+    # O is exact; p / q agree with the reference within 1e-6, so '.3g' strings can differ only in the last digit
+    assert len(got) == len(exp) == z["table"].shape[0]
+    key = lambda ln: tuple(ln.split('\t')[:8])
+    assert {key(l) for l in got} == {key(l) for l in exp}
+    same = len(got & exp)
+    assert same >= 0.98 * len(exp), (same, len(exp))
+    assert "Done!" in open(tmp_path / 'log.txt').read()
+
+
+@pytest.mark.gpu
+def test_pybhfdr_end_to_end(tmp_path):
+    z, inp, kw, res = gu.load("bh_synth_p2w5")
+    Lib = FakeCooler(res, {"chr3": (inp["Diags"], inp["weights"])})
+    out = tmp_path / "bh.txt"
+    cli.run_bhfdr(['-O', str(out), '-p', 'fake.cool', '--logFile', str(tmp_path / 'log.txt'), '--pw', '2', '--ww', '5',
+                   '--maxapart', str(kw["maxapart"]), '-C', '3'], Lib=Lib)
+    got = set(open(out).read().splitlines(True))
+    exp = _expected_lines(z["table"], cli.BHFDR_LINE, "3", res, 4)
+    key = lambda ln: tuple(ln.split('\t')[:8])
+    assert len(got) == len(exp) and {key(l) for l in got} == {key(l) for l in exp}
