@@ -29,7 +29,7 @@ PF_BHFDR = 2
 SF_VALID_K, SF_VALID_Y, SF_REJECT_K, SF_REJECT_Y, SF_CEMY_NONZERO = 1, 2, 4, 8, 16
 
 LIB_NAME = "libhicpeaks_b200.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+LIB_PATH = os.environ.get("HICPEAKS_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 # every symbol include/hicpeaks_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [

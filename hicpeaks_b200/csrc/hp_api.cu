@@ -93,6 +93,17 @@ static int fail(hp_ctx* c, int code, const std::string& msg) {
             return fail(ctx, HP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
     } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when a launch needs more than was granted before
+// (per function and device; the attribute sticks)
+template <typename K>
+static cudaError_t want_smem(K kernel, int device, size_t smem, std::atomic<size_t>* granted) {
+    std::atomic<size_t>& g = granted[device & 63];
+    if (smem <= g.load(std::memory_order_acquire)) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) g.store(smem, std::memory_order_release);
+    return e;
+}
+
 template <typename T>
 static cudaError_t ensure(T** p, size_t* cap, size_t want) {
     if (*cap >= want && *p) return cudaSuccess;
@@ -380,13 +391,15 @@ struct SpecKernel {
 };
 template <class PG>
 static int launch_levels_spec(hp_ctx* ctx, const CUtensorMap& tm, const LevelArgs& A, dim3 grid, size_t smem, cudaStream_t st) {
-    CK(cudaFuncSetAttribute(k_levels_spec<PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static std::atomic<size_t> granted[64];
+    CK(want_smem(k_levels_spec<PG>, ctx->device, smem, granted));
     k_levels_spec<PG><<<grid, kThreads, smem, st>>>(tm, A);
     return HP_OK;
 }
 template <class PG>
 static int launch_spec(hp_ctx* ctx, const CUtensorMap& tm, const ScoreArgs& A, dim3 grid, size_t smem, cudaStream_t st) {
-    CK(cudaFuncSetAttribute(k_score_spec<PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static std::atomic<size_t> granted[64];
+    CK(want_smem(k_score_spec<PG>, ctx->device, smem, granted));
     k_score_spec<PG><<<grid, kSpecThreads, smem, st>>>(tm, A);
     return HP_OK;
 }
@@ -481,7 +494,8 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
             rc = make_map_plane(ctx, &tm_raw, CU_TENSOR_MAP_DATA_TYPE_INT32, 4, ctx->d_raw, A.NQ, A.BD);
             if (rc) return rc;
             const size_t smem = (size_t)A.BD * 4 * A.NQ * 4 + 16 + (G.nsteps + 2) * 4;
-            CK(cudaFuncSetAttribute(k_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            static std::atomic<size_t> granted[64];
+            CK(want_smem(k_levels, ctx->device, smem, granted));
             dim3 grid((n + kTR - 1) / kTR, (dhi - dlo + A.TD) / A.TD);
             k_levels<<<grid, kThreads, smem, st>>>(tm_raw, A);
         }
@@ -552,16 +566,16 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
         // 4x4 register-block kernel: one CTA per SM (all 8 warps share one big tile), TD diagonals per CTA
         A.HR = kHR; A.NQ = kNQ;
         int TD = 64;
-        while (TD > 8 && score_smem_bytes(TD + 3 + 4 * F, kNQ, sh_pairs, kSpecThreads / 32, kQCap) > 224 * 1024) TD /= 2;
+        while (TD > 8 && score_smem_bytes(TD + 3 + 4 * F, kNQ, sh_pairs, kSpecThreads / 32, kQCap, nexec, TD + 8) > 224 * 1024) TD /= 2;
         A.TD = TD; A.BD = TD + 3 + 4 * F;
-        smem = score_smem_bytes(A.BD, kNQ, sh_pairs, kSpecThreads / 32, kQCap);
+        smem = score_smem_bytes(A.BD, kNQ, sh_pairs, kSpecThreads / 32, kQCap, nexec, TD + 8);
         grid = dim3((n + kTR - 1) / kTR, (dhi - dlo + 3 + TD) / TD);
     } else {
         A.HR = (F + 7) & ~7; A.NQ = (kTR + 2 * A.HR) / 4;
         int TD = 32;
-        while (TD > 8 && score_smem_bytes(TD + 4 * F, A.NQ, sh_pairs, 0, 0) > 110 * 1024) TD /= 2;   // two CTAs per SM where possible
+        while (TD > 8 && score_smem_bytes(TD + 4 * F, A.NQ, sh_pairs, 0, 0, 0, 0) > 110 * 1024) TD /= 2;   // two CTAs per SM where possible
         A.TD = TD; A.BD = TD + 4 * F;
-        smem = score_smem_bytes(A.BD, A.NQ, sh_pairs, 0, 0);
+        smem = score_smem_bytes(A.BD, A.NQ, sh_pairs, 0, 0, 0, 0);
         grid = dim3((n + kTR - 1) / kTR, (dhi - dlo + TD) / TD);
     }
     if (smem > 227 * 1024) return fail(ctx, HP_ERR_INVALID, "tile does not fit shared memory");
@@ -624,7 +638,8 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
             rc = spec->launch(ctx, tm_bal, A, grid, smem, st);
             if (rc) return rc;
         } else {
-            CK(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            static std::atomic<size_t> granted[64];
+            CK(want_smem(k_score, ctx->device, smem, granted));
             k_score<<<grid, kThreads, smem, st>>>(tm_bal, A);
         }
         ++launches;
@@ -690,6 +705,7 @@ extern "C" int hp_hiccups_fdr(hp_ctx* ctx, const int32_t* numbin_override, hp_hi
         CK(cudaGetLastError());
     }
     unsigned int cnt[4] = {0, 0, 0, 0};
+    unsigned long long nrej[16] = {0};
     size_t want = std::max<size_t>(65536, ctx->ncand / 4 + 1024);
     for (int attempt = 0; attempt < 2 && ctx->ncand > 0; ++attempt) {
         CK(ensure(&ctx->d_surv, &ctx->cap_surv, want));
@@ -705,15 +721,17 @@ extern "C" int hp_hiccups_fdr(hp_ctx* ctx, const int32_t* numbin_override, hp_hi
         ++launches;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(cnt, ctx->d_cnt + 4, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(nrej, ctx->d_small + 32, sizeof(nrej), cudaMemcpyDeviceToHost, st));
+        if (attempt == 0) CK(cudaEventRecord(ctx->ev[5], st));
         CK(cudaStreamSynchronize(st));
         if (cnt[1] == 0) break;
         if (attempt == 1) return fail(ctx, HP_ERR_CAPACITY, "survivor buffer overflow");
         want = (size_t)ctx->ncand + 16;
     }
-    CK(cudaEventRecord(ctx->ev[5], st));
-    unsigned long long nrej[16] = {0};
-    CK(cudaMemcpyAsync(nrej, ctx->d_small + 32, sizeof(nrej), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    if (ctx->ncand == 0) {
+        CK(cudaEventRecord(ctx->ev[5], st));
+        CK(cudaStreamSynchronize(st));
+    }
     for (int i = 0; i < P.npw; ++i)
         for (int fl = 0; fl < 2; ++fl) S.lf[i][fl].n_reject = (int64_t)nrej[i * 2 + fl];
     ctx->nsurv = cnt[0];

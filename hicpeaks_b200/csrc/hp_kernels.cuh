@@ -171,16 +171,27 @@ struct ScoreSmem {                     // carve-up of the dynamic shared memory 
     Cand* stage;                       // [kStage]
     double2* qsum;                     // [warps][kQCap] resolved (bS_K, bS_Y) waiting for the tail (k_score_spec only)
     int2* qmeta;                       // [warps][kQCap] {r, d << 16 | step << 8 | pair}
+    int* qobs;                         // [warps][kQCap] raw count of the pixel
+    // per-CTA copies of the small tables the tail reads (k_score_spec only): interior bE, IR, biases
+    double* tb_be;                     // [2][nexec][tb_nd], diagonals tb_d0 .. tb_d0 + tb_nd - 1
+    double* tb_ir;                     // [tb_nd]
+    double* tb_b1;                     // [kTR] rows r0 ..
+    double* tb_b2;                     // [kTR + tb_nd] columns r0 + tb_d0 ..
+    int tb_d0, tb_nd, tb_r0;
     unsigned int* hist;                // [sh_pairs*2][kShI][kShK]
 };
+__host__ __device__ __forceinline__ size_t score_tab_bytes(int nexec, int nd) {
+    return ((size_t)2 * nexec * nd + nd + kTR + kTR + nd) * 8;
+}
 constexpr int kChunkTab = kMaxChunk + 4;   // shared-memory copies of the chunk tables, +inf padded
 constexpr int kChunkTabBytes = kChunkTab * 24;
 // qwarps: warps that own a tail queue (0: none), qcap: records per queue
-__host__ __device__ __forceinline__ size_t score_smem_bytes(int BD, int NQ, int sh_pairs, int qwarps, int qcap) {
-    return (size_t)BD * 4 * NQ * 8 + 32 + 128 + 64 + kChunkTabBytes + (size_t)kStage * sizeof(Cand) + (size_t)qwarps * qcap * 24 +
-           (size_t)sh_pairs * 2 * kShI * kShK * 4;
+// tab_nexec / tab_nd: size the per-CTA table copies (0: none)
+__host__ __device__ __forceinline__ size_t score_smem_bytes(int BD, int NQ, int sh_pairs, int qwarps, int qcap, int tab_nexec, int tab_nd) {
+    return (size_t)BD * 4 * NQ * 8 + 32 + 128 + 64 + kChunkTabBytes + (size_t)kStage * sizeof(Cand) + (size_t)qwarps * qcap * 28 +
+           (tab_nd ? score_tab_bytes(tab_nexec, tab_nd) : 0) + (size_t)sh_pairs * 2 * kShI * kShK * 4;
 }
-__device__ __forceinline__ ScoreSmem score_smem(unsigned char* smem, int BD, int NQ, int qwarps, int qcap) {
+__device__ __forceinline__ ScoreSmem score_smem(unsigned char* smem, int BD, int NQ, int qwarps, int qcap, int tab_nexec, int tab_nd) {
     ScoreSmem S;
     unsigned char* p = smem;
     S.tile = reinterpret_cast<double*>(p); p += (size_t)BD * 4 * NQ * 8;
@@ -195,7 +206,15 @@ __device__ __forceinline__ ScoreSmem score_smem(unsigned char* smem, int BD, int
     S.stage = reinterpret_cast<Cand*>(p); p += (size_t)kStage * sizeof(Cand);
     S.qsum = reinterpret_cast<double2*>(p);
     S.qmeta = reinterpret_cast<int2*>(p + (size_t)qwarps * qcap * 16);
-    p += (size_t)qwarps * qcap * 24;
+    S.qobs = reinterpret_cast<int*>(p + (size_t)qwarps * qcap * 24);
+    p += (size_t)qwarps * qcap * 28;
+    p += (16 - ((size_t)(p - smem) & 15)) & 15;
+    S.tb_be = reinterpret_cast<double*>(p);
+    S.tb_ir = S.tb_be + (size_t)2 * tab_nexec * tab_nd;
+    S.tb_b1 = S.tb_ir + tab_nd;
+    S.tb_b2 = S.tb_b1 + kTR;
+    S.tb_d0 = 0; S.tb_nd = tab_nd; S.tb_r0 = 0;
+    if (tab_nd) p += score_tab_bytes(tab_nexec, tab_nd);
     S.hist = reinterpret_cast<unsigned int*>(p);
     return S;
 }
@@ -229,9 +248,10 @@ struct TailAcc {                       // per-thread running totals of a single-
 // Per-pixel tail (callers.py:244-256 + chunk id + histograms), called by every lane of a converged warp.
 // `act`: this lane holds a pixel (r, r + d) that resolves pair `pi` at executed step `s` with donut /
 // lower-left sums SK, SY; s and pi may differ between lanes.  NPW == 1: single pair, totals kept in `acc`.
-template <int NPW>
+// SM: the small tables come from the CTA's shared-memory copies and the raw count from `obs_in`.
+template <int NPW, bool SM>
 __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem& sh, TailAcc& acc, bool act, double SK, double SY,
-                                            int r, int d, int s, int pi, int lane) {
+                                            int r, int d, int s, int pi, int lane, int obs_in) {
     const int nexec = A.nexec;
     const int mc = A.maxchunk;
     if (NPW == 1) pi = 0;
@@ -240,18 +260,24 @@ __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem&
     double Ev[2] = {0.0, 0.0};
     int obs = 0;
     if (act) {
-        obs = A.raw[qidx(d, r, A.pitch)];
+        obs = SM ? obs_in : A.raw[qidx(d, r, A.pitch)];
         double be[2];
         const bool top = r < A.F, end = r + d >= A.n - A.F;
         if (top && end) {                      // chromosome shorter than the band + two windows: walk the cell list
             edge_be(A.tab, A.ir, r, d, A.n, A.num, A.bal_first, s, be[0], be[1]);
+        } else if (SM && !top && !end) {
+            const double* bt = sh.tb_be + (size_t)s * sh.tb_nd + (d - sh.tb_d0);
+            be[0] = bt[0];
+            be[1] = bt[(size_t)nexec * sh.tb_nd];
         } else {
             const int z = top ? 1 + r : end ? 1 + A.F + (A.n - 1 - r - d) : 0;
             const double* bt = A.betab + ((size_t)(z * 2) * nexec + s) * A.num + d;
             be[0] = bt[0];
             be[1] = bt[(size_t)nexec * A.num];
         }
-        const double ird = A.ir[d], bb1 = A.b1[r], bb2 = A.b2[r + d];
+        const double ird = SM ? sh.tb_ir[d - sh.tb_d0] : A.ir[d];
+        const double bb1 = SM ? sh.tb_b1[r - sh.tb_r0] : A.b1[r];
+        const double bb2 = SM ? sh.tb_b2[r + d - sh.tb_r0 - sh.tb_d0] : A.b2[r + d];
 #pragma unroll
         for (int fl = 0; fl < 2; ++fl) {
             if (fl == 1 && A.bhfdr) break;
@@ -404,7 +430,7 @@ __device__ __forceinline__ void score_epilogue(const ScoreArgs& A, const ScoreSm
 // generic kernel: walks the op table of the sweep program, one pixel per thread per diagonal
 __global__ void __launch_bounds__(kThreads) k_score(const __grid_constant__ CUtensorMap tm_bal, ScoreArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const ScoreSmem sh = score_smem(smem, A.BD, A.NQ, 0, 0);
+    const ScoreSmem sh = score_smem(smem, A.BD, A.NQ, 0, 0, 0, 0);
     const int sh_bins = A.sh_pairs * 2 * kShI * kShK;
     const int r0 = blockIdx.x * kTR;
     const int d0 = A.dlo + blockIdx.y * A.TD;
@@ -449,7 +475,7 @@ __global__ void __launch_bounds__(kThreads) k_score(const __grid_constant__ CUte
             }
             const int pi = T.prog.step_pi[s];
             const bool em = (s <= last) && (d >= T.prog.ww[pi]) && (T.prog.next_step[pi][lv] == s);
-            if (__any_sync(0xffffffffu, em)) emit_record<0>(A, sh, tacc, em, SK, SY, r, d, s, pi, lane);
+            if (__any_sync(0xffffffffu, em)) emit_record<0, false>(A, sh, tacc, em, SK, SY, r, d, s, pi, lane, 0);
         }
     }
     score_epilogue(A, sh, sh_bins);

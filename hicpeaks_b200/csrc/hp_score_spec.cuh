@@ -193,12 +193,30 @@ template <class PG>
 __global__ void __launch_bounds__(kSpecThreads, HP_SPEC_MINB) k_score_spec(const __grid_constant__ CUtensorMap tm_bal,
                                                                             const __grid_constant__ ScoreArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const ScoreSmem sh = score_smem(smem, A.BD, kNQ, kSpecThreads / 32, kQCap);
+    ScoreSmem sh = score_smem(smem, A.BD, kNQ, kSpecThreads / 32, kQCap, A.nexec, A.TD + 8);
     const int sh_bins = A.sh_pairs * 2 * kShI * kShK;
     const int r0 = blockIdx.x * kTR;
     // far diagonals first: they run the deepest levels, so the cheap tiles fill the tail of the grid
     const int d0 = A.dlo + (int)(gridDim.y - 1 - blockIdx.y) * A.TD;
     const int plane0 = d0 - 3 - 2 * A.F;
+    // per-CTA copies of the tables the tail reads: bE of interior pixels, IR, biases of the tile's rows / columns
+    sh.tb_d0 = d0 - 3; sh.tb_r0 = r0;
+    {
+        const int nd = sh.tb_nd, nexec = A.nexec;
+        for (int t = threadIdx.x; t < 2 * nexec * nd; t += kSpecThreads) {
+            const int dd = t % nd, fs = t / nd, d = sh.tb_d0 + dd;       // fs = fl * nexec + s; interior table is z = 0
+            sh.tb_be[t] = (d >= 0 && d < A.num) ? A.betab[(size_t)fs * A.num + d] : 0.0;
+        }
+        for (int t = threadIdx.x; t < nd; t += kSpecThreads) {
+            const int d = sh.tb_d0 + t;
+            sh.tb_ir[t] = (d >= 0 && d < A.num) ? A.ir[d] : 0.0;
+        }
+        for (int t = threadIdx.x; t < kTR; t += kSpecThreads) sh.tb_b1[t] = r0 + t < A.n ? A.b1[r0 + t] : 0.0;
+        for (int t = threadIdx.x; t < kTR + nd; t += kSpecThreads) {
+            const int c = r0 + sh.tb_d0 + t;
+            sh.tb_b2[t] = (c >= 0 && c < A.n) ? A.b2[c] : 0.0;
+        }
+    }
     score_prologue(A, sh, &tm_bal, A.BD * 4 * kNQ * 8, (r0 - kHR) / 4, plane0, sh_bins);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -207,33 +225,68 @@ __global__ void __launch_bounds__(kSpecThreads, HP_SPEC_MINB) k_score_spec(const
     const int dspan = A.dspan;
     double2* qs = sh.qsum + warp * kQCap;
     int2* qm = sh.qmeta + warp * kQCap;
+    int* qo = sh.qobs + warp * kQCap;
     int cnt = 0;                                     // warp-uniform queue fill
     TailAcc tacc{};
+    const int ntask = min(A.TD / kTC, (A.dhi + 3 - d0) / kTC + 1);   // column blocks with a pixel in [dlo, dhi]
     for (;;) {
-        int kb = 0;                                  // column blocks are claimed dynamically: deep (sparse) blocks take longer
-        if (lane == 0) kb = (int)atomicAdd(sh.next, 1u);
+        int kb = 0;                                  // column blocks are claimed dynamically, deepest (largest d) first
+#ifdef HP_TASK_ASC
+        if (lane == 0) { kb = (int)atomicAdd(sh.next, 1u); if (kb >= ntask) kb = -1; }
+#else
+        if (lane == 0) kb = ntask - 1 - (int)atomicAdd(sh.next, 1u);
+#endif
         kb = __shfl_sync(0xffffffffu, kb, 0);
+        if (kb < 0) break;
         const int dc = d0 + kb * kTC;                // diagonal of pixel (0, 0) of the block; warp-uniform
-        if (kb * kTC >= A.TD || dc - 3 > A.dhi) break;
         unsigned lvp[4];                             // levels of the 16 pixels, one byte each, [i] = row
         int last = -1;
+        // whole block inside the band and the chromosome (true for almost every block): no per-pixel bounds checks
+        const bool interior = dc - 3 >= A.dlo && dc + kTC - 1 <= A.dhi && r0 + kTR - 1 + dc + kTC - 1 < A.n;
+        int obsv[4][kTC];                            // raw counts, loaded now so that the tail never waits on HBM
+        if (interior) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            unsigned pk = 0;
+            for (int i = 0; i < 4; ++i) {
+                unsigned pk = 0;
+#pragma unroll
+                for (int j = 0; j < kTC; ++j) {
+                    const size_t q = qidx(dc + j - i, r + i, A.pitch);
+                    pk |= (unsigned)A.lvl[q] << (8 * j);
+                    obsv[i][j] = A.raw[q];
+                }
+                lvp[i] = pk;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                unsigned pk = 0;
+#pragma unroll
+                for (int j = 0; j < kTC; ++j) {
+                    const int rr = r + i, d = dc + j - i;
+                    unsigned lv = kLvlNone;
+                    obsv[i][j] = 0;
+                    if (d >= A.dlo && d <= A.dhi && rr < A.n && rr + d < A.n) {
+                        const size_t q = qidx(d, rr, A.pitch);
+                        lv = A.lvl[q];
+                        obsv[i][j] = A.raw[q];
+                    }
+                    pk |= lv << (8 * j);
+                }
+                lvp[i] = pk;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < kTC; ++j) {
-                const int rr = r + i, d = dc + j - i;
-                unsigned lv = kLvlNone;
-                if (d >= A.dlo && d <= A.dhi && rr < A.n && rr + d < A.n) lv = A.lvl[qidx(d, rr, A.pitch)];
-                pk |= lv << (8 * j);
+                const unsigned lv = (lvp[i] >> (8 * j)) & 0xffu;
                 if (lv < kLvlNever) {
+                    const int d = dc + j - i;
                     const int k = d - A.dlo < dspan ? d - A.dlo : dspan;
                     const int rs = A.last_need[k][lv];
                     if (rs != kNoStep && rs > last) last = rs;
                 }
             }
-            lvp[i] = pk;
-        }
         const int wlast = __reduce_max_sync(0xffffffffu, last);
         if (wlast < 0) continue;
         double aK[4][kTC], aY[4][kTC];
@@ -253,7 +306,9 @@ __global__ void __launch_bounds__(kSpecThreads, HP_SPEC_MINB) k_score_spec(const
 #pragma unroll
                 for (int j = 0; j < kTC; ++j) {
                     const int lv = (lvp[i] >> (8 * j)) & 0xff;
-                    if (lv >= lo && lv <= s && (dc + j - i) >= wmin) em |= 1u << (i * kTC + j);
+                    // single pair: level s resolves at step s (every in-band diagonal is >= ww)
+                    const bool e = PG::npw == 1 ? lv == s : (lv >= lo && lv <= s && (dc + j - i) >= wmin);
+                    if (e) em |= 1u << (i * kTC + j);
                 }
             if (!__any_sync(0xffffffffu, em != 0u)) continue;
 #pragma unroll 1
@@ -271,6 +326,7 @@ __global__ void __launch_bounds__(kSpecThreads, HP_SPEC_MINB) k_score_spec(const
                                 const int slot = cnt + __popc(m & lt);
                                 qs[slot] = make_double2(aK[ii][j], aY[ii][j]);
                                 qm[slot] = make_int2(r + ii, ((dc + j - ii) << 16) | (s << 8) | pi);
+                                qo[slot] = obsv[ii][j];
                             }
                             cnt += __popc(m);
                         }
@@ -280,17 +336,20 @@ __global__ void __launch_bounds__(kSpecThreads, HP_SPEC_MINB) k_score_spec(const
                     cnt -= 32;
                     const double2 v = qs[cnt + lane];
                     const int2 mt = qm[cnt + lane];
-                    emit_record<PG::npw>(A, sh, tacc, true, v.x, v.y, mt.x, mt.y >> 16, (mt.y >> 8) & 0xff, mt.y & 0xff, lane);
+                    emit_record<PG::npw, true>(A, sh, tacc, true, v.x, v.y, mt.x, mt.y >> 16, (mt.y >> 8) & 0xff, mt.y & 0xff, lane,
+                                               qo[cnt + lane]);
                 }
                 __syncwarp();
             }
         }
     }
-    if (cnt > 0) {                                    // leftover records of this warp
-        const bool act = lane < cnt;
-        const double2 v = act ? qs[lane] : make_double2(0.0, 0.0);
-        const int2 mt = act ? qm[lane] : make_int2(0, 0);
-        emit_record<PG::npw>(A, sh, tacc, act, v.x, v.y, mt.x, mt.y >> 16, (mt.y >> 8) & 0xff, mt.y & 0xff, lane);
+    for (; cnt > 0; cnt -= 32) {                      // leftover records of this warp
+        const int k = cnt - 1 - lane;
+        const bool act = k >= 0;
+        const double2 v = act ? qs[k] : make_double2(0.0, 0.0);
+        const int2 mt = act ? qm[k] : make_int2(0, 0);
+        emit_record<PG::npw, true>(A, sh, tacc, act, v.x, v.y, mt.x, mt.y >> 16, (mt.y >> 8) & 0xff, mt.y & 0xff, lane,
+                                   act ? qo[k] : 0);
     }
     if (PG::npw == 1) tail_acc_flush(sh, tacc);
     score_epilogue(A, sh, sh_bins);
