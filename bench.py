@@ -12,8 +12,11 @@ per GPU) every rank owns its own batch (weak scaling, chromosomes are independen
 on the data path); value = all pixels / max-over-ranks time.
 
 `value`  : inputs resident in HBM, whole-job.        `e2e` : same steps with HOST buffers -- pack +
-H2D upload + kernels + survivor/gap D2H inside the timed region, through the C-ABI calls the
-reference-facing operator (hicpeaks_b200.callers.hiccups) makes.
+H2D upload + kernels + survivor/gap D2H inside the timed region, through the C-ABI calls of the
+reference-facing entry points.  Two boundaries are timed: the worker-level one the pyHICCUPS front end
+uses (hicpeaks_b200.callers.hiccups_from_counts: raw count diagonals + bin weights in, 4 B/pixel over
+PCIe; the balanced band / IR / biases of scripts/pyHICCUPS:149-166 are derived on the GPU) is `e2e`, and the
+operator-level one (callers.hiccups: Diags + cDiags + IR + biases in, 12 B/pixel) is `e2e_operator`.
 `--impl reference`: the CPU restatement of the reference path (oracle/, kind "port") on all host
 cores, bounded sample, same metric.
 """
@@ -207,16 +210,19 @@ def main():
             acc["ms_levels"] += S.ms_levels; acc["ms_score"] += S.ms_score; acc["ms_fdr"] += S.ms_fdr
         return acc
 
-    def e2e_one(job):
+    def e2e_one(job, counts):
         ctx, inp, (Dg, cD, ir) = job
-        ctx.upload(inp["n"], inp["num"], inp["min_ww"], Dg, cD, ir, inp["biases"], inp["biases"])
+        if counts:
+            ctx.upload_counts(inp["n"], inp["num"], inp["min_ww"], Dg, inp["weights"])
+        else:
+            ctx.upload(inp["n"], inp["num"], inp["min_ww"], Dg, cD, ir, inp["biases"], inp["biases"])
         S = ctx.hiccups(P)
         sv = ctx.survivors()
         g = ctx.gaps()
         return S.band_pixels, sv.nbytes + g.size * 4
 
-    def e2e_step():
-        res = list(pool.map(e2e_one, zip(ctxs, batch, arrays)))
+    def e2e_step(counts=True):
+        res = list(pool.map(lambda j: e2e_one(j, counts), zip(ctxs, batch, arrays)))
         return sum(r[0] for r in res), sum(r[1] for r in res)
 
     for _ in range(args.warmup):
@@ -239,19 +245,28 @@ def main():
             seq.append((S.ms_levels, S.ms_score, S.ms_fdr))
 
     for _ in range(2):
-        e2e_step()
+        e2e_step(False)
     barrier()
     t0 = time.perf_counter()
-    e2e_res = [e2e_step() for _ in range(args.steps)]
+    for _ in range(args.steps):
+        e2e_step(False)
+    barrier()
+    dt_e2e_op = time.perf_counter() - t0
+    for _ in range(2):
+        e2e_step(True)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_res = [e2e_step(True) for _ in range(args.steps)]
     barrier()
     dt_e2e = time.perf_counter() - t0
+    h2d_counts = sum(sum(a.nbytes for a in Dg) + inp["weights"].nbytes for inp, (Dg, cD, ir) in zip(batch, arrays))
 
     px_step = accs[0]["px"]
     if dist is not None:
         import torch
-        t = torch.tensor([dt, dt_e2e], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dt, dt_e2e, dt_e2e_op], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt, dt_e2e = t.tolist()
+        dt, dt_e2e, dt_e2e_op = t.tolist()
         c = torch.tensor([px_step], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         px_total = c.item()
@@ -291,9 +306,14 @@ def main():
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "alg_bytes_per_pixel": ALG_BYTES_PER_PIXEL, "pixels_per_launch": px_launch,
                      "avg_launch_ms": ms_score},
-        "e2e": {"value": e2e_value, "unit": "pixels/s", "h2d_bytes_per_step": h2d * world,
+        "e2e": {"value": e2e_value, "unit": "pixels/s", "h2d_bytes_per_step": h2d_counts * world,
                 "d2h_bytes_per_step": int(np.mean([r[1] for r in e2e_res])) * world,
-                "ms_per_step": 1e3 * dt_e2e / args.steps},
+                "ms_per_step": 1e3 * dt_e2e / args.steps,
+                "boundary": "worker level: callers.hiccups_from_counts / hp_band_upload_counts (raw int32 diagonals + bin weights "
+                            "from pageable host arrays; balanced band, IR, biases derived on the GPU)"},
+        "e2e_operator": {"value": px_total * args.steps / dt_e2e_op, "unit": "pixels/s", "h2d_bytes_per_step": h2d * world,
+                         "ms_per_step": 1e3 * dt_e2e_op / args.steps,
+                         "boundary": "operator level: callers.hiccups / hp_band_upload (Diags + cDiags + IR + biases, 12 B/pixel)"},
         "gpu_launches": int(sum(a["launches"] for a in accs)),
         "clocks": clocks,
         "survivors_per_step": accs[0]["surv"],

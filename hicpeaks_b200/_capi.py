@@ -34,7 +34,7 @@ LIB_PATH = os.environ.get("HICPEAKS_B200_LIB") or os.path.join(os.path.dirname(o
 # every symbol include/hicpeaks_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "hp_abi_version", "hp_device_count", "hp_ctx_create", "hp_ctx_destroy", "hp_last_error",
-    "hp_band_upload", "hp_hiccups_score", "hp_hiccups_fdr", "hp_hiccups", "hp_get_survivors",
+    "hp_band_upload", "hp_band_upload_counts", "hp_dump_band", "hp_hiccups_score", "hp_hiccups_fdr", "hp_hiccups", "hp_get_survivors",
     "hp_hist_bins", "hp_hist_export", "hp_hist_import", "hp_get_gaps", "hp_dump_levels", "hp_dump_plane", "hp_get_chunk_table", "hp_poisson_sf",
 ]
 
@@ -43,6 +43,11 @@ class BandDesc(C.Structure):
     _fields_ = [("n", C.c_int64), ("num", C.c_int32), ("bal_first", C.c_int32),
                 ("raw_diags", C.POINTER(C.c_void_p)), ("bal_diags", C.POINTER(C.c_void_p)),
                 ("ir", C.c_void_p), ("b1", C.c_void_p), ("b2", C.c_void_p)]
+
+
+class CountsDesc(C.Structure):
+    _fields_ = [("n", C.c_int64), ("num", C.c_int32), ("bal_first", C.c_int32),
+                ("raw_diags", C.POINTER(C.c_void_p)), ("weights", C.c_void_p)]
 
 
 class ApaDesc(C.Structure):
@@ -106,6 +111,8 @@ def load_library(path: str | None = None):
     lib.hp_last_error.argtypes = [vp]
     lib.hp_last_error.restype = C.c_char_p
     lib.hp_band_upload.argtypes = [vp, C.POINTER(BandDesc)]
+    lib.hp_band_upload_counts.argtypes = [vp, C.POINTER(CountsDesc)]
+    lib.hp_dump_band.argtypes = [vp, i32, vp, i64]
     lib.hp_hiccups_score.argtypes = [vp, C.POINTER(HiccupsParams), C.POINTER(HiccupsSummary)]
     lib.hp_hiccups_fdr.argtypes = [vp, vp, C.POINTER(HiccupsSummary)]
     lib.hp_hiccups.argtypes = [vp, C.POINTER(HiccupsParams), C.POINTER(HiccupsSummary)]
@@ -206,6 +213,28 @@ class Context:
                         ir.ctypes.data, b1.ctypes.data, b2.ctypes.data)
         self._check(self.lib.hp_band_upload(self._h, C.byref(desc)))
         self.n, self.num = int(n), int(num)
+
+    def upload_counts(self, n, num, bal_first, Diags, weights):
+        """Worker-level input: ``Diags`` (``num`` contiguous int32 arrays) and the bin weights (float64[n], NaN for
+        masked bins); the balanced band, IR and the biases are derived on the GPU (scripts/pyHICCUPS:143-166)."""
+        rp = (C.c_void_p * num)()
+        for d in range(num):
+            a = Diags[d]
+            if a.dtype != np.int32 or not a.flags.c_contiguous or a.size != n - d:
+                raise ValueError("Diags[%d] must be contiguous int32 of length %d" % (d, n - d))
+            rp[d] = a.ctypes.data
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        if w.size != n:
+            raise ValueError("weights length mismatch")
+        desc = CountsDesc(n, num, bal_first, C.cast(rp, C.POINTER(C.c_void_p)), w.ctypes.data)
+        self._check(self.lib.hp_band_upload_counts(self._h, C.byref(desc)))
+        self.n, self.num = int(n), int(num)
+
+    def dump_band(self, what):
+        shape = {0: (self.num,), 1: (self.n,), 2: (self.num, self.n)}[what]
+        out = np.empty(shape, dtype=np.float64)
+        self._check(self.lib.hp_dump_band(self._h, what, _ptr(out), out.size))
+        return out
 
     # -- scoring -------------------------------------------------------------------------------
     @staticmethod

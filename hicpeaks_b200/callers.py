@@ -81,12 +81,29 @@ def _numpy_numbin(e_max, n_valid):
     return int(np.ceil(np.log(e_max) / np.log(2) * 3 + 1))
 
 
+def _as_counts(Diags, num):
+    raw = []
+    for d in range(num):
+        a = np.asarray(Diags[d])
+        if a.dtype != np.int32:
+            b = a.astype(np.int32)
+            if not np.array_equal(b, a):
+                raise ValueError("Diags[%d] holds values that are not int32 counts" % d)
+            a = b
+        raw.append(np.ascontiguousarray(a))
+    return raw
+
+
 def score_chromosome(ctx, chromLen, Diags, cDiags, IR, B1, B2, num, pw, ww, maxww, sig, maxapart_bins,
-                     min_local_reads, chrom="", dump=False):
-    """Upload one chromosome band and run the GPU scoring path.  Returns (summary, survivors, gaps)."""
+                     min_local_reads, chrom="", dump=False, weights=None):
+    """Upload one chromosome band and run the GPU scoring path.  Returns (summary, survivors, gaps).
+    ``weights`` given: worker-level input (``cDiags`` / ``IR`` / biases are derived on the GPU)."""
     min_ww = min(ww)
-    raw, bal, ir = _as_diags(Diags, cDiags, IR, chromLen, num, min_ww)
-    ctx.upload(chromLen, num, min_ww, raw, bal, ir, B1, B2)
+    if weights is not None:
+        ctx.upload_counts(chromLen, num, min_ww, _as_counts(Diags, num), weights)
+    else:
+        raw, bal, ir = _as_diags(Diags, cDiags, IR, chromLen, num, min_ww)
+        ctx.upload(chromLen, num, min_ww, raw, bal, ir, B1, B2)
     P = ctx.make_params(pw, ww, maxww, sig, maxapart_bins, min_local_reads, dump=dump)
     try:
         S = ctx.score(P)
@@ -116,17 +133,24 @@ def _log_sweep(chrom, S):
         logger.info('Chrom:{0},    ({1},{2}) Total Valid Ratio after This Loop: {3:.3f}'.format(chrom, st.p, st.w, 1 - st.left_ratio))
 
 
+def hiccups_from_counts(weights, chromLen, Diags, num, chrom, **kw):
+    """The reference's per-chromosome worker minus the cooler fetch (/root/reference/scripts/pyHICCUPS:146-173):
+    takes the raw count diagonals and the bin weights, derives the balanced band, ``IR`` and the biases on the GPU
+    (bit-identical to the worker's numpy code) and calls the peak caller.  Same keywords and result as ``hiccups``."""
+    return hiccups(None, None, None, None, None, chromLen, Diags, None, num, chrom, weights=weights, **kw)
+
+
 def hiccups(M, cM, B1, B2, IR, chromLen, Diags, cDiags, num, chrom, pw=[2], ww=[5],
             maxww=20, sig=0.1, sumq=0.01, double_fold=1.75, single_fold=2, maxapart=2000000,
             res=10000, use_raw=False, min_marginal_peaks=3, onlyanchor=True, min_local_reads=25,
-            device=0):
+            device=0, weights=None):
     """HiCCUPS peak calling for one chromosome.  ``M`` and ``cM`` are accepted for signature parity;
     the engine reads the same data from ``Diags`` / ``cDiags``.  Returns
     ``{(x_bp, y_bp): (cx_bp, cy_bp, radius_bp, O, foldK, pK, qK, foldY, pY, qY)}``."""
     ctx = get_context(device)
     pw, ww = list(pw), list(ww)
     S, sv, gaps = score_chromosome(ctx, chromLen, Diags, cDiags, IR, B1, B2, num, pw, ww, maxww, sig,
-                                   maxapart // res, min_local_reads, chrom)
+                                   maxapart // res, min_local_reads, chrom, weights=weights)
     _log_sweep(chrom, S)
     logger.info('Chrom:{0}, Poisson Models and Benjamini-Hochberg Correcting for lambda chunks ...'.format(chrom))
     for pi, (p, w) in enumerate(zip(pw, ww)):
@@ -157,8 +181,13 @@ def bh_adjust(p, n, alpha):
     return reject, qv
 
 
+def bhfdr_from_counts(weights, chromLen, Diags, num, chrom, **kw):
+    """Worker-level entry of the BH-FDR caller (scripts/pyBHFDR:112-146), see ``hiccups_from_counts``."""
+    return bhfdr(None, None, None, None, None, chromLen, Diags, None, num, chrom, weights=weights, **kw)
+
+
 def bhfdr(M, cM, B1, B2, IR, chromLen, Diags, cDiags, num, chrom, pw=2, ww=5, sig=0.05,
-          maxww=20, maxapart=2000000, res=10000, min_marginal_peaks=3, onlyanchor=False, device=0):
+          maxww=20, maxapart=2000000, res=10000, min_marginal_peaks=3, onlyanchor=False, device=0, weights=None):
     """BH-FDR peak calling for one chromosome -- same contract as the reference's ``bhfdr``
     (/root/reference/hicpeaks/callers.py:364-590).  Returns ``{(x_bp, y_bp): (cx_bp, cy_bp, radius_bp, O, fold, p, q)}``.
 
@@ -166,8 +195,11 @@ def bhfdr(M, cM, B1, B2, IR, chromLen, Diags, cDiags, num, chrom, pw=2, ww=5, si
     tail (:536-540) for every pixel that can still pass ``sig``.  Host (a few thousand records): the chromosome-wide
     Benjamini-Hochberg step (:545-547), gap filter (:557-577), clustering (:580-582) and ``fold > 2`` (:587)."""
     ctx = get_context(device)
-    raw, bal, ir = _as_diags(Diags, cDiags, IR, chromLen, num, ww)
-    ctx.upload(chromLen, num, ww, raw, bal, ir, B1, B2)
+    if weights is not None:
+        ctx.upload_counts(chromLen, num, ww, _as_counts(Diags, num), weights)
+    else:
+        raw, bal, ir = _as_diags(Diags, cDiags, IR, chromLen, num, ww)
+        ctx.upload(chromLen, num, ww, raw, bal, ir, B1, B2)
     P = ctx.make_params([pw], [ww], maxww, sig, maxapart // res, 16, bhfdr=True)
     try:
         S = ctx.score(P)

@@ -147,6 +147,16 @@ def prepare_chromosome(Lib, key, weight_name, maxapart, maxww, min_ww, res):
     return dict(n=int(chromLen), num=int(num), min_ww=int(min_ww), Diags=Diags, cDiags=cDiags, IR=IR, biases=biases)
 
 
+def prepare_counts(Lib, key, weight_name, maxapart, maxww, res):
+    """Worker-level input for the engine: the raw count diagonals and the bin weights only; the balanced band, ``IR``
+    and the biases of pyHICCUPS:149-166 are derived on the GPU (``hicpeaks_b200.callers.hiccups_from_counts``)."""
+    H = Lib.matrix(balance=False, sparse=True).fetch(key)
+    num = maxapart // res + maxww + 1
+    Diags = [np.asarray(H.diagonal(i)) for i in np.arange(num)]
+    weights = np.asarray(Lib.bins().fetch(key)[weight_name].values, dtype=np.float64)
+    return dict(n=int(H.shape[0]), num=int(num), Diags=Diags, weights=weights)
+
+
 def _open_cooler(path):
     try:
         import cooler
@@ -233,9 +243,8 @@ def run_hiccups(argv=None, Lib=None):
             tables = runner.run({k: (lambda k=k: load(k)) for k in keys}, sizes, **kw)
         else:
             def one(key, gpu):
-                b = load(key)
-                return callers.hiccups(None, None, b["biases"], b["biases"], b["IR"], b["n"], b["Diags"], b["cDiags"],
-                                       b["num"], key.lstrip('chr'), device=gpu, **kw)
+                b = prepare_counts(Lib, key, args.clr_weight_name, args.maxapart, args.maxww, res)
+                return callers.hiccups_from_counts(b["weights"], b["n"], b["Diags"], b["num"], key.lstrip('chr'), device=gpu, **kw)
             sizes = {k: 1 for k in keys}
             tables = _map_over_gpus(keys, sizes, ngpu, one)
         with open(args.output, 'w') as OF:
@@ -260,10 +269,10 @@ def run_bhfdr(argv=None, Lib=None):
         log.info('Calling Peaks ...')
 
         def one(key, gpu):
-            b = prepare_chromosome(Lib, key, args.clr_weight_name, args.maxapart, args.maxww, args.ww, res)
-            return callers.bhfdr(None, None, b["biases"], b["biases"], b["IR"], b["n"], b["Diags"], b["cDiags"], b["num"],
-                                 key.lstrip('chr'), pw=args.pw, ww=args.ww, sig=args.siglevel, maxww=args.maxww,
-                                 maxapart=args.maxapart, res=res, device=gpu)
+            b = prepare_counts(Lib, key, args.clr_weight_name, args.maxapart, args.maxww, res)
+            return callers.bhfdr_from_counts(b["weights"], b["n"], b["Diags"], b["num"], key.lstrip('chr'), pw=args.pw,
+                                             ww=args.ww, sig=args.siglevel, maxww=args.maxww, maxapart=args.maxapart, res=res,
+                                             device=gpu)
 
         tables = _map_over_gpus(keys, {k: 1 for k in keys}, _n_gpus(args), one)
         with open(args.output, 'w') as OF:

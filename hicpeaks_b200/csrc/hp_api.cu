@@ -15,6 +15,7 @@
 #include "hp_kernels.cuh"
 #include "hp_score_spec.cuh"
 #include "hp_apa.cuh"
+#include "hp_prep.cuh"
 
 using namespace hp;
 
@@ -68,6 +69,9 @@ struct hp_ctx {
     unsigned int ncand = 0, nsurv = 0;
     bool spec_used = false;
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    // K0 scratch (hp_prep.cuh)
+    double* d_w = nullptr; size_t cap_w = 0;
+    unsigned char* d_prep = nullptr; size_t cap_prep = 0;
     // APA (hp_apa.cuh)
     double* d_apa_bal = nullptr; size_t cap_apa_bal = 0;
     int64_t apa_n = 0; int apa_num = 0;
@@ -206,7 +210,7 @@ extern "C" void hp_ctx_destroy(hp_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_ptab, ctx->d_raw, ctx->d_bal, ctx->d_lvl, ctx->d_ir, ctx->d_b1, ctx->d_b2, ctx->d_rownz,
                     ctx->d_lhist, ctx->d_betab, ctx->d_hist, ctx->d_qtab, ctx->d_small, ctx->d_cnt, ctx->d_numbin,
-                    ctx->d_cand, ctx->d_surv, ctx->d_dump, ctx->d_tmp, ctx->d_tab, ctx->d_apa_bal, ctx->d_apa_plan, ctx->d_apa_pos,
+                    ctx->d_cand, ctx->d_surv, ctx->d_dump, ctx->d_tmp, ctx->d_tab, ctx->d_w, ctx->d_prep, ctx->d_apa_bal, ctx->d_apa_plan, ctx->d_apa_pos,
                     ctx->d_apa_wins, ctx->d_apa_valid, ctx->d_apa_mean, ctx->d_apa_sel, ctx->d_apa_avg};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -217,11 +221,12 @@ extern "C" void hp_ctx_destroy(hp_ctx* ctx) {
 }
 
 // ---------------------------------------------------------------------------------------------
-extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
-    if (!ctx || !b) return fail(ctx, HP_ERR_INVALID, "NULL argument");
+static int band_alloc(hp_ctx* ctx, int64_t n_, int num_, int bal_first_) {
+    struct { int64_t n; int num; int bal_first; } bb{n_, num_, bal_first_};
+    auto* b = &bb;
+    if (!ctx) return fail(ctx, HP_ERR_INVALID, "NULL argument");
     if (b->n <= 0 || b->n > (1ll << 30) || b->num <= 0 || b->num > b->n || b->bal_first < 0 || b->bal_first >= b->num)
         return fail(ctx, HP_ERR_INVALID, "bad band geometry (need 0 < num <= n, 0 <= bal_first < num)");
-    if (!b->raw_diags || !b->bal_diags || !b->ir || !b->b1 || !b->b2) return fail(ctx, HP_ERR_INVALID, "NULL band array");
     CK(cudaSetDevice(ctx->device));
     ctx->have_band = false; ctx->scored = false; ctx->fdr_done = false;
     const int64_t n = b->n;
@@ -253,6 +258,20 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
         CK(cudaHostAlloc(&ctx->h_stage, stage_bytes, cudaHostAllocDefault));
         ctx->cap_stage = stage_bytes;
     }
+    return HP_OK;
+}
+
+extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
+    if (!ctx || !b) return fail(ctx, HP_ERR_INVALID, "NULL argument");
+    if (!b->raw_diags || !b->bal_diags || !b->ir || !b->b1 || !b->b2) return fail(ctx, HP_ERR_INVALID, "NULL band array");
+    {
+        const int rc0 = band_alloc(ctx, b->n, b->num, b->bal_first);
+        if (rc0) return rc0;
+    }
+    const int64_t n = b->n;
+    const int num = b->num;
+    const int pitch = (int)((n + 31) / 32 * 32);
+    const size_t plane = (size_t)num * pitch;
     double* hbal = (double*)ctx->h_stage;
     int* hraw = (int*)((char*)ctx->h_stage + plane * 8);
     double* hir = (double*)((char*)ctx->h_stage + plane * 12);
@@ -323,6 +342,117 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->n = n; ctx->num = num; ctx->bal_first = bf; ctx->pitch = pitch; ctx->plane = plane;
     ctx->have_band = true;
+    return HP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// worker-level entry: raw counts + balancing weights; the balanced band, IR and the biases are built on the
+// device exactly as the reference's worker builds them on the host (scripts/pyHICCUPS:143-166)
+extern "C" int hp_band_upload_counts(hp_ctx* ctx, const hp_counts_desc* b) {
+    if (!ctx || !b) return fail(ctx, HP_ERR_INVALID, "NULL argument");
+    if (!b->raw_diags || !b->weights) return fail(ctx, HP_ERR_INVALID, "NULL band array");
+    {
+        const int rc0 = band_alloc(ctx, b->n, b->num, b->bal_first);
+        if (rc0) return rc0;
+    }
+    const int64_t n = b->n;
+    const int num = b->num, bf = b->bal_first;
+    const int pitch = (int)((n + 31) / 32 * 32);
+    const size_t plane = (size_t)num * pitch;
+    cudaStream_t st = ctx->stream;
+    int* hraw = (int*)((char*)ctx->h_stage + plane * 8);
+    int* traw = (int*)((char*)ctx->d_tmp + plane * 8);
+    double* comp = ctx->d_tmp;                        // [num - bf][pitch] compaction scratch (the unused balanced landing zone)
+    CK(ensure(&ctx->d_w, &ctx->cap_w, (size_t)n + 64));
+    const int maxleaf = pitch / 64 + 8;
+    const int nb = num - bf;
+    const size_t prep_bytes = (size_t)nb * maxleaf * (8 + 8 + 64);
+    CK(ensure(&ctx->d_prep, &ctx->cap_prep, prep_bytes));
+    int2* leaf = (int2*)ctx->d_prep;
+    int2* comb = leaf + (size_t)nb * maxleaf;
+    double* part = (double*)(comb + (size_t)nb * maxleaf);
+    CK(cudaMemcpyAsync(ctx->d_w, b->weights, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    // raw counts: packed by worker threads chunk by chunk while the copy engine uploads the previous chunk
+    auto pack = [&](int d_begin, int d_end) {
+        for (int d = d_begin; d < d_end; ++d) {
+            const size_t len = (size_t)(n - d);
+            int* rr = hraw + (size_t)d * pitch;
+            memcpy(rr, b->raw_diags[d], len * sizeof(int));
+            memset(rr + len, 0, (pitch - len) * sizeof(int));
+        }
+    };
+    const int per = std::max(1, (int)((size_t)(8u << 20) / ((size_t)pitch * 4)));
+    const int nchunk = (num + per - 1) / per;
+    unsigned nthreads = std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    if (plane < (1u << 20)) nthreads = 1;
+    cudaError_t cerr = cudaSuccess;
+    auto send = [&](int k) {
+        const int d0 = k * per, d1 = std::min(num, d0 + per);
+        const size_t off = (size_t)d0 * pitch, cnt = (size_t)(d1 - d0) * pitch;
+        cudaError_t e = cudaMemcpyAsync(traw + off, hraw + off, cnt * 4, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess && cerr == cudaSuccess) cerr = e;
+    };
+    if (nthreads == 1) {
+        for (int k = 0; k < nchunk; ++k) { pack(k * per, std::min(num, (k + 1) * per)); send(k); }
+    } else {
+        std::atomic<int> next{0};
+        std::vector<std::atomic<int>> done(nchunk);
+        for (auto& f : done) f.store(0, std::memory_order_relaxed);
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nthreads; ++t)
+            th.emplace_back([&]() {
+                for (;;) {
+                    const int k = next.fetch_add(1);
+                    if (k >= nchunk) break;
+                    pack(k * per, std::min(num, (k + 1) * per));
+                    done[k].store(1, std::memory_order_release);
+                }
+            });
+        for (int k = 0; k < nchunk; ++k) {
+            while (!done[k].load(std::memory_order_acquire)) std::this_thread::yield();
+            send(k);
+        }
+        for (auto& t : th) t.join();
+    }
+    if (cerr != cudaSuccess) return fail(ctx, HP_ERR_CUDA, std::string("band upload: ") + cudaGetErrorString(cerr));
+    CK(cudaMemsetAsync(ctx->d_rownz, 0, (size_t)n * sizeof(unsigned int), st));
+    CK(cudaMemsetAsync(ctx->d_ir, 0, (size_t)num * 8, st));
+    k_relayout<int><<<dim3((pitch + 255) / 256, num), 256, 0, st>>>(traw, ctx->d_raw, nullptr, pitch, num);
+    CK(cudaGetLastError());
+    if (bf > 0) {
+        const size_t cnt = (size_t)bf * pitch;
+        k_zero_planes<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(ctx->d_bal, cnt);
+    }
+    k_prep_band<<<nb, kPrepThreads, 0, st>>>(traw, ctx->d_w, (int)n, num, pitch, bf, ctx->d_bal, ctx->d_rownz, ctx->d_ir, comp, leaf, part,
+                                           comb, maxleaf);
+    CK(cudaGetLastError());
+    k_prep_bias<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_w, ctx->d_b1, ctx->d_b2, (int)n);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    ctx->n = n; ctx->num = num; ctx->bal_first = bf; ctx->pitch = pitch; ctx->plane = plane;
+    ctx->have_band = true;
+    return HP_OK;
+}
+
+// inspection: what = 0 IR[num], 1 B1[n], 2 balanced band [num][n] (plain layout)
+extern "C" int hp_dump_band(hp_ctx* ctx, int32_t what, double* out, int64_t capacity) {
+    if (!ctx || !out) return fail(ctx, HP_ERR_INVALID, "NULL argument");
+    if (!ctx->have_band) return fail(ctx, HP_ERR_STATE, "upload a band first");
+    CK(cudaSetDevice(ctx->device));
+    if (what == 0 || what == 1) {
+        const int64_t cnt = what == 0 ? ctx->num : ctx->n;
+        if (capacity < cnt) return fail(ctx, HP_ERR_CAPACITY, "buffer too small");
+        CK(cudaMemcpyAsync(out, what == 0 ? ctx->d_ir : ctx->d_b1, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return HP_OK;
+    }
+    if (what != 2) return fail(ctx, HP_ERR_INVALID, "bad selector");
+    if (capacity < (int64_t)ctx->num * ctx->n) return fail(ctx, HP_ERR_CAPACITY, "buffer too small");
+    std::vector<double> tmp(ctx->plane);
+    CK(cudaMemcpyAsync(tmp.data(), ctx->d_bal, ctx->plane * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int d = 0; d < ctx->num; ++d)
+        for (int64_t r = 0; r < ctx->n; ++r) out[(size_t)d * ctx->n + r] = tmp[qidx(d, (int)r, ctx->pitch)];
     return HP_OK;
 }
 

@@ -1,0 +1,149 @@
+// K0 -- the worker's input preparation on the device (/root/reference/scripts/pyHICCUPS:143-166).
+//
+// From raw counts and the balancing weights it builds what the reference's worker hands to hiccups():
+//   balanced diagonal d   = count * w[r] * w[r + d] where a count is stored (cooler's `balance=` transform,
+//                           evaluated left to right), 0 elsewhere, NaN -> 0                  (:143, :153-157)
+//   IR[d]                 = mean of the non-NaN entries of that diagonal, zeros included     (:154-156)
+//   biases                = 1 / w, 0 where w is 0 or NaN                                     (:163-166)
+// so that only 4 bytes per band pixel cross PCIe instead of 12.  `ndarray.mean()` is numpy's pairwise
+// summation (see hp_apa.cuh) over the COMPACTED array of non-NaN entries; the kernel compacts each
+// diagonal and walks the same recursion, so IR is bit-identical to the reference's.
+#pragma once
+#include "hp_device.cuh"
+
+namespace hp {
+
+constexpr int kPrepThreads = 256;
+
+// one CTA per diagonal d in [bal_first, num).  comp: scratch [num][pitch] doubles; leaf: scratch [num][maxleaf] int2
+// (start, len); part: scratch [num][maxleaf * 8] doubles; comb: scratch [num][maxleaf] int2.
+__global__ void __launch_bounds__(kPrepThreads) k_prep_band(const int* __restrict__ raw_plain, const double* __restrict__ w, int n, int num,
+                                                            int pitch, int bal_first, double* __restrict__ bal, unsigned int* __restrict__ rownz,
+                                                            double* __restrict__ ir, double* __restrict__ comp, int2* __restrict__ leaf,
+                                                            double* __restrict__ part, int2* __restrict__ comb, int maxleaf) {
+    __shared__ int sh_scan[kPrepThreads / 32];
+    __shared__ int sh_base, sh_nleaf, sh_ncomb;
+    const int d = bal_first + blockIdx.x;
+    const int len = n - d;
+    const int* src = raw_plain + (size_t)d * pitch;
+    double* cp = comp + (size_t)blockIdx.x * pitch;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) sh_base = 0;
+    __syncthreads();
+    // ---- balanced values, NaN compaction (order preserved) ------------------------------------------
+    for (int r0 = 0; r0 < pitch; r0 += kPrepThreads) {
+        const int r = r0 + threadIdx.x;
+        double v = 0.0;
+        bool in = r < len;
+        if (in) {
+            const int c = src[r];
+            if (c != 0) v = __dmul_rn(__dmul_rn((double)c, w[r]), w[r + d]);
+        }
+        const bool isn = v != v;
+        const bool keep = in && !isn;
+        if (r < pitch) {
+            const double out = isn ? 0.0 : v;
+            bal[qidx(d, r, pitch)] = out;
+            if (out != 0.0) rownz[r] = 1u;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) sh_scan[wid] = __popc(m);
+        __syncthreads();
+        int pre = sh_base;
+        for (int k = 0; k < wid; ++k) pre += sh_scan[k];
+        if (keep) cp[pre + __popc(m & ((1u << lane) - 1u))] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int k = 0; k < kPrepThreads / 32; ++k) tot += sh_scan[k];
+            sh_base += tot;
+        }
+        __syncthreads();
+    }
+    const int m = sh_base;
+    // ---- numpy pairwise_sum(cp[0..m)) -------------------------------------------------------------------
+    int2* lf = leaf + (size_t)blockIdx.x * maxleaf;
+    int2* cb = comb + (size_t)blockIdx.x * maxleaf;
+    double* pt = part + (size_t)blockIdx.x * maxleaf * 8;
+    if (threadIdx.x == 0) {
+        // depth-first walk of the recursion: leaves left to right, combines in post-order
+        int nleaf = 0, ncomb = 0, sp = 0;
+        int st_start[40], st_n[40], st_state[40], st_left[40];
+        st_start[0] = 0; st_n[0] = m; st_state[0] = 0; st_left[0] = 0;
+        int ret = 0;                                   // leaf slot that holds the result of the last finished node
+        while (sp >= 0) {
+            const int s0 = st_start[sp], nn = st_n[sp];
+            if (nn <= 128) {
+                lf[nleaf] = make_int2(s0, nn);
+                ret = nleaf++;
+                --sp;
+                continue;
+            }
+            int n2 = nn / 2;
+            n2 -= n2 % 8;
+            if (st_state[sp] == 0) {                   // descend left
+                st_state[sp] = 1;
+                ++sp; st_start[sp] = s0; st_n[sp] = n2; st_state[sp] = 0;
+            } else if (st_state[sp] == 1) {            // left done, descend right
+                st_left[sp] = ret;
+                st_state[sp] = 2;
+                ++sp; st_start[sp] = s0 + n2; st_n[sp] = nn - n2; st_state[sp] = 0;
+            } else {                                   // both done: res[left] += res[right]
+                cb[ncomb++] = make_int2(st_left[sp], ret);
+                ret = st_left[sp];
+                --sp;
+            }
+        }
+        sh_nleaf = nleaf; sh_ncomb = ncomb;
+    }
+    __syncthreads();
+    const int nleaf = sh_nleaf;
+    for (int t = threadIdx.x; t < nleaf * 8; t += kPrepThreads) {
+        const int2 L = lf[t >> 3];
+        const int j = t & 7;
+        double r = 0.0;
+        if (L.y >= 8) {
+            r = cp[L.x + j];
+            for (int i = 8; i < L.y - (L.y % 8); i += 8) r = __dadd_rn(r, cp[L.x + i + j]);
+        }
+        pt[t] = r;
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l < nleaf; l += kPrepThreads) {
+        const int2 L = lf[l];
+        double r;
+        if (L.y < 8) {
+            r = 0.0;
+            for (int i = 0; i < L.y; ++i) r = __dadd_rn(r, cp[L.x + i]);
+        } else {
+            const double* p = pt + l * 8;
+            r = __dadd_rn(__dadd_rn(__dadd_rn(p[0], p[1]), __dadd_rn(p[2], p[3])), __dadd_rn(__dadd_rn(p[4], p[5]), __dadd_rn(p[6], p[7])));
+            for (int i = L.y - (L.y % 8); i < L.y; ++i) r = __dadd_rn(r, cp[L.x + i]);
+        }
+        pt[l * 8] = r;                                 // only this thread reads the 8 partials of leaf l
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int ncomb = sh_ncomb;
+        for (int k = 0; k < ncomb; ++k) pt[cb[k].x * 8] = __dadd_rn(pt[cb[k].x * 8], pt[cb[k].y * 8]);
+        ir[d] = __ddiv_rn(m ? pt[0] : 0.0, (double)m);     // mean of an empty slice is NaN, as numpy's
+    }
+}
+
+// biases = 1 / w (0 where w is 0 or NaN) -- pyHICCUPS:163-166
+__global__ void k_prep_bias(const double* __restrict__ w, double* __restrict__ b1, double* __restrict__ b2, int n) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const double v = w[r];
+    const double b = (v == 0.0 || v != v) ? 0.0 : __ddiv_rn(1.0, v);
+    b1[r] = b;
+    b2[r] = b;
+}
+
+// planes below bal_first hold no balanced values
+__global__ void k_zero_planes(double* __restrict__ bal, size_t count) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) bal[i] = 0.0;
+}
+
+}  // namespace hp

@@ -78,6 +78,22 @@ typedef struct hp_band_desc {
 } hp_band_desc;
 int hp_band_upload(hp_ctx* ctx, const hp_band_desc* band);
 
+/* Worker-level input (replaces the whole input preparation of scripts/pyHICCUPS:143-166): raw count
+ * diagonals and the balancing weight of every bin (cooler's `bins[weight]`, NaN for masked bins).  The
+ * balanced band (count * w[r] * w[c], NaN -> 0), IR[d] (mean of the non-NaN entries of balanced diagonal d,
+ * bit-identical to numpy's mean) and the biases (1 / w, 0 where w is 0 or NaN) are computed on the device:
+ * 4 bytes per band pixel cross PCIe instead of 12. */
+typedef struct hp_counts_desc {
+    int64_t n;
+    int32_t num;
+    int32_t bal_first;                /* min(ww)                                            */
+    const int32_t* const* raw_diags;  /* [num]                                              */
+    const double* weights;            /* [n]                                                */
+} hp_counts_desc;
+int hp_band_upload_counts(hp_ctx* ctx, const hp_counts_desc* band);
+/* inspection of the uploaded / derived band: what = 0 IR[num], 1 biases[n], 2 balanced band [num][n] */
+int hp_dump_band(hp_ctx* ctx, int32_t what, double* out, int64_t capacity);
+
 /* ---- HiCCUPS scoring: callers.py:98-287 ------------------------------------------------------ */
 typedef struct hp_hiccups_params {
     int32_t npw;                 /* number of (pw, ww) pairs                                   */

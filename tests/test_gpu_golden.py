@@ -109,3 +109,27 @@ def test_bhfdr_matches_reference(name):
     assert np.array_equal(s["r"], surv[0]) and np.array_equal(s["c"], surv[1])
     assert np.array_equal(s["e"][:, 0], surv[3])
     assert np.abs(s["p"][:, 0] - surv[4]).max() <= Q_TOL and np.abs(q[reject] - surv[5]).max() <= Q_TOL
+
+
+@pytest.mark.parametrize("name", ["chr21_25k_p1w3", "synth_p2w5", "synth_union_124", "synth_p4w7"])
+def test_device_input_prep_is_bit_identical(name):
+    """K0: balanced band, IR (numpy's pairwise mean over the non-NaN entries) and biases derived on the GPU from raw
+    counts + weights equal the worker's host arrays bit for bit (scripts/pyHICCUPS:143-166)."""
+    z, inp, kw, res = gu.load(name)
+    n, num, mw = inp["n"], inp["num"], inp["min_ww"]
+    ctx = callers.get_context(0)
+    ctx.upload_counts(n, num, mw, [np.ascontiguousarray(d, dtype=np.int32) for d in inp["Diags"]], inp["weights"])
+    ir = ctx.dump_band(0)
+    exp = np.array([inp["IR"][d] for d in range(mw, num)])
+    assert np.array_equal(ir[mw:], exp, equal_nan=True) and np.all(ir[:mw] == 0)
+    assert np.array_equal(ctx.dump_band(1), inp["biases"])
+    bal = ctx.dump_band(2)
+    for i, d in enumerate(range(mw, num)):
+        assert np.array_equal(bal[d, : n - d], inp["cDiags"][i]), d
+    assert np.all(bal[:mw] == 0)
+    if str(z["raises"]):
+        return
+    a = callers.hiccups_from_counts(inp["weights"], n, inp["Diags"], num, "21", res=res, **kw)
+    b = callers.hiccups(None, None, inp["biases"], inp["biases"], dict(inp["IR"]), n, inp["Diags"], inp["cDiags"], num, "21",
+                        res=res, **kw)
+    assert a == b and np.array_equal(gu.table_rows(a)[:, :6], z["table"][:, :6])
