@@ -36,6 +36,7 @@ SYMBOLS = [
     "hp_abi_version", "hp_device_count", "hp_ctx_create", "hp_ctx_destroy", "hp_last_error",
     "hp_band_upload", "hp_band_upload_counts", "hp_dump_band", "hp_hiccups_score", "hp_hiccups_fdr", "hp_hiccups", "hp_get_survivors",
     "hp_hist_bins", "hp_hist_export", "hp_hist_import", "hp_get_gaps", "hp_dump_levels", "hp_dump_plane", "hp_get_chunk_table", "hp_poisson_sf",
+    "hp_apa_upload", "hp_apa_windows", "hp_apa_load_windows", "hp_apa_accumulate", "hp_apa_get_windows",
 ]
 
 

@@ -296,7 +296,7 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
     for (int d = 0; d < num; ++d) hir[d] = d >= bf ? b->ir[d - bf] : 0.0;
     double* tbal = ctx->d_tmp;
     int* traw = (int*)((char*)ctx->d_tmp + plane * 8);
-    const int per = std::max(1, (int)((size_t)(8u << 20) / ((size_t)pitch * 12)));     // ~8 MB per chunk
+    const int per = std::max(1, (int)((size_t)(4u << 20) / ((size_t)pitch * 12)));     // ~4 MB per chunk
     const int nchunk = (num + per - 1) / per;
     unsigned nthreads = std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
     if (plane < (1u << 20)) nthreads = 1;
@@ -381,7 +381,7 @@ extern "C" int hp_band_upload_counts(hp_ctx* ctx, const hp_counts_desc* b) {
             memset(rr + len, 0, (pitch - len) * sizeof(int));
         }
     };
-    const int per = std::max(1, (int)((size_t)(8u << 20) / ((size_t)pitch * 4)));
+    const int per = std::max(1, (int)((size_t)(2u << 20) / ((size_t)pitch * 4)));      // ~2 MB per chunk
     const int nchunk = (num + per - 1) / per;
     unsigned nthreads = std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
     if (plane < (1u << 20)) nthreads = 1;
@@ -423,8 +423,9 @@ extern "C" int hp_band_upload_counts(hp_ctx* ctx, const hp_counts_desc* b) {
         const size_t cnt = (size_t)bf * pitch;
         k_zero_planes<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(ctx->d_bal, cnt);
     }
-    k_prep_band<<<nb, kPrepThreads, 0, st>>>(traw, ctx->d_w, (int)n, num, pitch, bf, ctx->d_bal, ctx->d_rownz, ctx->d_ir, comp, leaf, part,
-                                           comb, maxleaf);
+    const int prep_smem = maxleaf * 16 <= 40 * 1024 ? maxleaf * 16 : 0;
+    k_prep_band<<<nb, kPrepThreads, prep_smem, st>>>(traw, ctx->d_w, (int)n, num, pitch, bf, ctx->d_bal, ctx->d_rownz, ctx->d_ir, comp, leaf,
+                                                   part, comb, maxleaf, prep_smem ? 1 : 0);
     CK(cudaGetLastError());
     k_prep_bias<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_w, ctx->d_b1, ctx->d_b2, (int)n);
     CK(cudaGetLastError());

@@ -20,7 +20,8 @@ constexpr int kPrepThreads = 256;
 __global__ void __launch_bounds__(kPrepThreads) k_prep_band(const int* __restrict__ raw_plain, const double* __restrict__ w, int n, int num,
                                                             int pitch, int bal_first, double* __restrict__ bal, unsigned int* __restrict__ rownz,
                                                             double* __restrict__ ir, double* __restrict__ comp, int2* __restrict__ leaf,
-                                                            double* __restrict__ part, int2* __restrict__ comb, int maxleaf) {
+                                                            double* __restrict__ part, int2* __restrict__ comb, int maxleaf, int use_smem) {
+    extern __shared__ __align__(16) unsigned char prep_smem[];     // use_smem: [maxleaf] leaf sums + [maxleaf] combine list
     __shared__ int sh_scan[kPrepThreads / 32];
     __shared__ int sh_base, sh_nleaf, sh_ncomb;
     const int d = bal_first + blockIdx.x;
@@ -30,28 +31,43 @@ __global__ void __launch_bounds__(kPrepThreads) k_prep_band(const int* __restric
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) sh_base = 0;
     __syncthreads();
-    // ---- balanced values, NaN compaction (order preserved) ------------------------------------------
-    for (int r0 = 0; r0 < pitch; r0 += kPrepThreads) {
-        const int r = r0 + threadIdx.x;
-        double v = 0.0;
-        bool in = r < len;
-        if (in) {
-            const int c = src[r];
-            if (c != 0) v = __dmul_rn(__dmul_rn((double)c, w[r]), w[r + d]);
+    // ---- balanced values, NaN compaction (order preserved): 4 consecutive bins per thread and round ----------
+    for (int r0 = 0; r0 < pitch; r0 += kPrepThreads * 4) {
+        const int rb = r0 + threadIdx.x * 4;
+        double v[4];
+        bool keep[4];
+        int nk = 0;
+        int4 c4 = make_int4(0, 0, 0, 0);
+        if (rb < pitch) c4 = *reinterpret_cast<const int4*>(src + rb);          // pitch is a multiple of 32
+        const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = rb + k;
+            const bool in = r < len;
+            v[k] = 0.0;
+            if (in && cc[k] != 0) v[k] = __dmul_rn(__dmul_rn((double)cc[k], w[r]), w[r + d]);
+            const bool isn = v[k] != v[k];
+            keep[k] = in && !isn;
+            nk += keep[k];
+            if (r < pitch) {
+                const double out = isn ? 0.0 : v[k];
+                bal[qidx(d, r, pitch)] = out;
+                if (out != 0.0) rownz[r] = 1u;
+            }
         }
-        const bool isn = v != v;
-        const bool keep = in && !isn;
-        if (r < pitch) {
-            const double out = isn ? 0.0 : v;
-            bal[qidx(d, r, pitch)] = out;
-            if (out != 0.0) rownz[r] = 1u;
+        int inc = nk;                                                            // inclusive scan of nk over the block
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) sh_scan[wid] = __popc(m);
+        if (lane == 31) sh_scan[wid] = inc;
         __syncthreads();
-        int pre = sh_base;
+        int pre = sh_base + inc - nk;
         for (int k = 0; k < wid; ++k) pre += sh_scan[k];
-        if (keep) cp[pre + __popc(m & ((1u << lane) - 1u))] = v;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (keep[k]) cp[pre++] = v[k];
         __syncthreads();
         if (threadIdx.x == 0) {
             int tot = 0;
@@ -63,8 +79,9 @@ __global__ void __launch_bounds__(kPrepThreads) k_prep_band(const int* __restric
     const int m = sh_base;
     // ---- numpy pairwise_sum(cp[0..m)) -------------------------------------------------------------------
     int2* lf = leaf + (size_t)blockIdx.x * maxleaf;
-    int2* cb = comb + (size_t)blockIdx.x * maxleaf;
+    int2* cb = use_smem ? reinterpret_cast<int2*>(prep_smem + (size_t)maxleaf * 8) : comb + (size_t)blockIdx.x * maxleaf;
     double* pt = part + (size_t)blockIdx.x * maxleaf * 8;
+    double* res = use_smem ? reinterpret_cast<double*>(prep_smem) : nullptr;   // leaf results (stride 1) when in smem
     if (threadIdx.x == 0) {
         // depth-first walk of the recursion: leaves left to right, combines in post-order
         int nleaf = 0, ncomb = 0, sp = 0;
@@ -120,13 +137,20 @@ __global__ void __launch_bounds__(kPrepThreads) k_prep_band(const int* __restric
             r = __dadd_rn(__dadd_rn(__dadd_rn(p[0], p[1]), __dadd_rn(p[2], p[3])), __dadd_rn(__dadd_rn(p[4], p[5]), __dadd_rn(p[6], p[7])));
             for (int i = L.y - (L.y % 8); i < L.y; ++i) r = __dadd_rn(r, cp[L.x + i]);
         }
-        pt[l * 8] = r;                                 // only this thread reads the 8 partials of leaf l
+        if (use_smem) res[l] = r; else pt[l * 8] = r;   // only this thread reads the 8 partials of leaf l
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         const int ncomb = sh_ncomb;
-        for (int k = 0; k < ncomb; ++k) pt[cb[k].x * 8] = __dadd_rn(pt[cb[k].x * 8], pt[cb[k].y * 8]);
-        ir[d] = __ddiv_rn(m ? pt[0] : 0.0, (double)m);     // mean of an empty slice is NaN, as numpy's
+        double total;
+        if (use_smem) {
+            for (int k = 0; k < ncomb; ++k) res[cb[k].x] = __dadd_rn(res[cb[k].x], res[cb[k].y]);
+            total = res[0];
+        } else {
+            for (int k = 0; k < ncomb; ++k) pt[cb[k].x * 8] = __dadd_rn(pt[cb[k].x * 8], pt[cb[k].y * 8]);
+            total = pt[0];
+        }
+        ir[d] = __ddiv_rn(m ? total : 0.0, (double)m);     // mean of an empty slice is NaN, as numpy's
     }
 }
 
