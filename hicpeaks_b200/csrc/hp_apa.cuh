@@ -59,6 +59,24 @@ __device__ __forceinline__ double apa_pairwise(const ApaPlan* __restrict__ P, co
     return s;
 }
 
+// upload helper: diagonal-major staging [num][n] -> row-major band [n][num], zero where r + d >= n
+__global__ void k_apa_transpose(const double* __restrict__ src, double* __restrict__ dst, long long n, int num) {
+    __shared__ double t[32][33];
+    const long long r0 = (long long)blockIdx.x * 32;
+    const int d0 = blockIdx.y * 32;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const long long r = r0 + threadIdx.x;
+        const int d = d0 + k;
+        t[k][threadIdx.x] = (d < num && r + d < n) ? src[(size_t)d * n + r] : 0.0;
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const long long r = r0 + k;
+        const int d = d0 + threadIdx.x;
+        if (r < n && d < num) dst[(size_t)r * num + d] = t[threadIdx.x][k];
+    }
+}
+
 // one block per anchor: gather, NaN / zero-mean rejection, normalise, mean of the normalised window
 __global__ void __launch_bounds__(kApaThreads) k_apa_windows(const ApaPlan* __restrict__ P, const double* __restrict__ bal, long long n,
                                                              int num, const int* __restrict__ pi, const int* __restrict__ pj, int w,

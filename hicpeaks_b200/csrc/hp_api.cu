@@ -1053,14 +1053,21 @@ extern "C" int hp_apa_upload(hp_ctx* ctx, const hp_apa_desc* b) {
         CK(cudaHostAlloc(&ctx->h_stage, cells * 8, cudaHostAllocDefault));
         ctx->cap_stage = cells * 8;
     }
-    double* h = (double*)ctx->h_stage;                 // row-major [r][d], zero where r + d >= n
+    double* h = (double*)ctx->h_stage;                 // diagonal-major staging [d][n]; transposed on the device
     for (int d = 0; d < num; ++d) {
-        const double* src = b->bal_diags[d];
-        for (int64_t r = 0; r < n - d; ++r) h[(size_t)r * num + d] = src[r];
-        for (int64_t r = n - d; r < n; ++r) h[(size_t)r * num + d] = 0.0;
+        memcpy(h + (size_t)d * n, b->bal_diags[d], (size_t)(n - d) * 8);
+        if (d) memset(h + (size_t)d * n + (n - d), 0, (size_t)d * 8);
     }
-    CK(cudaMemcpyAsync(ctx->d_apa_bal, h, cells * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    double* tmp = nullptr;
+    CK(cudaMalloc(&tmp, cells * 8));
+    cudaError_t e = cudaMemcpyAsync(tmp, h, cells * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        k_apa_transpose<<<dim3((unsigned)((n + 31) / 32), (num + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(tmp, ctx->d_apa_bal, n, num);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(ctx, HP_ERR_CUDA, std::string("APA band upload: ") + cudaGetErrorString(e));
     ctx->apa_n = n; ctx->apa_num = num; ctx->apa_npos = 0;
     return HP_OK;
 }
