@@ -1,9 +1,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 1800 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --chroms 2 --no-cpu-baseline > gpurun_out/b_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_score_spec -s 2 -c 1 -o gpurun_out/prof_score -f python bench.py --steps 1 --warmup 3 --chroms 2 --no-cpu-baseline > gpurun_out/b_ncu2.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_levels_spec -s 2 -c 1 -o gpurun_out/prof_levels -f python bench.py --steps 1 --warmup 3 --chroms 2 --no-cpu-baseline > gpurun_out/b_ncu3.log 2>&1
-ls -la gpurun_out | tail -12
+timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "n129 or n500_b60 or n515 or n400" 2>&1 | tail -12
+echo "memcheck rc=$?"
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python scratch/dbg.py spec 2>&1 | tail -6
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_apa.py tests/test_gpu_golden.py -x -q -m gpu -k "apa_rejections or bhfdr_matches_reference and synth_p2w5 or prep and synth_p2w5" 2>&1 | tail -6

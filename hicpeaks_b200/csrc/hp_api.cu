@@ -221,6 +221,15 @@ extern "C" void hp_ctx_destroy(hp_ctx* ctx) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// host threads that pack diagonals into the pinned staging buffer (HP_PACK_THREADS overrides)
+static unsigned pack_threads() {
+    static const unsigned n = []() {
+        if (const char* e = getenv("HP_PACK_THREADS")) return (unsigned)std::max(1, atoi(e));
+        return std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    }();
+    return n;
+}
+
 static int band_alloc(hp_ctx* ctx, int64_t n_, int num_, int bal_first_) {
     struct { int64_t n; int num; int bal_first; } bb{n_, num_, bal_first_};
     auto* b = &bb;
@@ -298,7 +307,7 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
     int* traw = (int*)((char*)ctx->d_tmp + plane * 8);
     const int per = std::max(1, (int)((size_t)(4u << 20) / ((size_t)pitch * 12)));     // ~4 MB per chunk
     const int nchunk = (num + per - 1) / per;
-    unsigned nthreads = std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    unsigned nthreads = pack_threads();
     if (plane < (1u << 20)) nthreads = 1;
     cudaError_t cerr = cudaSuccess;
     auto send = [&](int k) {
@@ -383,7 +392,7 @@ extern "C" int hp_band_upload_counts(hp_ctx* ctx, const hp_counts_desc* b) {
     };
     const int per = std::max(1, (int)((size_t)(2u << 20) / ((size_t)pitch * 4)));      // ~2 MB per chunk
     const int nchunk = (num + per - 1) / per;
-    unsigned nthreads = std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    unsigned nthreads = pack_threads();
     if (plane < (1u << 20)) nthreads = 1;
     cudaError_t cerr = cudaSuccess;
     auto send = [&](int k) {
