@@ -285,6 +285,108 @@ def run_bhfdr(argv=None, Lib=None):
             h.close()
 
 
+# ---------------------------------------------------------------------------------------------------------
+# apa-analysis (/root/reference/scripts/apa-analysis)
+def apa_parser(prog="apa-analysis"):
+    p = argparse.ArgumentParser(prog=prog, description='Perform Aggregate Peak Analysis (APA).',
+                                formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    p.add_argument('-v', '--version', action='version', version=' '.join(['%(prog)s', __version__]))
+    p.add_argument('-O', '--output', help='Output file name.')
+    p.add_argument('--dpi', default=200, type=int, help='The resolution in dots per inch of the output figure.')
+    p.add_argument('-p', '--path', help='Cooler URI.')
+    p.add_argument('-I', '--loop-file', help='Loop file in bedpe format.')
+    p.add_argument('-S', '--skip-rows', default=0, type=int, help='Number of leading lines in the loop file to skip.')
+    p.add_argument('-M', '--min-dis', default=10, type=int,
+                   help='Only peak calls whose loci are separated by at least this number of bins are examined.')
+    p.add_argument('-W', '--window', default=5, type=int, help='Width of the window in APA analysis.')
+    p.add_argument('-C', '--corner-size', default=3, type=int, help='Lower-/upper-corner size of the resulted APA matrix.')
+    p.add_argument('--clr-weight-name', default='weight', help='Weight column; "raw" uses the raw signals.')
+    p.add_argument('--colormap-name', default='traditional', help='Name of the colormap in matplotlib.')
+    p.add_argument('--vmax', type=float, help='The maximum value that the colorbar covers.')
+    return p
+
+
+def find_chrom_pre(chromlabels):
+    """utilities.py:433-441."""
+    return 'chr' if chromlabels[0].startswith('chr') else ''
+
+
+def parse_peakfile(filpath, skip=1):
+    """utilities.py:443-467: {chrom label without prefix: [(x1, x2, y1, y2)]} from BEDPE columns 0, 1, 2, 4, 5."""
+    D = {}
+    with open(filpath, 'r') as source:
+        for i, line in enumerate(source):
+            if i < skip:
+                continue
+            parse = line.rstrip().split()
+            D.setdefault(parse[0], []).append((int(parse[1]), int(parse[2]), int(parse[4]), int(parse[5])))
+    pre = find_chrom_pre(list(D.keys())) if D else ''
+    return {chrom.lstrip(pre): v for chrom, v in D.items()}
+
+
+def locate_anchors(M, loops, res, min_dis):
+    """apa-analysis:98-119: the strongest pixel inside the bin ranges of every loop, upper-triangle order."""
+    pos = []
+    n = M.shape[0]
+    for p in loops:
+        x, y = p[0], p[2]
+        if abs(y - x) < min_dis * res:
+            continue
+        s_l = range(p[0] // res, int(np.ceil(p[1] / float(res))))
+        e_l = range(p[2] // res, int(np.ceil(p[3] / float(res))))
+        si, ei = None, None
+        for st in s_l:
+            for et in e_l:
+                if (st < n) and (et < n):
+                    if si is None:
+                        si, ei = st, et
+                    elif M[st, et] > M[si, ei]:
+                        si, ei = st, et
+        if si is not None:
+            pos.append((si, ei) if si < ei else (ei, si))
+    return pos
+
+
+def run_apa(argv=None, Lib=None):
+    """Returns (avg, score, z, p, maxi, n_windows); writes the figure when matplotlib is available, else the averaged
+    window as text (``numpy.savetxt``) to ``--output``."""
+    args = apa_parser().parse_args(argv if argv else ['-h'])
+    from . import apa as apa_mod
+    correct = False if args.clr_weight_name.lower() == 'raw' else args.clr_weight_name
+    Lib = Lib if Lib is not None else _open_cooler(args.path)
+    res = Lib.binsize
+    pre = find_chrom_pre(Lib.chromnames)
+    peaks = parse_peakfile(args.loop_file, args.skip_rows)
+    parts = []
+    for c in peaks:
+        chrom = pre + c
+        if chrom not in Lib.chromnames:
+            continue
+        M = Lib.matrix(balance=correct, sparse=True).fetch(chrom).tocsr()
+        pos = locate_anchors(M, peaks[c], res, args.min_dis)
+        if pos:
+            parts.append(apa_mod.apa_submatrix(M, pos, w=args.window))
+    n_windows = sum(len(p) for p in parts)
+    print(n_windows)
+    avg, score, z, p, maxi = apa_mod.apa_analysis(parts, w=args.window, cw=args.corner_size)
+    vmax = maxi if args.vmax is None else args.vmax
+    try:
+        import matplotlib
+        matplotlib.use('Agg')
+        import matplotlib.pyplot as plt
+        from matplotlib.colors import LinearSegmentedColormap
+        cmap = LinearSegmentedColormap.from_list('interaction', ['#FFFFFF', '#ff9292', '#ff6767', '#F70000'])
+        plt.imshow(avg, cmap=cmap if args.colormap_name == 'traditional' else args.colormap_name, vmax=vmax, interpolation='none')
+        plt.tick_params(axis='both', bottom=False, top=False, left=False, right=False, labelbottom=False, labeltop=False,
+                        labelleft=False, labelright=False)
+        plt.colorbar()
+        plt.savefig(args.output, dpi=args.dpi, bbox_inches='tight')
+        plt.close()
+    except ImportError:
+        np.savetxt(args.output, avg, header='APA score = {0:.6g}, z = {1:.6g}, p-value = {2:.6g}, vmax = {3:.6g}'.format(score, z, p, vmax))
+    return avg, score, z, p, maxi, n_windows
+
+
 if __name__ == "__main__":
     (run_bhfdr if (len(sys.argv) > 1 and sys.argv[1] == "bhfdr") else run_hiccups)(sys.argv[2:] if len(sys.argv) > 1 and
                                                                                    sys.argv[1] in ("bhfdr", "hiccups") else sys.argv[1:])

@@ -78,3 +78,34 @@ def test_pybhfdr_end_to_end(tmp_path):
     exp = _expected_lines(z["table"], cli.BHFDR_LINE, "3", res, 4)
     key = lambda ln: tuple(ln.split('\t')[:8])
     assert len(got) == len(exp) and {key(l) for l in got} == {key(l) for l in exp}
+
+
+def test_peakfile_parser(tmp_path):
+    f = tmp_path / "loops.bedpe"
+    f.write_text("#header\nchr1\t100\t200\tchr1\t900\t1000\t.\t5\nchr2\t10\t20\tchr2\t70\t80\t.\t3\nchr1\t300\t400\tchr1\t500\t600\n")
+    D = cli.parse_peakfile(str(f), skip=1)
+    assert D == {"1": [(100, 200, 900, 1000), (300, 400, 500, 600)], "2": [(10, 20, 70, 80)]}
+
+
+@pytest.mark.gpu
+def test_apa_analysis_end_to_end(tmp_path):
+    """Loop file + (fake) cooler in, averaged window out: the front end against the oracle on the same anchors."""
+    from oracle import apa_oracle as ao
+    z, n, Diags, weights = gu.load_apa("apa_w5")
+    res, w = 10000, 5
+    Lib = FakeCooler(res, {"chr1": (Diags, weights)})
+    rng = np.random.default_rng(3)
+    loops = tmp_path / "loops.bedpe"
+    with open(loops, "w") as f:
+        for _ in range(400):
+            i = int(rng.integers(10, n - 130)); j = i + int(rng.integers(12, 100))
+            f.write("chr1\t%d\t%d\tchr1\t%d\t%d\t.\t1\n" % (i * res, (i + 2) * res, j * res, (j + 1) * res))
+    out = tmp_path / "apa.txt"
+    avg, score, zz, p, maxi, nwin = cli.run_apa(['-O', str(out), '-p', 'fake.cool', '-I', str(loops), '-W', str(w), '-M', '10'], Lib=Lib)
+    M = Lib.matrix(balance="weight", sparse=True).fetch("chr1").tocsr()
+    pos = cli.locate_anchors(M, cli.parse_peakfile(str(loops), 0)["1"], res, 10)
+    exp, valid = ao.apa_submatrix(ao.balanced_diags(Diags, weights), n, pos, w=w)
+    e_avg, e_score, e_z, e_p, e_maxi, _, _ = ao.apa_analysis(exp, w=w, cw=3)
+    assert nwin == len(exp) > 100
+    assert np.array_equal(avg, e_avg) and score == e_score and zz == e_z and maxi == e_maxi
+    assert os.path.exists(out)
