@@ -706,8 +706,9 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
         // 4x4 register-block kernel: one CTA per SM (all 8 warps share one big tile), TD diagonals per CTA
         A.HR = kHR; A.NQ = kNQ;
         int TD = 64;
-        while (TD > 8 && score_smem_bytes(TD + 3 + 4 * F, kNQ, sh_pairs, kSpecThreads / 32, kQCap, nexec, TD + 8) > 224 * 1024) TD /= 2;
-        A.TD = TD; A.BD = TD + 3 + 4 * F;
+        auto planes = [&](int td) { return (td + 3 + 4 * F + kTileParts - 1) / kTileParts * kTileParts; };   // whole TMA parts
+        while (TD > 8 && score_smem_bytes(planes(TD), kNQ, sh_pairs, kSpecThreads / 32, kQCap, nexec, TD + 8) > 224 * 1024) TD /= 2;
+        A.TD = TD; A.BD = planes(TD);
         smem = score_smem_bytes(A.BD, kNQ, sh_pairs, kSpecThreads / 32, kQCap, nexec, TD + 8);
         grid = dim3((n + kTR - 1) / kTR, (dhi - dlo + 3 + TD) / TD);
     } else {
@@ -750,7 +751,9 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     size_t want = std::min<size_t>((size_t)total * P.npw, (size_t)((double)total * P.npw * std::max(0.15, 1.5 * P.sig)) + 65536);
     want = std::max<size_t>(want, 65536);
     CUtensorMap tm_bal;
-    rc = make_map_plane(ctx, &tm_bal, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, ctx->d_bal, A.NQ, A.BD);
+    // the specialised kernel loads its tile as kTileParts boxes of consecutive planes
+    rc = make_map_plane(ctx, &tm_bal, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, ctx->d_bal, A.NQ,
+                        spec ? (A.BD + kTileParts - 1) / kTileParts : A.BD);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev[2], st));
     k_betab<<<dim3((num + 127) / 128, nexec, 1 + 2 * F), 128, 0, st>>>(ctx->d_tab, ctx->d_ir, ctx->d_betab, num, ctx->bal_first, nexec, F);

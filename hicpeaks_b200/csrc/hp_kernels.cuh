@@ -188,17 +188,17 @@ constexpr int kChunkTabBytes = kChunkTab * 24;
 // qwarps: warps that own a tail queue (0: none), qcap: records per queue
 // tab_nexec / tab_nd: size the per-CTA table copies (0: none)
 __host__ __device__ __forceinline__ size_t score_smem_bytes(int BD, int NQ, int sh_pairs, int qwarps, int qcap, int tab_nexec, int tab_nd) {
-    return (size_t)BD * 4 * NQ * 8 + 32 + 128 + 64 + kChunkTabBytes + (size_t)kStage * sizeof(Cand) + (size_t)qwarps * qcap * 28 +
+    return (size_t)BD * 4 * NQ * 8 + 48 + 128 + 64 + kChunkTabBytes + (size_t)kStage * sizeof(Cand) + (size_t)qwarps * qcap * 28 +
            (tab_nd ? score_tab_bytes(tab_nexec, tab_nd) : 0) + (size_t)sh_pairs * 2 * kShI * kShK * 4;
 }
 __device__ __forceinline__ ScoreSmem score_smem(unsigned char* smem, int BD, int NQ, int qwarps, int qcap, int tab_nexec, int tab_nd) {
     ScoreSmem S;
     unsigned char* p = smem;
     S.tile = reinterpret_cast<double*>(p); p += (size_t)BD * 4 * NQ * 8;
-    S.bar = reinterpret_cast<uint64_t*>(p);
-    S.cnt = reinterpret_cast<unsigned int*>(p + 8);
-    S.base = reinterpret_cast<unsigned int*>(p + 12);
-    S.next = reinterpret_cast<unsigned int*>(p + 16); p += 32;
+    S.bar = reinterpret_cast<uint64_t*>(p);                       // kTileParts barriers
+    S.cnt = reinterpret_cast<unsigned int*>(p + 32);
+    S.base = reinterpret_cast<unsigned int*>(p + 36);
+    S.next = reinterpret_cast<unsigned int*>(p + 40); p += 48;
     S.emax = reinterpret_cast<unsigned long long*>(p); p += 128;
     S.nval = reinterpret_cast<unsigned int*>(p); p += 64;
     S.cinfo = reinterpret_cast<int4*>(p); p += kChunkTab * 16;
@@ -377,10 +377,33 @@ __device__ __forceinline__ void tail_acc_flush(const ScoreSmem& sh, const TailAc
     }
 }
 
+// the tile arrives in kTileParts boxes of consecutive planes, each on its own mbarrier and the far planes first: the
+// column blocks the warps claim first (largest d) can start as soon as their planes have landed
+constexpr int kTileParts = 4;
+__device__ __forceinline__ void score_issue_tile(const ScoreSmem& sh, const CUtensorMap* tm, int BD, int NQ, int q0, int plane0) {
+    if (threadIdx.x == 0) {
+        const int per = (BD + kTileParts - 1) / kTileParts;        // the tensor map's box holds `per` planes
+        for (int k = 0; k < kTileParts; ++k) mbar_init(sh.bar + k, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int k = kTileParts - 1; k >= 0; --k) {
+            mbar_expect_tx(sh.bar + k, (uint32_t)(per * 4 * NQ * 8));
+            tma_load_3d(sh.tile + (size_t)k * per * 4 * NQ, tm, q0, 0, plane0 + k * per, sh.bar + k);
+        }
+        *sh.cnt = 0;
+        *sh.next = 0;
+    }
+}
+// wait for the planes [lo, hi] (tile-relative) of the tile
+__device__ __forceinline__ void score_wait_planes(const ScoreSmem& sh, int BD, int lo, int hi) {
+    const int per = (BD + kTileParts - 1) / kTileParts;
+    for (int k = lo / per; k <= hi / per && k < kTileParts; ++k) mbar_wait(sh.bar + k, 0);
+}
+
+template <bool ISSUE>
 __device__ __forceinline__ void score_prologue(const ScoreArgs& A, const ScoreSmem& sh, const CUtensorMap* tm, int tile_bytes, int q0,
                                                int plane0, int sh_bins) {
     const Chunks& C = A.tab->chunks;
-    if (threadIdx.x == 0) {
+    if (ISSUE && threadIdx.x == 0) {
         mbar_init(sh.bar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(sh.bar, (uint32_t)tile_bytes);
@@ -396,7 +419,7 @@ __device__ __forceinline__ void score_prologue(const ScoreArgs& A, const ScoreSm
         sh.cinfo[i] = in ? make_int4(C.hoff[i], C.hw[i], C.kcand[i], 0) : make_int4(0, 1, 0x7fffffff, 0);
     }
     __syncthreads();
-    mbar_wait(sh.bar, 0);
+    if (ISSUE) mbar_wait(sh.bar, 0);
 }
 
 // flush: privatised histogram, counters, staged candidates
@@ -436,7 +459,7 @@ __global__ void __launch_bounds__(kThreads) k_score(const __grid_constant__ CUte
     const int d0 = A.dlo + blockIdx.y * A.TD;
     const Tables& T = *A.tab;
     const int npw = T.prog.npw;
-    score_prologue(A, sh, &tm_bal, A.BD * 4 * A.NQ * 8, (r0 - A.HR) / 4, d0 - 2 * A.F, sh_bins);
+    score_prologue<true>(A, sh, &tm_bal, A.BD * 4 * A.NQ * 8, (r0 - A.HR) / 4, d0 - 2 * A.F, sh_bins);
 
     const int lane = threadIdx.x & 31;
     const int rl = threadIdx.x & (kTR - 1);

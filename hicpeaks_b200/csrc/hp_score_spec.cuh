@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(kSpecThreads, HP_SPEC_MINB) k_score_spec(const
     // far diagonals first: they run the deepest levels, so the cheap tiles fill the tail of the grid
     const int d0 = A.dlo + (int)(gridDim.y - 1 - blockIdx.y) * A.TD;
     const int plane0 = d0 - 3 - 2 * A.F;
+    score_issue_tile(sh, &tm_bal, A.BD, kNQ, (r0 - kHR) / 4, plane0);      // TMA first; the table copies below overlap it
     // per-CTA copies of the tables the tail reads: bE of interior pixels, IR, biases of the tile's rows / columns
     sh.tb_d0 = d0 - 3; sh.tb_r0 = r0;
     {
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(kSpecThreads, HP_SPEC_MINB) k_score_spec(const
             sh.tb_b2[t] = (c >= 0 && c < A.n) ? A.b2[c] : 0.0;
         }
     }
-    score_prologue(A, sh, &tm_bal, A.BD * 4 * kNQ * 8, (r0 - kHR) / 4, plane0, sh_bins);
+    score_prologue<false>(A, sh, &tm_bal, 0, 0, 0, sh_bins);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = r0 + 4 * lane;
@@ -275,6 +276,16 @@ __global__ void __launch_bounds__(kSpecThreads, HP_SPEC_MINB) k_score_spec(const
                 lvp[i] = pk;
             }
         }
+        // step 0 does not depend on the levels: run it while the level / count loads above are still in flight
+        if (r0 + dc - 3 >= A.n) continue;                            // every pixel of the block is beyond the chromosome
+        double aK[4][kTC], aY[4][kTC];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < kTC; ++j) { aK[i][j] = 0.0; aY[i][j] = 0.0; }
+        score_wait_planes(sh, A.BD, dc - plane0 - 3 - 2 * A.F, dc - plane0 + kTC + 2 + 2 * A.F);
+        const double* base = sh.tile + (size_t)(dc - plane0) * 4 * kNQ + (lane + kHR / 4);
+        spec_dispatch<PG, 0>(0, base, aK, aY);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -289,15 +300,9 @@ __global__ void __launch_bounds__(kSpecThreads, HP_SPEC_MINB) k_score_spec(const
             }
         const int wlast = __reduce_max_sync(0xffffffffu, last);
         if (wlast < 0) continue;
-        double aK[4][kTC], aY[4][kTC];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < kTC; ++j) { aK[i][j] = 0.0; aY[i][j] = 0.0; }
-        const double* base = sh.tile + (size_t)(dc - plane0) * 4 * kNQ + (lane + kHR / 4);
 #pragma unroll 1
         for (int s = 0; s <= wlast; ++s) {
-            spec_dispatch<PG, 0>(s, base, aK, aY);
+            if (s > 0) spec_dispatch<PG, 0>(s, base, aK, aY);
             // pixels whose level lies in (previous executed step of this pair, s] resolve the pair now
             const int pi = A.step_pi[s], lo = A.step_lo[s], wmin = A.ww[pi];
             unsigned em = 0;

@@ -1,6 +1,6 @@
 cd $GRAFT_REPO_ROOT
-mkdir -p gpurun_out
-timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "n129 or n500_b60 or n515 or n400" 2>&1 | tail -12
-echo "memcheck rc=$?"
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python scratch/dbg.py spec 2>&1 | tail -6
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_apa.py tests/test_gpu_golden.py -x -q -m gpu -k "apa_rejections or bhfdr_matches_reference and synth_p2w5 or prep and synth_p2w5" 2>&1 | tail -6
+HICPEAKS_B200_LIB=$PWD/scratch/lib_new.so timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "n600 or n129 or n1000 or n777 or n500_b60" 2>&1 | tail -2
+for i in 1 2; do
+HICPEAKS_B200_LIB=$PWD/scratch/lib_new.so timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; b=json.loads(sys.stdin.read()); print('new', b['value'], b['kernel_ms_per_chromosome_alone'])"
+HICPEAKS_B200_LIB=$PWD/scratch/lib_old.so timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; b=json.loads(sys.stdin.read()); print('old', b['value'], b['kernel_ms_per_chromosome_alone'])"
+done
