@@ -136,7 +136,8 @@ typedef struct hp_hiccups_summary {
     hp_lf_stat lf[HP_MAX_PW][2]; /* [pair][0 = donut 'K', 1 = lower-left 'Y']                    */
     int64_t n_candidates;
     int64_t n_survivors;         /* records available to hp_get_survivors                       */
-    float ms_levels, ms_score, ms_fdr, ms_total; /* device time (CUDA events on the ctx stream) */
+    float ms_levels, ms_score, ms_fdr, ms_total; /* device time (CUDA events on the ctx stream): level kernel, score
+                                                    kernel, BH + survivor kernels, their sum                      */
     int32_t launches;            /* kernels launched by this call                               */
     int32_t spec_kernel;         /* 1: the score kernel specialised for this sweep program ran   */
 } hp_hiccups_summary;
