@@ -6,7 +6,7 @@
 Workload (`config.workload`): BASELINE.json configs[1] -- synthetic chromosome of 20 000 bins @10 kb,
 5 Mb band (num = 511 stored diagonals), (p, w) = (2, 5), maxww 10, min_local_reads 16, sig 0.1,
 generator of SURVEY.md 8(d).  One step = one pass of the whole hot path (level kernel, frozen_w
-replay, score kernel, BH kernel, survivor filter) over a batch of `--chroms` such chromosomes that
+replay, score kernel, BH kernel, survivor filter) over a batch of `--chroms` (default 8) such chromosomes that
 are resident in HBM (batch > L2, so every step streams from HBM).  For N > 1 (torchrun, one rank
 per GPU) every rank owns its own batch (weak scaling, chromosomes are independent: no collective
 on the data path); value = all pixels / max-over-ranks time.
@@ -162,7 +162,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chroms", type=int, default=4, help="chromosomes per GPU per step")
+    ap.add_argument("--chroms", type=int, default=8, help="chromosomes per GPU per step (one host thread each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
