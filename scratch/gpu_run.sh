@@ -1,4 +1,7 @@
 cd $GRAFT_REPO_ROOT
-for c in 4 6 8; do
-timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --chroms $c 2>/dev/null | python -c "import json,sys; b=json.loads(sys.stdin.read()); print('chroms', $c, 'value', b['value'], 'ms/step', b['ms_per_step'], 'e2e', b['e2e']['value'], 'e2e_op', b['e2e_operator']['value'])"
-done
+mkdir -p gpurun_out
+timeout 1800 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --chroms 2 --no-cpu-baseline > gpurun_out/b_ncu.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_score_spec -s 2 -c 1 -o gpurun_out/prof_score -f python bench.py --steps 1 --warmup 3 --chroms 2 --no-cpu-baseline > gpurun_out/b_ncu2.log 2>&1
