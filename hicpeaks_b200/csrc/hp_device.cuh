@@ -71,6 +71,20 @@ __host__ __device__ __forceinline__ size_t qidx(int d, int r, int pitch) {
 // ---- mbarrier / TMA -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// shared-memory atomics through explicit shared-space addresses: on a generic pointer the compiler emits the
+// "which address space is this" fallback around every atomic (dozens of instructions and two branches each)
+__device__ __forceinline__ unsigned smem_atom_add(unsigned* p, unsigned v) {
+    unsigned old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void smem_red_add(unsigned* p, unsigned v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void smem_red_max(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.shared.max.u64 [%0], %1;" ::"r"(smem_u32(p)), "l"(v) : "memory");
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kThreads) k_levels(const __grid_constant__ CUt
             }
             const int slot = (out == kLvlNever) ? nsteps : out;
             const unsigned m = __match_any_sync(__activemask(), slot);
-            if ((threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&sh_hist[slot], __popc(m));
+            if ((threadIdx.x & 31) == __ffs(m) - 1) smem_red_add(&sh_hist[slot], __popc(m));
         }
         A.lvl[qidx(d, r, A.pitch)] = out;
     }
@@ -306,7 +306,7 @@ __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem&
                     acc.emax[fl] = eb > acc.emax[fl] ? eb : acc.emax[fl];
                     ++acc.nval[fl];
                 } else {
-                    if (eb > sh.emax[pi * 2 + fl]) atomicMax(&sh.emax[pi * 2 + fl], eb);
+                    if (eb > sh.emax[pi * 2 + fl]) smem_red_max(&sh.emax[pi * 2 + fl], eb);
                 }
                 bool member;
                 const int ci = find_chunk(sh.rv, mc, E, member);
@@ -320,7 +320,7 @@ __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem&
                     const int4 inf = sh.cinfo[ci];
                     const int kb = obs < inf.y - 1 ? obs : inf.y - 1;
                     if (pi < A.sh_pairs && ci <= kShI && kb < kShK)
-                        atomicAdd(&sh.hist[((pi * 2 + fl) * kShI + (ci - 1)) * kShK + kb], 1u);
+                        smem_red_add(&sh.hist[((pi * 2 + fl) * kShI + (ci - 1)) * kShK + kb], 1u);
                     else
                         atomicAdd(&A.hist[(size_t)(pi * 2 + fl) * A.total_bins + inf.x + kb], 1u);
                     cand |= (obs >= inf.z);
@@ -336,14 +336,14 @@ __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem&
             const bool v = (flags & (fl ? HP_SF_VALID_Y : HP_SF_VALID_K)) != 0;
             for (int k = 0; k < npw; ++k) {
                 const unsigned mv = __ballot_sync(0xffffffffu, v && pi == k);
-                if (mv && lane == 0) atomicAdd(&sh.nval[k * 2 + fl], (unsigned)__popc(mv));
+                if (mv && lane == 0) smem_red_add(&sh.nval[k * 2 + fl], (unsigned)__popc(mv));
             }
         }
     }
     const unsigned mcand = __ballot_sync(0xffffffffu, cand);
     if (mcand) {
         unsigned base = 0;
-        if (lane == 0) base = atomicAdd(sh.cnt, (unsigned)__popc(mcand));
+        if (lane == 0) base = smem_atom_add(sh.cnt, (unsigned)__popc(mcand));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (cand) {
             const unsigned slot = base + __popc(mcand & ((1u << lane) - 1u));
@@ -370,9 +370,9 @@ __device__ __forceinline__ void tail_acc_flush(const ScoreSmem& sh, const TailAc
         const unsigned lo = hi == mhi ? (unsigned)acc.emax[fl] : 0u;
         const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
         if ((threadIdx.x & 31) == 0) {
-            if (nv) atomicAdd(&sh.nval[fl], nv);
+            if (nv) smem_red_add(&sh.nval[fl], nv);
             const unsigned long long m = ((unsigned long long)mhi << 32) | mlo;
-            if (m) atomicMax(&sh.emax[fl], m);
+            if (m) smem_red_max(&sh.emax[fl], m);
         }
     }
 }

@@ -233,9 +233,9 @@ __global__ void __launch_bounds__(kSpecThreads, HP_SPEC_MINB) k_score_spec(const
     for (;;) {
         int kb = 0;                                  // column blocks are claimed dynamically, deepest (largest d) first
 #ifdef HP_TASK_ASC
-        if (lane == 0) { kb = (int)atomicAdd(sh.next, 1u); if (kb >= ntask) kb = -1; }
+        if (lane == 0) { kb = (int)smem_atom_add(sh.next, 1u); if (kb >= ntask) kb = -1; }
 #else
-        if (lane == 0) kb = ntask - 1 - (int)atomicAdd(sh.next, 1u);
+        if (lane == 0) kb = ntask - 1 - (int)smem_atom_add(sh.next, 1u);
 #endif
         kb = __shfl_sync(0xffffffffu, kb, 0);
         if (kb < 0) break;
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(kThreads) k_levels_spec(const __grid_constant_
     const int thr = T.prog.thr;
     for (;;) {
         int kb = 0;
-        if (lane == 0) kb = (int)atomicAdd(next, 1u);
+        if (lane == 0) kb = (int)smem_atom_add(next, 1u);
         kb = __shfl_sync(0xffffffffu, kb, 0);
         const int dc = d0 + kb * kTCL;
         if (kb * kTCL >= A.TD || dc - 3 > A.dhi) break;
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(kThreads) k_levels_spec(const __grid_constant_
                 open |= __vcmpeq4(lvp[i], 0xFEFEFEFEu) != 0u;
             }
             hit = __reduce_add_sync(0xffffffffu, hit);
-            if (lane == 0 && hit) atomicAdd(&sh_hist[s], (unsigned)hit);
+            if (lane == 0 && hit) smem_red_add(&sh_hist[s], (unsigned)hit);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(kThreads) k_levels_spec(const __grid_constant_
             }
         }
         never = __reduce_add_sync(0xffffffffu, never);
-        if (lane == 0 && never) atomicAdd(&sh_hist[nsteps], (unsigned)never);
+        if (lane == 0 && never) smem_red_add(&sh_hist[nsteps], (unsigned)never);
     }
     __syncthreads();
     for (int i = threadIdx.x; i <= nsteps; i += kThreads)
