@@ -259,7 +259,8 @@ def main():
     e2e_res = [e2e_step(True) for _ in range(args.steps)]
     barrier()
     dt_e2e = time.perf_counter() - t0
-    h2d_counts = sum(sum(a.nbytes for a in Dg) + inp["weights"].nbytes for inp, (Dg, cD, ir) in zip(batch, arrays))
+    h2d_counts = sum(c.upload_bytes() for c in ctxs)          # counted by the library from the copies it issued
+    host_counts = sum(sum(a.nbytes for a in Dg) + inp["weights"].nbytes for inp, (Dg, cD, ir) in zip(batch, arrays))
 
     px_step = accs[0]["px"]
     if dist is not None:
@@ -308,9 +309,10 @@ def main():
                      "avg_launch_ms": ms_score},
         "e2e": {"value": e2e_value, "unit": "pixels/s", "h2d_bytes_per_step": h2d_counts * world,
                 "d2h_bytes_per_step": int(np.mean([r[1] for r in e2e_res])) * world,
-                "ms_per_step": 1e3 * dt_e2e / args.steps,
+                "ms_per_step": 1e3 * dt_e2e / args.steps, "host_input_bytes_per_step": host_counts * world,
                 "boundary": "worker level: callers.hiccups_from_counts / hp_band_upload_counts (raw int32 diagonals + bin weights "
-                            "from pageable host arrays; balanced band, IR, biases derived on the GPU)"},
+                            "from pageable host arrays; the library narrows each diagonal to u8/u16/i32 into pinned staging, "
+                            "h2d_bytes_per_step is what crossed PCIe; balanced band, IR, biases derived on the GPU)"},
         "e2e_operator": {"value": px_total * args.steps / dt_e2e_op, "unit": "pixels/s", "h2d_bytes_per_step": h2d * world,
                          "ms_per_step": 1e3 * dt_e2e_op / args.steps,
                          "boundary": "operator level: callers.hiccups / hp_band_upload (Diags + cDiags + IR + biases, 12 B/pixel)"},

@@ -34,7 +34,7 @@ LIB_PATH = os.environ.get("HICPEAKS_B200_LIB") or os.path.join(os.path.dirname(o
 # every symbol include/hicpeaks_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "hp_abi_version", "hp_device_count", "hp_ctx_create", "hp_ctx_destroy", "hp_last_error",
-    "hp_band_upload", "hp_band_upload_counts", "hp_dump_band", "hp_hiccups_score", "hp_hiccups_fdr", "hp_hiccups", "hp_get_survivors",
+    "hp_band_upload", "hp_band_upload_counts", "hp_upload_bytes", "hp_dump_band", "hp_hiccups_score", "hp_hiccups_fdr", "hp_hiccups", "hp_get_survivors",
     "hp_hist_bins", "hp_hist_export", "hp_hist_import", "hp_get_gaps", "hp_dump_levels", "hp_dump_plane", "hp_get_chunk_table", "hp_poisson_sf",
     "hp_apa_upload", "hp_apa_windows", "hp_apa_load_windows", "hp_apa_accumulate", "hp_apa_get_windows",
 ]
@@ -114,6 +114,7 @@ def load_library(path: str | None = None):
     lib.hp_band_upload.argtypes = [vp, C.POINTER(BandDesc)]
     lib.hp_band_upload_counts.argtypes = [vp, C.POINTER(CountsDesc)]
     lib.hp_dump_band.argtypes = [vp, i32, vp, i64]
+    lib.hp_upload_bytes.argtypes = [vp, C.POINTER(i64)]
     lib.hp_hiccups_score.argtypes = [vp, C.POINTER(HiccupsParams), C.POINTER(HiccupsSummary)]
     lib.hp_hiccups_fdr.argtypes = [vp, vp, C.POINTER(HiccupsSummary)]
     lib.hp_hiccups.argtypes = [vp, C.POINTER(HiccupsParams), C.POINTER(HiccupsSummary)]
@@ -151,6 +152,34 @@ def chunk_edges(max_chunks: int) -> np.ndarray:
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+try:                                     # built by __graft_entry__.build() (csrc/hp_pyhelper.c); host glue only
+    from . import _hpfast
+except ImportError:                      # pragma: no cover - same checks, ~50x slower
+    _hpfast = None
+
+_KIND = {"i": np.signedinteger, "f": np.floating}
+
+
+def first_nonconforming(seq, count, first_len, len_step, itemsize, kind, table=None):
+    """Index of the first of ``seq[:count]`` that is not a C-contiguous 1-D native array of ``itemsize``-byte
+    ``kind`` ('i' / 'f') elements with ``first_len + i * len_step`` elements, or -1 when all conform.  ``table``
+    (a ctypes ``c_void_p`` array) receives the data pointers of the conforming prefix."""
+    if _hpfast is not None:
+        return _hpfast.collect(seq, count, first_len, len_step, itemsize, kind, C.addressof(table) if table is not None else 0)
+    if not isinstance(seq, (list, tuple)):
+        return 0
+    if len(seq) < count:
+        return len(seq)
+    for i in range(count):
+        a = seq[i]
+        if (not isinstance(a, np.ndarray) or a.ndim != 1 or a.dtype.itemsize != itemsize or not a.dtype.isnative
+                or not np.issubdtype(a.dtype, _KIND[kind]) or not a.flags.c_contiguous or a.size != first_len + i * len_step):
+            return i
+        if table is not None:
+            table[i] = a.ctypes.data
+    return -1
 
 
 class Context:
@@ -192,18 +221,14 @@ class Context:
         right dtype (the caller normalises); they are only read during this call."""
         keep = []
         rp = (C.c_void_p * num)()
-        for d in range(num):
-            a = Diags[d]
-            if a.dtype != np.int32 or not a.flags.c_contiguous or a.size != n - d:
-                raise ValueError("Diags[%d] must be contiguous int32 of length %d" % (d, n - d))
-            rp[d] = a.ctypes.data
+        d = first_nonconforming(Diags, num, n, -1, 4, "i", rp)
+        if d >= 0:
+            raise ValueError("Diags[%d] must be contiguous int32 of length %d" % (d, n - d))
         nb = num - bal_first
         bp = (C.c_void_p * nb)()
-        for i in range(nb):
-            a = cDiags[i]
-            if a.dtype != np.float64 or not a.flags.c_contiguous or a.size != n - bal_first - i:
-                raise ValueError("cDiags[%d] must be contiguous float64 of length %d" % (i, n - bal_first - i))
-            bp[i] = a.ctypes.data
+        i = first_nonconforming(cDiags, nb, n - bal_first, -1, 8, "f", bp)
+        if i >= 0:
+            raise ValueError("cDiags[%d] must be contiguous float64 of length %d" % (i, n - bal_first - i))
         ir = np.ascontiguousarray(ir, dtype=np.float64)
         b1 = np.ascontiguousarray(b1, dtype=np.float64)
         b2 = np.ascontiguousarray(b2, dtype=np.float64)
@@ -219,17 +244,21 @@ class Context:
         """Worker-level input: ``Diags`` (``num`` contiguous int32 arrays) and the bin weights (float64[n], NaN for
         masked bins); the balanced band, IR and the biases are derived on the GPU (scripts/pyHICCUPS:143-166)."""
         rp = (C.c_void_p * num)()
-        for d in range(num):
-            a = Diags[d]
-            if a.dtype != np.int32 or not a.flags.c_contiguous or a.size != n - d:
-                raise ValueError("Diags[%d] must be contiguous int32 of length %d" % (d, n - d))
-            rp[d] = a.ctypes.data
+        d = first_nonconforming(Diags, num, n, -1, 4, "i", rp)
+        if d >= 0:
+            raise ValueError("Diags[%d] must be contiguous int32 of length %d" % (d, n - d))
         w = np.ascontiguousarray(weights, dtype=np.float64)
         if w.size != n:
             raise ValueError("weights length mismatch")
         desc = CountsDesc(n, num, bal_first, C.cast(rp, C.POINTER(C.c_void_p)), w.ctypes.data)
         self._check(self.lib.hp_band_upload_counts(self._h, C.byref(desc)))
         self.n, self.num = int(n), int(num)
+
+    def upload_bytes(self):
+        """Bytes the last upload moved over PCIe (count diagonals travel narrowed to u8 / u16 where they fit)."""
+        v = C.c_int64()
+        self._check(self.lib.hp_upload_bytes(self._h, C.byref(v)))
+        return v.value
 
     def dump_band(self, what):
         shape = {0: (self.num,), 1: (self.n,), 2: (self.num, self.n)}[what]
@@ -274,7 +303,7 @@ class Context:
     def survivors(self):
         cnt = C.c_int64()
         self._check(self.lib.hp_get_survivors(self._h, None, 0, C.byref(cnt)))
-        out = np.zeros(cnt.value, dtype=SURVIVOR_DTYPE)
+        out = np.empty(cnt.value, dtype=SURVIVOR_DTYPE)
         if cnt.value:
             self._check(self.lib.hp_get_survivors(self._h, _ptr(out), cnt.value, C.byref(cnt)))
         return out
@@ -292,9 +321,9 @@ class Context:
         self._check(self.lib.hp_hist_import(self._h, _ptr(h), h.size))
 
     def gaps(self):
-        out = np.zeros(self.n, dtype=np.uint8)
+        out = np.empty(self.n, dtype=np.bool_)
         self._check(self.lib.hp_get_gaps(self._h, _ptr(out), self.n))
-        return out.astype(bool)
+        return out
 
     # -- inspection ----------------------------------------------------------------------------
     def dump_levels(self):

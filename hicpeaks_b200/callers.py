@@ -56,16 +56,11 @@ def lambdachunk(E):
 
 
 def _as_diags(Diags, cDiags, IR, chromLen, num, min_ww):
-    raw = []
-    for d in range(num):
-        a = np.asarray(Diags[d])
-        if a.dtype != np.int32:
-            b = a.astype(np.int32)
-            if not np.array_equal(b, a):
-                raise ValueError("Diags[%d] holds values that are not int32 counts" % d)
-            a = b
-        raw.append(np.ascontiguousarray(a))
-    bal = [np.ascontiguousarray(c, dtype=np.float64) for c in cDiags]
+    raw = _as_counts(Diags, num, chromLen)
+    if _capi.first_nonconforming(cDiags, num - min_ww, chromLen - min_ww, -1, 8, "f") < 0 and len(cDiags) == num - min_ww:
+        bal = cDiags                       # already what the engine reads: no per-diagonal Python work
+    else:
+        bal = [np.ascontiguousarray(c, dtype=np.float64) for c in cDiags]
     if len(bal) != num - min_ww:
         raise ValueError("cDiags must hold offsets min(ww)..num-1 (got %d arrays, expected %d)" % (len(bal), num - min_ww))
     keys = sorted(IR)
@@ -81,7 +76,9 @@ def _numpy_numbin(e_max, n_valid):
     return int(np.ceil(np.log(e_max) / np.log(2) * 3 + 1))
 
 
-def _as_counts(Diags, num):
+def _as_counts(Diags, num, chromLen=None):
+    if chromLen is not None and _capi.first_nonconforming(Diags, num, chromLen, -1, 4, "i") < 0:
+        return Diags                       # contiguous int32 diagonals of the right lengths (what `H.diagonal(d)` gives)
     raw = []
     for d in range(num):
         a = np.asarray(Diags[d])
@@ -100,7 +97,7 @@ def score_chromosome(ctx, chromLen, Diags, cDiags, IR, B1, B2, num, pw, ww, maxw
     ``weights`` given: worker-level input (``cDiags`` / ``IR`` / biases are derived on the GPU)."""
     min_ww = min(ww)
     if weights is not None:
-        ctx.upload_counts(chromLen, num, min_ww, _as_counts(Diags, num), weights)
+        ctx.upload_counts(chromLen, num, min_ww, _as_counts(Diags, num, chromLen), weights)
     else:
         raw, bal, ir = _as_diags(Diags, cDiags, IR, chromLen, num, min_ww)
         ctx.upload(chromLen, num, min_ww, raw, bal, ir, B1, B2)
@@ -196,7 +193,7 @@ def bhfdr(M, cM, B1, B2, IR, chromLen, Diags, cDiags, num, chrom, pw=2, ww=5, si
     Benjamini-Hochberg step (:545-547), gap filter (:557-577), clustering (:580-582) and ``fold > 2`` (:587)."""
     ctx = get_context(device)
     if weights is not None:
-        ctx.upload_counts(chromLen, num, ww, _as_counts(Diags, num), weights)
+        ctx.upload_counts(chromLen, num, ww, _as_counts(Diags, num, chromLen), weights)
     else:
         raw, bal, ir = _as_diags(Diags, cDiags, IR, chromLen, num, ww)
         ctx.upload(chromLen, num, ww, raw, bal, ir, B1, B2)

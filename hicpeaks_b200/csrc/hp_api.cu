@@ -2,11 +2,14 @@
 // program builder (callers.py:15-23,132-198), the frozen_w replay (callers.py:203-232) and the
 // launch sequence  K1 levels -> replay -> bE table -> K2 score -> K3 BH -> survivor filter.
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -16,6 +19,7 @@
 #include "hp_score_spec.cuh"
 #include "hp_apa.cuh"
 #include "hp_prep.cuh"
+#include "hp_hostpack.h"
 
 using namespace hp;
 
@@ -45,6 +49,8 @@ struct hp_ctx {
     double* d_tmp = nullptr;          // plain-layout landing zone of the uploads (re-laid out on the device)
     void* h_stage = nullptr;          // pinned staging for uploads
     size_t cap_stage = 0;
+    void* h_out = nullptr;            // pinned staging for result downloads (a D2H copy into pageable memory runs at ~3 GB/s)
+    size_t cap_out = 0;
     bool have_band = false;
     // run state
     hp_hiccups_params prm{};
@@ -71,6 +77,8 @@ struct hp_ctx {
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     // K0 scratch (hp_prep.cuh)
     double* d_w = nullptr; size_t cap_w = 0;
+    PackedDiag* d_pk = nullptr; size_t cap_pk = 0;       // per-diagonal format table of the narrowed count upload
+    int64_t h2d_bytes = 0;                               // bytes the last band upload moved over PCIe
     unsigned char* d_prep = nullptr; size_t cap_prep = 0;
     // APA (hp_apa.cuh)
     double* d_apa_bal = nullptr; size_t cap_apa_bal = 0;
@@ -105,6 +113,16 @@ static cudaError_t want_smem(K kernel, int device, size_t smem, std::atomic<size
     if (smem <= g.load(std::memory_order_acquire)) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) g.store(smem, std::memory_order_release);
+    return e;
+}
+
+static cudaError_t ensure_host(void** p, size_t* cap, size_t bytes) {
+    if (*cap >= bytes && *p) return cudaSuccess;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *cap = 0;
+    bytes = (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
+    cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocDefault);
+    if (e == cudaSuccess) *cap = bytes;
     return e;
 }
 
@@ -210,7 +228,7 @@ extern "C" void hp_ctx_destroy(hp_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_ptab, ctx->d_raw, ctx->d_bal, ctx->d_lvl, ctx->d_ir, ctx->d_b1, ctx->d_b2, ctx->d_rownz,
                     ctx->d_lhist, ctx->d_betab, ctx->d_hist, ctx->d_qtab, ctx->d_small, ctx->d_cnt, ctx->d_numbin,
-                    ctx->d_cand, ctx->d_surv, ctx->d_dump, ctx->d_tmp, ctx->d_tab, ctx->d_w, ctx->d_prep, ctx->d_apa_bal, ctx->d_apa_plan, ctx->d_apa_pos,
+                    ctx->d_cand, ctx->d_surv, ctx->d_dump, ctx->d_tmp, ctx->d_tab, ctx->d_w, ctx->d_pk, ctx->d_prep, ctx->d_apa_bal, ctx->d_apa_plan, ctx->d_apa_pos,
                     ctx->d_apa_wins, ctx->d_apa_valid, ctx->d_apa_mean, ctx->d_apa_sel, ctx->d_apa_avg};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -221,14 +239,92 @@ extern "C" void hp_ctx_destroy(hp_ctx* ctx) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// host threads that pack diagonals into the pinned staging buffer (HP_PACK_THREADS overrides)
-static unsigned pack_threads() {
-    static const unsigned n = []() {
-        if (const char* e = getenv("HP_PACK_THREADS")) return (unsigned)std::max(1, atoi(e));
-        return std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
-    }();
-    return n;
-}
+// Host threads that pack diagonals into the pinned staging buffers: ONE pool per process, shared by every
+// context, so that eight chromosomes uploading at once (one caller thread per context) split the cores between
+// them instead of starting eight private thread teams.  HP_PACK_THREADS overrides the pool size.
+class PackPool {
+  public:
+    static PackPool& get() {
+        static PackPool* p = new PackPool();          // never destroyed: workers may outlive static destructors
+        return *p;
+    }
+    unsigned size() const { return (unsigned)workers_.size(); }
+    // Runs fn(0) .. fn(count - 1) on the pool; calls ready(k) on the CALLING thread, in order k = 0, 1, ..., as soon
+    // as fn(k) has finished (the caller issues chunk k's copy while later chunks are still being packed).
+    template <typename F, typename R>
+    void run_ordered(int count, F&& fn, R&& ready) {
+        if (count <= 0) return;
+        if (workers_.empty() || count == 1 || forked_) {
+            for (int k = 0; k < count; ++k) { fn(k); ready(k); }
+            return;
+        }
+        Job job;
+        job.count = count;
+        job.done.assign(count, 0);
+        job.fn = [&fn](int k) { fn(k); };
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            jobs_.push_back(&job);
+        }
+        cv_.notify_all();
+        for (int k = 0; k < count; ++k) {
+            for (;;) {
+                int mine = -1;
+                {
+                    std::unique_lock<std::mutex> lk(m_);
+                    if (job.done[k]) break;
+                    if (job.next < job.count) mine = job.next++;         // the caller packs too instead of idling
+                    else { job.cv.wait(lk, [&] { return job.done[k] != 0; }); break; }
+                }
+                fn(mine);
+                std::lock_guard<std::mutex> lk(m_);
+                job.done[mine] = 1;
+                ++job.finished;
+            }
+            ready(k);
+        }
+        std::unique_lock<std::mutex> lk(m_);                              // workers may still be leaving the job
+        job.cv.wait(lk, [&] { return job.finished == job.count && job.active == 0; });
+        jobs_.erase(std::find(jobs_.begin(), jobs_.end(), &job));
+    }
+
+  private:
+    struct Job {
+        int count = 0, next = 0, finished = 0, active = 0;
+        std::vector<char> done;
+        std::function<void(int)> fn;
+        std::condition_variable cv;
+    };
+    PackPool() {
+        unsigned n = std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+        if (const char* e = getenv("HP_PACK_THREADS")) n = (unsigned)std::max(1, atoi(e));
+        for (unsigned t = 0; t + 1 < n; ++t) workers_.emplace_back([this] { work(); }), workers_.back().detach();
+        pthread_atfork(nullptr, nullptr, [] { forked_ = true; });      // a forked child has no workers: pack inline
+    }
+    void work() {
+        std::unique_lock<std::mutex> lk(m_);
+        for (;;) {
+            Job* job = nullptr;
+            for (Job* j : jobs_)
+                if (j->next < j->count) { job = j; break; }
+            if (!job) { cv_.wait(lk); continue; }
+            const int k = job->next++;
+            ++job->active;
+            lk.unlock();
+            job->fn(k);
+            lk.lock();
+            job->done[k] = 1;
+            ++job->finished;
+            --job->active;
+            job->cv.notify_all();
+        }
+    }
+    static inline bool forked_ = false;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::vector<Job*> jobs_;
+    std::vector<std::thread> workers_;
+};
 
 static int band_alloc(hp_ctx* ctx, int64_t n_, int num_, int bal_first_) {
     struct { int64_t n; int num; int bal_first; } bb{n_, num_, bal_first_};
@@ -260,7 +356,7 @@ static int band_alloc(hp_ctx* ctx, int64_t n_, int num_, int bal_first_) {
         CK(cudaMalloc(&ctx->d_rownz, n * sizeof(unsigned int)));
         ctx->cap_n = n;
     }
-    const size_t stage_bytes = plane * 12 + (size_t)num * 8;
+    const size_t stage_bytes = plane * 12 + (size_t)num * 8 + (size_t)num * sizeof(PackedDiag);
     if (stage_bytes > ctx->cap_stage) {
         if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
         ctx->h_stage = nullptr; ctx->cap_stage = 0;
@@ -307,8 +403,6 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
     int* traw = (int*)((char*)ctx->d_tmp + plane * 8);
     const int per = std::max(1, (int)((size_t)(4u << 20) / ((size_t)pitch * 12)));     // ~4 MB per chunk
     const int nchunk = (num + per - 1) / per;
-    unsigned nthreads = pack_threads();
-    if (plane < (1u << 20)) nthreads = 1;
     cudaError_t cerr = cudaSuccess;
     auto send = [&](int k) {
         const int d0 = k * per, d1 = std::min(num, d0 + per);
@@ -317,28 +411,7 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
         if (e == cudaSuccess) e = cudaMemcpyAsync(traw + off, hraw + off, cnt * 4, cudaMemcpyHostToDevice, ctx->stream);
         if (e != cudaSuccess && cerr == cudaSuccess) cerr = e;
     };
-    if (nthreads == 1) {
-        for (int k = 0; k < nchunk; ++k) { pack(k * per, std::min(num, (k + 1) * per)); send(k); }
-    } else {
-        std::atomic<int> next{0};
-        std::vector<std::atomic<int>> done(nchunk);
-        for (auto& f : done) f.store(0, std::memory_order_relaxed);
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nthreads; ++t)
-            th.emplace_back([&]() {
-                for (;;) {
-                    const int k = next.fetch_add(1);
-                    if (k >= nchunk) break;
-                    pack(k * per, std::min(num, (k + 1) * per));
-                    done[k].store(1, std::memory_order_release);
-                }
-            });
-        for (int k = 0; k < nchunk; ++k) {
-            while (!done[k].load(std::memory_order_acquire)) std::this_thread::yield();
-            send(k);
-        }
-        for (auto& t : th) t.join();
-    }
+    PackPool::get().run_ordered(nchunk, [&](int k) { pack(k * per, std::min(num, (k + 1) * per)); }, send);
     if (cerr != cudaSuccess) return fail(ctx, HP_ERR_CUDA, std::string("band upload: ") + cudaGetErrorString(cerr));
     CK(cudaMemsetAsync(ctx->d_rownz, 0, (size_t)n * sizeof(unsigned int), ctx->stream));
     k_relayout<double><<<dim3((pitch + 255) / 256, num), 256, 0, ctx->stream>>>(tbal, ctx->d_bal, ctx->d_rownz, pitch, num);
@@ -350,7 +423,15 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
     CK(cudaMemcpyAsync(ctx->d_b2, b->b2, n * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->n = n; ctx->num = num; ctx->bal_first = bf; ctx->pitch = pitch; ctx->plane = plane;
+    ctx->h2d_bytes = (int64_t)(plane * 12 + (size_t)num * 8 + (size_t)n * 16);
     ctx->have_band = true;
+    return HP_OK;
+}
+
+extern "C" int hp_upload_bytes(hp_ctx* ctx, int64_t* bytes) {
+    if (!ctx || !bytes) return fail(ctx, HP_ERR_INVALID, "NULL argument");
+    if (!ctx->have_band) return fail(ctx, HP_ERR_STATE, "no band uploaded");
+    *bytes = ctx->h2d_bytes;
     return HP_OK;
 }
 
@@ -381,49 +462,43 @@ extern "C" int hp_band_upload_counts(hp_ctx* ctx, const hp_counts_desc* b) {
     int2* comb = leaf + (size_t)nb * maxleaf;
     double* part = (double*)(comb + (size_t)nb * maxleaf);
     CK(cudaMemcpyAsync(ctx->d_w, b->weights, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    // raw counts: packed by worker threads chunk by chunk while the copy engine uploads the previous chunk
-    auto pack = [&](int d_begin, int d_end) {
-        for (int d = d_begin; d < d_end; ++d) {
-            const size_t len = (size_t)(n - d);
-            int* rr = hraw + (size_t)d * pitch;
-            memcpy(rr, b->raw_diags[d], len * sizeof(int));
-            memset(rr + len, 0, (pitch - len) * sizeof(int));
-        }
-    };
-    const int per = std::max(1, (int)((size_t)(2u << 20) / ((size_t)pitch * 4)));      // ~2 MB per chunk
+    // raw counts: worker threads narrow each diagonal to u8 / u16 / i32 (hp_hostpack.cpp) straight into the pinned
+    // staging buffer, chunk by chunk, while the copy engine uploads the chunks already done; the device widens
+    // them back into the plain int32 landing zone (k_unpack_counts).  A chunk owns the byte range its diagonals
+    // would take as int32, so chunks are packed independently and only the bytes used are sent.
+    unsigned char* hpk = (unsigned char*)hraw;                       // pinned, plane * 4 bytes
+    unsigned char* dpk = (unsigned char*)ctx->d_tmp;                 // device: first plane * 4 bytes of the landing zone
+    PackedDiag* htab = (PackedDiag*)((char*)ctx->h_stage + plane * 12 + (size_t)num * 8);
+    CK(ensure(&ctx->d_pk, &ctx->cap_pk, (size_t)num));
+    const int per = std::max(1, (int)((size_t)(5u << 19) / ((size_t)pitch * 4)));      // ~2.5 MB of int32 per chunk
     const int nchunk = (num + per - 1) / per;
-    unsigned nthreads = pack_threads();
-    if (plane < (1u << 20)) nthreads = 1;
-    cudaError_t cerr = cudaSuccess;
-    auto send = [&](int k) {
+    std::vector<size_t> used(nchunk);
+    auto pack = [&](int k) {
         const int d0 = k * per, d1 = std::min(num, d0 + per);
-        const size_t off = (size_t)d0 * pitch, cnt = (size_t)(d1 - d0) * pitch;
-        cudaError_t e = cudaMemcpyAsync(traw + off, hraw + off, cnt * 4, cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess && cerr == cudaSuccess) cerr = e;
-    };
-    if (nthreads == 1) {
-        for (int k = 0; k < nchunk; ++k) { pack(k * per, std::min(num, (k + 1) * per)); send(k); }
-    } else {
-        std::atomic<int> next{0};
-        std::vector<std::atomic<int>> done(nchunk);
-        for (auto& f : done) f.store(0, std::memory_order_relaxed);
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nthreads; ++t)
-            th.emplace_back([&]() {
-                for (;;) {
-                    const int k = next.fetch_add(1);
-                    if (k >= nchunk) break;
-                    pack(k * per, std::min(num, (k + 1) * per));
-                    done[k].store(1, std::memory_order_release);
-                }
-            });
-        for (int k = 0; k < nchunk; ++k) {
-            while (!done[k].load(std::memory_order_acquire)) std::this_thread::yield();
-            send(k);
+        const size_t base = (size_t)d0 * pitch * 4;
+        size_t off = base;
+        for (int d = d0; d < d1; ++d) {
+            const size_t len = (size_t)(n - d);
+            const int es = narrow_diagonal((const int32_t*)b->raw_diags[d], len, hpk + off);
+            htab[d].off = off; htab[d].esize = es; htab[d].len = (unsigned)len;
+            off += (len * es + 15) & ~(size_t)15;
         }
-        for (auto& t : th) t.join();
-    }
+        used[k] = off - base;
+    };
+    cudaError_t cerr = cudaSuccess;
+    size_t sent = 0;
+    auto send = [&](int k) {
+        const size_t base = (size_t)k * per * pitch * 4;
+        cudaError_t e = cudaMemcpyAsync(dpk + base, hpk + base, used[k], cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess && cerr == cudaSuccess) cerr = e;
+        sent += used[k];
+    };
+    PackPool::get().run_ordered(nchunk, pack, send);
     if (cerr != cudaSuccess) return fail(ctx, HP_ERR_CUDA, std::string("band upload: ") + cudaGetErrorString(cerr));
+    CK(cudaMemcpyAsync(ctx->d_pk, htab, (size_t)num * sizeof(PackedDiag), cudaMemcpyHostToDevice, st));
+    ctx->h2d_bytes = (int64_t)(sent + (size_t)num * sizeof(PackedDiag) + (size_t)n * 8);
+    k_unpack_counts<<<dim3((pitch / 4 + 255) / 256, num), 256, 0, st>>>(dpk, ctx->d_pk, traw, pitch);
+    CK(cudaGetLastError());
     CK(cudaMemsetAsync(ctx->d_rownz, 0, (size_t)n * sizeof(unsigned int), st));
     CK(cudaMemsetAsync(ctx->d_ir, 0, (size_t)num * 8, st));
     k_relayout<int><<<dim3((pitch + 255) / 256, num), 256, 0, st>>>(traw, ctx->d_raw, nullptr, pitch, num);
@@ -904,8 +979,11 @@ extern "C" int hp_get_survivors(hp_ctx* ctx, hp_survivor* buf, int64_t capacity,
     if (capacity < (int64_t)ctx->nsurv) return fail(ctx, HP_ERR_CAPACITY, "survivor buffer too small");
     CK(cudaSetDevice(ctx->device));
     if (ctx->nsurv) {
-        CK(cudaMemcpyAsync(buf, ctx->d_surv, (size_t)ctx->nsurv * sizeof(hp_survivor), cudaMemcpyDeviceToHost, ctx->stream));
+        const size_t bytes = (size_t)ctx->nsurv * sizeof(hp_survivor);
+        CK(ensure_host(&ctx->h_out, &ctx->cap_out, bytes));
+        CK(cudaMemcpyAsync(ctx->h_out, ctx->d_surv, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        memcpy(buf, ctx->h_out, bytes);
     }
     return HP_OK;
 }
@@ -951,8 +1029,9 @@ extern "C" int hp_get_gaps(hp_ctx* ctx, uint8_t* out, int64_t n) {
     if (!ctx->have_band) return fail(ctx, HP_ERR_STATE, "hp_band_upload must come first");
     if (n < ctx->n) return fail(ctx, HP_ERR_CAPACITY, "gap buffer too small");
     CK(cudaSetDevice(ctx->device));
-    std::vector<unsigned int> nz(ctx->n);
-    CK(cudaMemcpyAsync(nz.data(), ctx->d_rownz, (size_t)ctx->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ensure_host(&ctx->h_out, &ctx->cap_out, (size_t)ctx->n * 4));
+    const unsigned int* nz = (const unsigned int*)ctx->h_out;
+    CK(cudaMemcpyAsync(ctx->h_out, ctx->d_rownz, (size_t)ctx->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (int64_t i = 0; i < ctx->n; ++i) out[i] = nz[i] ? 0 : 1;
     return HP_OK;

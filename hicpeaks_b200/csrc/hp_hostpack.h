@@ -1,0 +1,13 @@
+// Host-side narrowing of count diagonals for the upload path (see hp_hostpack.cpp).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace hp {
+
+// Writes src[0..len) to dst in the narrowest of u8 / u16 / i32 that holds every value exactly (counts are
+// non-negative; a negative value forces i32).  dst must have room for len * 4 bytes.  Returns the element size
+// chosen: 1, 2 or 4.
+int narrow_diagonal(const int32_t* src, size_t len, void* dst);
+
+}  // namespace hp

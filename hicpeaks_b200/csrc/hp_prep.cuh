@@ -15,6 +15,40 @@ namespace hp {
 
 constexpr int kPrepThreads = 256;
 
+// Count upload: the host narrows every diagonal to the smallest of u8 / u16 / i32 that holds its values
+// (hp_hostpack.cpp) so that ~1 byte per band pixel crosses PCIe; this widens them back into the plain
+// [num][pitch] int32 landing zone (zero tails) that k_relayout / k_prep_band read.  4 bins per thread.
+struct PackedDiag {
+    unsigned long long off;      // byte offset of the diagonal in the packed buffer (16-byte aligned)
+    unsigned int esize;          // 1, 2 or 4
+    unsigned int len;            // n - d
+};
+
+__global__ void __launch_bounds__(256) k_unpack_counts(const unsigned char* __restrict__ packed, const PackedDiag* __restrict__ tab,
+                                                       int* __restrict__ raw_plain, int pitch) {
+    const int d = blockIdx.y;
+    const int rb = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (rb >= pitch) return;
+    const PackedDiag t = tab[d];
+    int4 v = make_int4(0, 0, 0, 0);
+    if (rb < (int)t.len) {
+        const unsigned char* src = packed + t.off;
+        if (t.esize == 1) {
+            const uchar4 u = *reinterpret_cast<const uchar4*>(src + rb);
+            v = make_int4(u.x, u.y, u.z, u.w);
+        } else if (t.esize == 2) {
+            const ushort4 u = *reinterpret_cast<const ushort4*>(src + (size_t)rb * 2);
+            v = make_int4(u.x, u.y, u.z, u.w);
+        } else {
+            v = *reinterpret_cast<const int4*>(src + (size_t)rb * 4);
+        }
+        if (rb + 1 >= (int)t.len) v.y = 0;           // the last quad of a diagonal may hold staging bytes past its end
+        if (rb + 2 >= (int)t.len) v.z = 0;
+        if (rb + 3 >= (int)t.len) v.w = 0;
+    }
+    *reinterpret_cast<int4*>(raw_plain + (size_t)d * pitch + rb) = v;
+}
+
 // one CTA per diagonal d in [bal_first, num).  comp: scratch [num][pitch] doubles; leaf: scratch [num][maxleaf] int2
 // (start, len); part: scratch [num][maxleaf * 8] doubles; comb: scratch [num][maxleaf] int2.
 __global__ void __launch_bounds__(kPrepThreads) k_prep_band(const int* __restrict__ raw_plain, const double* __restrict__ w, int n, int num,

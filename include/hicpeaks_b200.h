@@ -94,6 +94,11 @@ int hp_band_upload_counts(hp_ctx* ctx, const hp_counts_desc* band);
 /* inspection of the uploaded / derived band: what = 0 IR[num], 1 biases[n], 2 balanced band [num][n] */
 int hp_dump_band(hp_ctx* ctx, int32_t what, double* out, int64_t capacity);
 
+/* Bytes the last hp_band_upload / hp_band_upload_counts moved host -> device.  hp_band_upload_counts narrows each
+ * count diagonal on the host to the smallest of u8 / u16 / i32 that holds its values exactly before it crosses
+ * PCIe (the device widens it again), so this is usually ~1 byte per band pixel.  Measurement aid (bench.py). */
+int hp_upload_bytes(hp_ctx* ctx, int64_t* bytes);
+
 /* ---- HiCCUPS scoring: callers.py:98-287 ------------------------------------------------------ */
 typedef struct hp_hiccups_params {
     int32_t npw;                 /* number of (pw, ww) pairs                                   */

@@ -56,3 +56,31 @@ def test_poisson_tail_matches_scipy(ctx):
     got = ctx.poisson_sf(k, mu)
     ref = 1 - pdtr(k, mu)
     assert np.abs(got - ref).max() < 2e-14
+
+
+def test_narrowed_count_upload_restores_every_count():
+    """hp_band_upload_counts sends each count diagonal as u8 / u16 / i32, whichever holds it exactly; the band the
+    device rebuilds (balanced = count * w[r] * w[c], scripts/pyHICCUPS:143) must not depend on the format taken."""
+    from hicpeaks_b200 import _capi
+    n, num, mw = 1237, 131, 3
+    rng = np.random.default_rng(5)
+    w = np.exp(rng.normal(0, 0.2, n))
+    w[rng.choice(n, 9, replace=False)] = np.nan
+    Dg = [rng.poisson(40.0 / (d + 1), n - d).astype(np.int32) for d in range(num)]
+    Dg[0][:] += 300                       # every value above a byte
+    Dg[4][n - 5] = 255                    # the last value a byte holds, in the final (partial) quad
+    Dg[5][17] = 256                       # one value over
+    Dg[9][n - 10] = 65535
+    Dg[11][0] = 65536
+    Dg[12][3] = 2 ** 31 - 1
+    Dg[13][:] = 0
+    with _capi.Context(0) as ctx:
+        ctx.upload_counts(n, num, mw, Dg, w)
+        bal = ctx.dump_band(2)
+        sent = ctx.upload_bytes()
+    for d in range(mw, num):
+        exp = Dg[d].astype(np.float64) * w[: n - d] * w[d:]
+        exp[Dg[d] == 0] = 0.0
+        exp[np.isnan(exp)] = 0.0
+        assert np.array_equal(bal[d, : n - d], exp), d
+    assert sent < 2 * sum(a.size for a in Dg)          # most diagonals travelled as bytes
