@@ -3,6 +3,7 @@
 // launch sequence  K1 levels -> replay -> bE table -> K2 score -> K3 BH -> survivor filter.
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -23,12 +24,17 @@
 
 using namespace hp;
 
+#ifndef HP_SYNC_DEFAULT
+#define HP_SYNC_DEFAULT 2
+#endif
+
 static thread_local std::string g_err;
 
 struct hp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};
+    cudaEvent_t ev_sync = nullptr;    // blocking-sync event (stream_sync)
     std::string err;
     // sweep program + chunk tables: pinned host mirror and the device copy the kernels read
     Tables* h_tab = nullptr;
@@ -92,6 +98,36 @@ struct hp_ctx {
     double* d_apa_avg = nullptr; size_t cap_apa_avg = 0;
     int64_t apa_npos = 0; int apa_w = 0;
 };
+
+// How a host thread waits for its context's stream (HP_SYNC=spin|yield|block):
+//   spin   cudaStreamSynchronize, the runtime's default policy: lowest latency while every waiting thread has a core
+//   yield  poll cudaStreamQuery and give the core away between polls: as quick as spinning on an idle box, and the
+//          waiting threads (one per chromosome in flight, times the ranks on the box) do not starve the ones that
+//          have launches to issue when they outnumber the cores
+//   block  a blocking-sync event: the thread sleeps; highest wake-up latency
+static int sync_mode() {
+    static const int mode = []() {
+        const char* e = getenv("HP_SYNC");
+        if (e && !strcmp(e, "spin")) return 0;
+        if (e && !strcmp(e, "block")) return 1;
+        if (e && !strcmp(e, "yield")) return 2;
+        return HP_SYNC_DEFAULT;
+    }();
+    return mode;
+}
+static cudaError_t stream_sync(hp_ctx* ctx) {
+    const int m = sync_mode();
+    if (m == 2) {
+        for (;;) {
+            const cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q != cudaErrorNotReady) return q;
+            sched_yield();
+        }
+    }
+    if (m == 0 || !ctx->ev_sync) return cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaEventRecord(ctx->ev_sync, ctx->stream);
+    return e == cudaSuccess ? cudaEventSynchronize(ctx->ev_sync) : e;
+}
 
 static int fail(hp_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg;
@@ -188,6 +224,7 @@ extern "C" int hp_ctx_create(int device, int max_chunks, const double* edges, hp
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(fail(nullptr, HP_ERR_CUDA, "stream create failed"));
     for (auto& e : ctx->ev) cudaEventCreate(&e);
+    cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming);
     cudaDriverEntryPointQueryResult qres;
     void* fn = nullptr;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
@@ -213,7 +250,7 @@ extern "C" int hp_ctx_create(int device, int max_chunks, const double* edges, hp
     k_ptab<<<(unsigned)((tb + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_tab, ctx->d_ptab);
     ctx->h_ptab.resize(tb);
     cudaMemcpyAsync(ctx->h_ptab.data(), ctx->d_ptab, tb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = stream_sync(ctx);
     if (e != cudaSuccess) return bail(fail(nullptr, HP_ERR_CUDA, std::string("Poisson table kernel: ") + cudaGetErrorString(e)));
     for (int i = 1; i <= max_chunks; ++i)
         if (ctx->h_ptab[ctx->chunks.hoff[i] + ctx->chunks.hw[i] - 1] != 0.0)
@@ -225,7 +262,7 @@ extern "C" int hp_ctx_create(int device, int max_chunks, const double* edges, hp
 extern "C" void hp_ctx_destroy(hp_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) stream_sync(ctx);
     void* ptrs[] = {ctx->d_ptab, ctx->d_raw, ctx->d_bal, ctx->d_lvl, ctx->d_ir, ctx->d_b1, ctx->d_b2, ctx->d_rownz,
                     ctx->d_lhist, ctx->d_betab, ctx->d_hist, ctx->d_qtab, ctx->d_small, ctx->d_cnt, ctx->d_numbin,
                     ctx->d_cand, ctx->d_surv, ctx->d_dump, ctx->d_tmp, ctx->d_tab, ctx->d_w, ctx->d_pk, ctx->d_prep, ctx->d_apa_bal, ctx->d_apa_plan, ctx->d_apa_pos,
@@ -234,6 +271,7 @@ extern "C" void hp_ctx_destroy(hp_ctx* ctx) {
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -421,7 +459,7 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
     CK(cudaMemcpyAsync(ctx->d_ir, hir, (size_t)num * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_b1, b->b1, n * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_b2, b->b2, n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     ctx->n = n; ctx->num = num; ctx->bal_first = bf; ctx->pitch = pitch; ctx->plane = plane;
     ctx->h2d_bytes = (int64_t)(plane * 12 + (size_t)num * 8 + (size_t)n * 16);
     ctx->have_band = true;
@@ -454,13 +492,15 @@ extern "C" int hp_band_upload_counts(hp_ctx* ctx, const hp_counts_desc* b) {
     int* traw = (int*)((char*)ctx->d_tmp + plane * 8);
     double* comp = ctx->d_tmp;                        // [num - bf][pitch] compaction scratch (the unused balanced landing zone)
     CK(ensure(&ctx->d_w, &ctx->cap_w, (size_t)n + 64));
-    const int maxleaf = pitch / 64 + 8;
+    int depth = 0;                                     // levels of numpy's pairwise recursion below the root (hp_prep.cuh)
+    while ((pitch >> depth) + 16 > 128) ++depth;   // a node of level l holds <= m / 2^l + 15 values
+    const int nslot = 2 << depth;
     const int nb = num - bf;
-    const size_t prep_bytes = (size_t)nb * maxleaf * (8 + 8 + 64);
+    const size_t prep_bytes = (size_t)nb * nslot * (8 + 8 + 4);
     CK(ensure(&ctx->d_prep, &ctx->cap_prep, prep_bytes));
     int2* leaf = (int2*)ctx->d_prep;
-    int2* comb = leaf + (size_t)nb * maxleaf;
-    double* part = (double*)(comb + (size_t)nb * maxleaf);
+    double* tval = (double*)(leaf + (size_t)nb * nslot);
+    int* tlist = (int*)(tval + (size_t)nb * nslot);
     CK(cudaMemcpyAsync(ctx->d_w, b->weights, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     // raw counts: worker threads narrow each diagonal to u8 / u16 / i32 (hp_hostpack.cpp) straight into the pinned
     // staging buffer, chunk by chunk, while the copy engine uploads the chunks already done; the device widens
@@ -507,13 +547,13 @@ extern "C" int hp_band_upload_counts(hp_ctx* ctx, const hp_counts_desc* b) {
         const size_t cnt = (size_t)bf * pitch;
         k_zero_planes<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(ctx->d_bal, cnt);
     }
-    const int prep_smem = maxleaf * 16 <= 40 * 1024 ? maxleaf * 16 : 0;
+    const int prep_smem = nslot * 20 <= 40 * 1024 ? nslot * 20 : 0;
     k_prep_band<<<nb, kPrepThreads, prep_smem, st>>>(traw, ctx->d_w, (int)n, num, pitch, bf, ctx->d_bal, ctx->d_rownz, ctx->d_ir, comp, leaf,
-                                                   part, comb, maxleaf, prep_smem ? 1 : 0);
+                                                   tval, tlist, depth, nslot, prep_smem ? 1 : 0);
     CK(cudaGetLastError());
     k_prep_bias<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_w, ctx->d_b1, ctx->d_b2, (int)n);
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(st));
+    CK(stream_sync(ctx));
     ctx->n = n; ctx->num = num; ctx->bal_first = bf; ctx->pitch = pitch; ctx->plane = plane;
     ctx->have_band = true;
     return HP_OK;
@@ -528,14 +568,14 @@ extern "C" int hp_dump_band(hp_ctx* ctx, int32_t what, double* out, int64_t capa
         const int64_t cnt = what == 0 ? ctx->num : ctx->n;
         if (capacity < cnt) return fail(ctx, HP_ERR_CAPACITY, "buffer too small");
         CK(cudaMemcpyAsync(out, what == 0 ? ctx->d_ir : ctx->d_b1, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(stream_sync(ctx));
         return HP_OK;
     }
     if (what != 2) return fail(ctx, HP_ERR_INVALID, "bad selector");
     if (capacity < (int64_t)ctx->num * ctx->n) return fail(ctx, HP_ERR_CAPACITY, "buffer too small");
     std::vector<double> tmp(ctx->plane);
     CK(cudaMemcpyAsync(tmp.data(), ctx->d_bal, ctx->plane * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     for (int d = 0; d < ctx->num; ++d)
         for (int64_t r = 0; r < ctx->n; ++r) out[(size_t)d * ctx->n + r] = tmp[qidx(d, (int)r, ctx->pitch)];
     return HP_OK;
@@ -720,7 +760,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     CK(cudaEventRecord(ctx->ev[1], st));
     std::vector<unsigned long long> lh(G.nsteps + 1);
     CK(cudaMemcpyAsync(lh.data(), ctx->d_lhist, lh.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(stream_sync(ctx));
 
     // ---- replay of the adaptive-width control flow (callers.py:203-232) ------------------------
     unsigned long long total = 0;
@@ -865,7 +905,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
         CK(cudaEventRecord(ctx->ev[3], st));
         CK(cudaMemcpyAsync(cnt, ctx->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(small, ctx->d_small, sizeof(small), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(stream_sync(ctx));
         if (cnt[1] == 0) break;
         if (attempt == 1) return fail(ctx, HP_ERR_CAPACITY, "candidate buffer overflow");
         want = (size_t)total * P.npw + 1024;      // every pixel can be a candidate at most once per pair
@@ -941,14 +981,14 @@ extern "C" int hp_hiccups_fdr(hp_ctx* ctx, const int32_t* numbin_override, hp_hi
         CK(cudaMemcpyAsync(cnt, ctx->d_cnt + 4, sizeof(cnt), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(nrej, ctx->d_small + 32, sizeof(nrej), cudaMemcpyDeviceToHost, st));
         if (attempt == 0) CK(cudaEventRecord(ctx->ev[5], st));
-        CK(cudaStreamSynchronize(st));
+        CK(stream_sync(ctx));
         if (cnt[1] == 0) break;
         if (attempt == 1) return fail(ctx, HP_ERR_CAPACITY, "survivor buffer overflow");
         want = (size_t)ctx->ncand + 16;
     }
     if (ctx->ncand == 0) {
         CK(cudaEventRecord(ctx->ev[5], st));
-        CK(cudaStreamSynchronize(st));
+        CK(stream_sync(ctx));
     }
     for (int i = 0; i < P.npw; ++i)
         for (int fl = 0; fl < 2; ++fl) S.lf[i][fl].n_reject = (int64_t)nrej[i * 2 + fl];
@@ -982,7 +1022,7 @@ extern "C" int hp_get_survivors(hp_ctx* ctx, hp_survivor* buf, int64_t capacity,
         const size_t bytes = (size_t)ctx->nsurv * sizeof(hp_survivor);
         CK(ensure_host(&ctx->h_out, &ctx->cap_out, bytes));
         CK(cudaMemcpyAsync(ctx->h_out, ctx->d_surv, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(stream_sync(ctx));
         memcpy(buf, ctx->h_out, bytes);
     }
     return HP_OK;
@@ -1002,7 +1042,7 @@ extern "C" int hp_hist_export(hp_ctx* ctx, int64_t* out, int64_t capacity) {
     CK(cudaSetDevice(ctx->device));
     std::vector<unsigned int> h(cnt);
     CK(cudaMemcpyAsync(h.data(), ctx->d_hist, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     for (size_t i = 0; i < cnt; ++i) out[i] = h[i];
     return HP_OK;
 }
@@ -1019,7 +1059,7 @@ extern "C" int hp_hist_import(hp_ctx* ctx, const int64_t* in, int64_t count) {
     }
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(ctx->d_hist, h.data(), cnt * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     ctx->fdr_done = false;
     return HP_OK;
 }
@@ -1032,7 +1072,7 @@ extern "C" int hp_get_gaps(hp_ctx* ctx, uint8_t* out, int64_t n) {
     CK(ensure_host(&ctx->h_out, &ctx->cap_out, (size_t)ctx->n * 4));
     const unsigned int* nz = (const unsigned int*)ctx->h_out;
     CK(cudaMemcpyAsync(ctx->h_out, ctx->d_rownz, (size_t)ctx->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     for (int64_t i = 0; i < ctx->n; ++i) out[i] = nz[i] ? 0 : 1;
     return HP_OK;
 }
@@ -1046,7 +1086,7 @@ extern "C" int hp_dump_levels(hp_ctx* ctx, uint8_t* out, int64_t capacity) {
     const int rows = ctx->dhi - ctx->dlo + 1, pitch = ctx->pitch;
     std::vector<unsigned char> tmp((size_t)rows * pitch);
     CK(cudaMemcpyAsync(tmp.data(), ctx->d_lvl + (size_t)ctx->dlo * pitch, tmp.size(), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     for (int k = 0; k < rows; ++k) {
         uint8_t* o = out + (size_t)(ctx->dlo + k) * ctx->n;
         for (int64_t r = 0; r < ctx->n; ++r) o[r] = tmp[qidx(k, (int)r, pitch)];
@@ -1063,7 +1103,7 @@ extern "C" int hp_dump_plane(hp_ctx* ctx, int32_t pair, int32_t background, int3
     CK(cudaSetDevice(ctx->device));
     const double* src = ctx->d_dump + (size_t)((pair * 2 + background) * 3 + what) * ctx->plane;
     CK(cudaMemcpy2DAsync(out, ctx->n * 8, src, (size_t)ctx->pitch * 8, ctx->n * 8, ctx->num, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     return HP_OK;
 }
 
@@ -1085,13 +1125,13 @@ extern "C" int hp_get_chunk_table(hp_ctx* ctx, int32_t pair, int32_t background,
     if (hist) {
         std::vector<unsigned int> h(cnt);
         CK(cudaMemcpyAsync(h.data(), ctx->d_hist + (size_t)lf * C.total_bins, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(stream_sync(ctx));
         for (size_t i = 0; i < cnt; ++i) hist[i] = h[i];
     }
     if (p) memcpy(p, ctx->h_ptab.data(), cnt * 8);
     if (q) {
         CK(cudaMemcpyAsync(q, ctx->d_qtab + (size_t)lf * C.total_bins, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(stream_sync(ctx));
     }
     return HP_OK;
 }
@@ -1108,7 +1148,7 @@ extern "C" int hp_poisson_sf(hp_ctx* ctx, const double* k, const double* mu, dou
         k_poisson_sf<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(d, d + count, d + 2 * count, count);
         e = cudaMemcpyAsync(out, d + 2 * count, count * 8, cudaMemcpyDeviceToHost, ctx->stream);
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = stream_sync(ctx);
     cudaFree(d);
     if (e != cudaSuccess) return fail(ctx, HP_ERR_CUDA, cudaGetErrorString(e));
     return HP_OK;
@@ -1156,7 +1196,7 @@ extern "C" int hp_apa_upload(hp_ctx* ctx, const hp_apa_desc* b) {
         k_apa_transpose<<<dim3((unsigned)((n + 31) / 32), (num + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(tmp, ctx->d_apa_bal, n, num);
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = stream_sync(ctx);
     cudaFree(tmp);
     if (e != cudaSuccess) return fail(ctx, HP_ERR_CUDA, std::string("APA band upload: ") + cudaGetErrorString(e));
     ctx->apa_n = n; ctx->apa_num = num; ctx->apa_npos = 0;
@@ -1195,7 +1235,7 @@ extern "C" int hp_apa_windows(hp_ctx* ctx, const int32_t* pos_i, const int32_t* 
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(valid, ctx->d_apa_valid, npos, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(mean_arr, ctx->d_apa_mean, npos * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(stream_sync(ctx));
     ctx->apa_npos = npos; ctx->apa_w = w;
     return HP_OK;
 }
@@ -1206,7 +1246,7 @@ static int apa_plan(hp_ctx* ctx, int cells) {
     P.n = cells;
     apa_rec(P, 0, cells);
     CK(cudaMemcpyAsync(ctx->d_apa_plan, &P, sizeof(P), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));      // P lives on this stack frame
+    CK(stream_sync(ctx));      // P lives on this stack frame
     return HP_OK;
 }
 
@@ -1227,7 +1267,7 @@ extern "C" int hp_apa_load_windows(hp_ctx* ctx, const double* wins, int64_t npos
     k_apa_means<<<(unsigned)npos, kApaThreads, smem, st>>>(ctx->d_apa_plan, ctx->d_apa_wins, cells, ctx->d_apa_mean);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(mean_arr, ctx->d_apa_mean, npos * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(stream_sync(ctx));
     ctx->apa_npos = npos; ctx->apa_w = w;
     return HP_OK;
 }
@@ -1248,7 +1288,7 @@ extern "C" int hp_apa_accumulate(hp_ctx* ctx, const int64_t* sel, int64_t nsel, 
     k_apa_accumulate<<<(cells + 31) / 32, 32, 0, st>>>(ctx->d_apa_wins, ctx->d_apa_sel, nsel, cells, ctx->d_apa_avg, init ? 1 : 0);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(acc, ctx->d_apa_avg, (size_t)cells * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(stream_sync(ctx));
     return HP_OK;
 }
 
@@ -1262,6 +1302,6 @@ extern "C" int hp_apa_get_windows(hp_ctx* ctx, const int64_t* sel, int64_t nsel,
         CK(cudaMemcpyAsync(out + (size_t)k * cells, ctx->d_apa_wins + (size_t)sel[k] * cells, (size_t)cells * 8, cudaMemcpyDeviceToHost,
                            ctx->stream));
     }
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     return HP_OK;
 }

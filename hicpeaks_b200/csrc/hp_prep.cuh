@@ -49,15 +49,17 @@ __global__ void __launch_bounds__(256) k_unpack_counts(const unsigned char* __re
     *reinterpret_cast<int4*>(raw_plain + (size_t)d * pitch + rb) = v;
 }
 
-// one CTA per diagonal d in [bal_first, num).  comp: scratch [num][pitch] doubles; leaf: scratch [num][maxleaf] int2
-// (start, len); part: scratch [num][maxleaf * 8] doubles; comb: scratch [num][maxleaf] int2.
+// one CTA per diagonal d in [bal_first, num).  comp: scratch [num][pitch] doubles.  The summation tree has `depth`
+// levels below the root and nslot = 2^(depth + 1) heap slots: in shared memory when it fits (use_smem), otherwise in
+// the scratch arrays tree / tval / tlist, [num][nslot] each.
 __global__ void __launch_bounds__(kPrepThreads) k_prep_band(const int* __restrict__ raw_plain, const double* __restrict__ w, int n, int num,
                                                             int pitch, int bal_first, double* __restrict__ bal, unsigned int* __restrict__ rownz,
-                                                            double* __restrict__ ir, double* __restrict__ comp, int2* __restrict__ leaf,
-                                                            double* __restrict__ part, int2* __restrict__ comb, int maxleaf, int use_smem) {
-    extern __shared__ __align__(16) unsigned char prep_smem[];     // use_smem: [maxleaf] leaf sums + [maxleaf] combine list
+                                                            double* __restrict__ ir, double* __restrict__ comp, int2* __restrict__ tree,
+                                                            double* __restrict__ tval, int* __restrict__ tlist, int depth, int nslot,
+                                                            int use_smem) {
+    extern __shared__ __align__(16) unsigned char prep_smem[];     // use_smem: the summation tree (nodes, values, leaf list)
     __shared__ int sh_scan[kPrepThreads / 32];
-    __shared__ int sh_base, sh_nleaf, sh_ncomb;
+    __shared__ int sh_base, sh_nleaf;
     const int d = bal_first + blockIdx.x;
     const int len = n - d;
     const int* src = raw_plain + (size_t)d * pitch;
@@ -79,7 +81,10 @@ __global__ void __launch_bounds__(kPrepThreads) k_prep_band(const int* __restric
             const int r = rb + k;
             const bool in = r < len;
             v[k] = 0.0;
-            if (in && cc[k] != 0) v[k] = __dmul_rn(__dmul_rn((double)cc[k], w[r]), w[r + d]);
+            if (in) {                                   // weights loaded whether or not a count is stored: no load waits on another
+                const double p = __dmul_rn(__dmul_rn((double)cc[k], w[r]), w[r + d]);
+                if (cc[k] != 0) v[k] = p;
+            }
             const bool isn = v[k] != v[k];
             keep[k] = in && !isn;
             nk += keep[k];
@@ -112,80 +117,75 @@ __global__ void __launch_bounds__(kPrepThreads) k_prep_band(const int* __restric
     }
     const int m = sh_base;
     // ---- numpy pairwise_sum(cp[0..m)) -------------------------------------------------------------------
-    int2* lf = leaf + (size_t)blockIdx.x * maxleaf;
-    int2* cb = use_smem ? reinterpret_cast<int2*>(prep_smem + (size_t)maxleaf * 8) : comb + (size_t)blockIdx.x * maxleaf;
-    double* pt = part + (size_t)blockIdx.x * maxleaf * 8;
-    double* res = use_smem ? reinterpret_cast<double*>(prep_smem) : nullptr;   // leaf results (stride 1) when in smem
-    if (threadIdx.x == 0) {
-        // depth-first walk of the recursion: leaves left to right, combines in post-order
-        int nleaf = 0, ncomb = 0, sp = 0;
-        int st_start[40], st_n[40], st_state[40], st_left[40];
-        st_start[0] = 0; st_n[0] = m; st_state[0] = 0; st_left[0] = 0;
-        int ret = 0;                                   // leaf slot that holds the result of the last finished node
-        while (sp >= 0) {
-            const int s0 = st_start[sp], nn = st_n[sp];
-            if (nn <= 128) {
-                lf[nleaf] = make_int2(s0, nn);
-                ret = nleaf++;
-                --sp;
-                continue;
+    // numpy's recursion: a block of n <= 128 values is summed with 8 interleaved accumulators; a longer block is
+    // split at n2 = n / 2 - (n / 2) % 8 and its value is value(left) + value(right).  The value of a node depends on
+    // its two children only, so the tree is built level by level (heap numbering: children of node k are 2k + 1,
+    // 2k + 2), all leaves are summed in parallel, and the levels are folded bottom-up -- the same additions in
+    // the same association as the sequential recursion, without one thread walking it.
+    int2* node = use_smem ? reinterpret_cast<int2*>(prep_smem) : tree + (size_t)blockIdx.x * nslot;          // (start, n); n < 0: absent
+    double* val = use_smem ? reinterpret_cast<double*>(prep_smem + (size_t)nslot * 8) : tval + (size_t)blockIdx.x * nslot;
+    int* lst = use_smem ? reinterpret_cast<int*>(prep_smem + (size_t)nslot * 16) : tlist + (size_t)blockIdx.x * nslot;
+    if (threadIdx.x == 0) { node[0] = make_int2(0, m); sh_nleaf = 0; }
+    __syncthreads();
+    for (int l = 0; l < depth; ++l) {
+        const int first = (1 << l) - 1;
+        for (int t = threadIdx.x; t < (1 << l); t += kPrepThreads) {
+            const int2 nd = node[first + t];
+            int2 lc = make_int2(0, -1), rc = make_int2(0, -1);
+            if (nd.y > 128) {
+                int n2 = nd.y / 2;
+                n2 -= n2 % 8;
+                lc = make_int2(nd.x, n2);
+                rc = make_int2(nd.x + n2, nd.y - n2);
             }
-            int n2 = nn / 2;
-            n2 -= n2 % 8;
-            if (st_state[sp] == 0) {                   // descend left
-                st_state[sp] = 1;
-                ++sp; st_start[sp] = s0; st_n[sp] = n2; st_state[sp] = 0;
-            } else if (st_state[sp] == 1) {            // left done, descend right
-                st_left[sp] = ret;
-                st_state[sp] = 2;
-                ++sp; st_start[sp] = s0 + n2; st_n[sp] = nn - n2; st_state[sp] = 0;
-            } else {                                   // both done: res[left] += res[right]
-                cb[ncomb++] = make_int2(st_left[sp], ret);
-                ret = st_left[sp];
-                --sp;
-            }
+            node[2 * (first + t) + 1] = lc;
+            node[2 * (first + t) + 2] = rc;
         }
-        sh_nleaf = nleaf; sh_ncomb = ncomb;
+        __syncthreads();
+    }
+    for (int k = threadIdx.x; k < nslot - 1; k += kPrepThreads) {
+        const int ny = node[k].y;
+        if (ny >= 0 && ny <= 128) lst[atomicAdd(&sh_nleaf, 1)] = k;
     }
     __syncthreads();
     const int nleaf = sh_nleaf;
+    // a leaf: 8 lanes hold numpy's r[0..7]; lane 0 folds them and adds the n % 8 trailing values
     for (int t = threadIdx.x; t < nleaf * 8; t += kPrepThreads) {
-        const int2 L = lf[t >> 3];
+        const int k = lst[t >> 3];
+        const int2 L = node[k];
         const int j = t & 7;
         double r = 0.0;
         if (L.y >= 8) {
             r = cp[L.x + j];
             for (int i = 8; i < L.y - (L.y % 8); i += 8) r = __dadd_rn(r, cp[L.x + i + j]);
         }
-        pt[t] = r;
+        const unsigned grp = 0xffu << ((threadIdx.x & 31) & ~7);
+        const int src = (threadIdx.x & 31) & ~7;
+        const double r1 = __shfl_sync(grp, r, src + 1), r2 = __shfl_sync(grp, r, src + 2), r3 = __shfl_sync(grp, r, src + 3);
+        const double r4 = __shfl_sync(grp, r, src + 4), r5 = __shfl_sync(grp, r, src + 5), r6 = __shfl_sync(grp, r, src + 6);
+        const double r7 = __shfl_sync(grp, r, src + 7);
+        if (j == 0) {
+            double v;
+            if (L.y < 8) {
+                v = 0.0;
+                for (int i = 0; i < L.y; ++i) v = __dadd_rn(v, cp[L.x + i]);
+            } else {
+                v = __dadd_rn(__dadd_rn(__dadd_rn(r, r1), __dadd_rn(r2, r3)), __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+                for (int i = L.y - (L.y % 8); i < L.y; ++i) v = __dadd_rn(v, cp[L.x + i]);
+            }
+            val[k] = v;
+        }
     }
     __syncthreads();
-    for (int l = threadIdx.x; l < nleaf; l += kPrepThreads) {
-        const int2 L = lf[l];
-        double r;
-        if (L.y < 8) {
-            r = 0.0;
-            for (int i = 0; i < L.y; ++i) r = __dadd_rn(r, cp[L.x + i]);
-        } else {
-            const double* p = pt + l * 8;
-            r = __dadd_rn(__dadd_rn(__dadd_rn(p[0], p[1]), __dadd_rn(p[2], p[3])), __dadd_rn(__dadd_rn(p[4], p[5]), __dadd_rn(p[6], p[7])));
-            for (int i = L.y - (L.y % 8); i < L.y; ++i) r = __dadd_rn(r, cp[L.x + i]);
+    for (int l = depth - 1; l >= 0; --l) {
+        const int first = (1 << l) - 1;
+        for (int t = threadIdx.x; t < (1 << l); t += kPrepThreads) {
+            const int k = first + t;
+            if (node[k].y > 128) val[k] = __dadd_rn(val[2 * k + 1], val[2 * k + 2]);
         }
-        if (use_smem) res[l] = r; else pt[l * 8] = r;   // only this thread reads the 8 partials of leaf l
+        __syncthreads();
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int ncomb = sh_ncomb;
-        double total;
-        if (use_smem) {
-            for (int k = 0; k < ncomb; ++k) res[cb[k].x] = __dadd_rn(res[cb[k].x], res[cb[k].y]);
-            total = res[0];
-        } else {
-            for (int k = 0; k < ncomb; ++k) pt[cb[k].x * 8] = __dadd_rn(pt[cb[k].x * 8], pt[cb[k].y * 8]);
-            total = pt[0];
-        }
-        ir[d] = __ddiv_rn(m ? total : 0.0, (double)m);     // mean of an empty slice is NaN, as numpy's
-    }
+    if (threadIdx.x == 0) ir[d] = __ddiv_rn(m ? val[0] : 0.0, (double)m);     // mean of an empty slice is NaN, as numpy's
 }
 
 // biases = 1 / w (0 where w is 0 or NaN) -- pyHICCUPS:163-166

@@ -1,7 +1,9 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-nproc
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_golden.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -3
-timeout 300 python scratch/e2e_probe2.py 8
-HP_PACK_THREADS=2 timeout 300 python scratch/e2e_probe2.py 8 | grep -v hiccups
-timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
+B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline"
+S="import json,sys; b=json.loads(sys.stdin.read()); print(b['value'], b['ms_per_step'], 'e2e', b['e2e']['value'], b['e2e']['ms_per_step'])"
+for m in spin yield; do
+echo ${m}16; HP_SYNC=$m $B 2>/dev/null | python -c "$S"
+echo ${m}8; HP_SYNC=$m taskset -c 0-7 $B 2>/dev/null | python -c "$S"
+echo ${m}4; HP_SYNC=$m taskset -c 0-3 $B 2>/dev/null | python -c "$S"
+done
