@@ -34,7 +34,7 @@ LIB_PATH = os.environ.get("HICPEAKS_B200_LIB") or os.path.join(os.path.dirname(o
 # every symbol include/hicpeaks_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "hp_abi_version", "hp_device_count", "hp_ctx_create", "hp_ctx_destroy", "hp_last_error",
-    "hp_band_upload", "hp_band_upload_counts", "hp_upload_bytes", "hp_dump_band", "hp_hiccups_score", "hp_hiccups_fdr", "hp_hiccups", "hp_get_survivors",
+    "hp_band_upload", "hp_band_upload_counts", "hp_upload_bytes", "hp_timer_start", "hp_timer_stop", "hp_dump_band", "hp_hiccups_score", "hp_hiccups_fdr", "hp_hiccups", "hp_get_survivors",
     "hp_hist_bins", "hp_hist_export", "hp_hist_import", "hp_get_gaps", "hp_dump_levels", "hp_dump_plane", "hp_get_chunk_table", "hp_poisson_sf",
     "hp_apa_upload", "hp_apa_windows", "hp_apa_load_windows", "hp_apa_accumulate", "hp_apa_get_windows",
 ]
@@ -115,6 +115,8 @@ def load_library(path: str | None = None):
     lib.hp_band_upload_counts.argtypes = [vp, C.POINTER(CountsDesc)]
     lib.hp_dump_band.argtypes = [vp, i32, vp, i64]
     lib.hp_upload_bytes.argtypes = [vp, C.POINTER(i64)]
+    lib.hp_timer_start.argtypes = [vp]
+    lib.hp_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     lib.hp_hiccups_score.argtypes = [vp, C.POINTER(HiccupsParams), C.POINTER(HiccupsSummary)]
     lib.hp_hiccups_fdr.argtypes = [vp, vp, C.POINTER(HiccupsSummary)]
     lib.hp_hiccups.argtypes = [vp, C.POINTER(HiccupsParams), C.POINTER(HiccupsSummary)]
@@ -259,6 +261,15 @@ class Context:
         v = C.c_int64()
         self._check(self.lib.hp_upload_bytes(self._h, C.byref(v)))
         return v.value
+
+    def timer_start(self):
+        self._check(self.lib.hp_timer_start(self._h))
+
+    def timer_stop(self):
+        """Milliseconds on the device clock since timer_start() (CUDA events on this context's stream)."""
+        ms = C.c_float()
+        self._check(self.lib.hp_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
 
     def dump_band(self, what):
         shape = {0: (self.num,), 1: (self.n,), 2: (self.num, self.n)}[what]

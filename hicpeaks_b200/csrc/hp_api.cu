@@ -35,6 +35,7 @@ struct hp_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};
     cudaEvent_t ev_sync = nullptr;    // blocking-sync event (stream_sync)
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;      // hp_timer_start / hp_timer_stop
     std::string err;
     // sweep program + chunk tables: pinned host mirror and the device copy the kernels read
     Tables* h_tab = nullptr;
@@ -272,6 +273,8 @@ extern "C" void hp_ctx_destroy(hp_ctx* ctx) {
     if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
+    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -334,7 +337,9 @@ class PackPool {
         std::condition_variable cv;
     };
     PackPool() {
-        unsigned n = std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+        unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) hw = std::max(2u, hw / (unsigned)std::max(1, atoi(e)));   // ranks share the box
+        unsigned n = std::min<unsigned>(16u, hw);
         if (const char* e = getenv("HP_PACK_THREADS")) n = (unsigned)std::max(1, atoi(e));
         for (unsigned t = 0; t + 1 < n; ++t) workers_.emplace_back([this] { work(); }), workers_.back().detach();
         pthread_atfork(nullptr, nullptr, [] { forked_ = true; });      // a forked child has no workers: pack inline
@@ -463,6 +468,26 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
     ctx->n = n; ctx->num = num; ctx->bal_first = bf; ctx->pitch = pitch; ctx->plane = plane;
     ctx->h2d_bytes = (int64_t)(plane * 12 + (size_t)num * 8 + (size_t)n * 16);
     ctx->have_band = true;
+    return HP_OK;
+}
+
+// Device-clock stopwatch on the context's stream: a CUDA event now, a second one at stop, elapsed time between them.
+// bench.py brackets a whole step with it (every context of the step has been synchronised before stop is called), so
+// the step is timed on the device, not by the host clock.
+extern "C" int hp_timer_start(hp_ctx* ctx) {
+    if (!ctx) return fail(ctx, HP_ERR_INVALID, "NULL ctx");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->ev_t0) { CK(cudaEventCreate(&ctx->ev_t0)); CK(cudaEventCreate(&ctx->ev_t1)); }
+    CK(cudaEventRecord(ctx->ev_t0, ctx->stream));
+    return HP_OK;
+}
+extern "C" int hp_timer_stop(hp_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return fail(ctx, HP_ERR_INVALID, "NULL argument");
+    if (!ctx->ev_t0) return fail(ctx, HP_ERR_STATE, "hp_timer_start must come first");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev_t1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev_t1));
+    CK(cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1));
     return HP_OK;
 }
 

@@ -99,6 +99,11 @@ int hp_dump_band(hp_ctx* ctx, int32_t what, double* out, int64_t capacity);
  * PCIe (the device widens it again), so this is usually ~1 byte per band pixel.  Measurement aid (bench.py). */
 int hp_upload_bytes(hp_ctx* ctx, int64_t* bytes);
 
+/* Device-clock stopwatch (CUDA events on the context's stream).  hp_timer_stop returns the milliseconds since
+ * hp_timer_start once the stream has drained.  Measurement aid (bench.py times its steps with it). */
+int hp_timer_start(hp_ctx* ctx);
+int hp_timer_stop(hp_ctx* ctx, float* ms);
+
 /* ---- HiCCUPS scoring: callers.py:98-287 ------------------------------------------------------ */
 typedef struct hp_hiccups_params {
     int32_t npw;                 /* number of (pw, ww) pairs                                   */

@@ -18,7 +18,7 @@ def big():
     return synth_chromosome(N, BAND, 5, maxww=10, seed=17)
 
 
-def _run(ctx, inp, pw, ww, generic=False, counts=False, sig=0.1):
+def _run(ctx, inp, pw, ww, generic=False, counts=False, sig=0.1, band=None):
     Dg = [np.ascontiguousarray(d, dtype=np.int32) for d in inp["Diags"]]
     if counts:
         ctx.upload_counts(inp["n"], inp["num"], min(ww), Dg, inp["weights"])
@@ -26,7 +26,7 @@ def _run(ctx, inp, pw, ww, generic=False, counts=False, sig=0.1):
         cD = [np.ascontiguousarray(c, dtype=np.float64) for c in inp["cDiags"]]
         ir = np.array([inp["IR"][d] for d in range(inp["min_ww"], inp["num"])])
         ctx.upload(inp["n"], inp["num"], inp["min_ww"], Dg, cD, ir, inp["biases"], inp["biases"])
-    P = ctx.make_params(pw, ww, 10, sig, BAND, 16, generic_kernel=generic)
+    P = ctx.make_params(pw, ww, 10, sig, band or BAND, 16, generic_kernel=generic)
     S = ctx.hiccups(P)
     sv = ctx.survivors()
     sv = sv[np.lexsort((sv["pair"], sv["c"], sv["r"]))]
@@ -65,4 +65,30 @@ def test_union_program_kernels_agree_at_scale():
         a = _run(c1, inp, [1, 2, 4], [3, 5, 7])
         b = _run(c2, inp, [1, 2, 4], [3, 5, 7], generic=True)
         assert a[0].spec_kernel == 1 and b[0].spec_kernel == 0
+        _same(a, b)
+
+
+def test_cfg4_shape_wide_band_p4w7():
+    """BASELINE configs[3] shape: 5 kb bins, 10 Mb band (num = 2011 stored diagonals), (p, w) = (4, 7); a chr21-sized
+    chromosome.  Both kernels, both input boundaries."""
+    n, band = 9342, 2000
+    inp = synth_chromosome(n, band, 7, maxww=10, seed=3)
+    with _capi.Context(0) as c1, _capi.Context(0) as c2:
+        a = _run(c1, inp, [4], [7], band=band)
+        b = _run(c2, inp, [4], [7], generic=True, band=band)
+        assert a[0].spec_kernel == 1 and b[0].spec_kernel == 0
+        assert a[0].band_pixels == band_pixels(n, 7, band)
+        _same(a, b)
+        _same(a, _run(c2, inp, [4], [7], counts=True, band=band))
+
+
+def test_cfg3_shape_chr1_union_worker_input():
+    """BASELINE configs[2] shape: hg38 chr1 @10 kb (24 896 bins), 5 Mb band, union (1,3)/(2,5)/(4,7), through the
+    worker-level upload (narrowed counts, band / IR / biases derived on the GPU) against the operator-level one."""
+    n = 24896
+    inp = synth_chromosome(n, BAND, 3, maxww=10, seed=29)
+    with _capi.Context(0) as c1, _capi.Context(0) as c2:
+        a = _run(c1, inp, [1, 2, 4], [3, 5, 7], counts=True)
+        b = _run(c2, inp, [1, 2, 4], [3, 5, 7])
+        assert a[0].spec_kernel == 1 and a[0].band_pixels == band_pixels(n, 3, BAND)
         _same(a, b)
