@@ -56,6 +56,9 @@ struct hp_ctx {
     double* d_tmp = nullptr;          // plain-layout landing zone of the uploads (re-laid out on the device)
     void* h_stage = nullptr;          // pinned staging for uploads
     size_t cap_stage = 0;
+    unsigned char* h_res = nullptr;   // pinned, 8 KB: landing zone of the small per-call readbacks (level histogram, counters).
+                                      // A D2H copy into pageable memory blocks inside the copy call; into pinned memory it
+                                      // is queued and the thread waits in stream_sync, the way HP_SYNC says
     void* h_out = nullptr;            // pinned staging for result downloads (a D2H copy into pageable memory runs at ~3 GB/s)
     size_t cap_out = 0;
     bool have_band = false;
@@ -237,6 +240,7 @@ extern "C" int hp_ctx_create(int device, int max_chunks, const double* edges, hp
     bool ok = cudaMalloc(&ctx->d_ptab, tb * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&ctx->d_tab, sizeof(Tables)) == cudaSuccess &&
               cudaHostAlloc(&ctx->h_tab, sizeof(Tables), cudaHostAllocDefault) == cudaSuccess &&
+              cudaHostAlloc((void**)&ctx->h_res, 8192, cudaHostAllocDefault) == cudaSuccess &&
               cudaMalloc(&ctx->d_lhist, (HP_MAX_STEPS + 2) * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&ctx->d_small, 48 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&ctx->d_cnt, 8 * sizeof(unsigned int)) == cudaSuccess &&
@@ -271,6 +275,8 @@ extern "C" void hp_ctx_destroy(hp_ctx* ctx) {
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
+    if (ctx->h_res) cudaFreeHost(ctx->h_res);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
@@ -783,9 +789,10 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(ctx->ev[1], st));
-    std::vector<unsigned long long> lh(G.nsteps + 1);
-    CK(cudaMemcpyAsync(lh.data(), ctx->d_lhist, lh.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    unsigned long long* hres_lh = (unsigned long long*)ctx->h_res;                 // [HP_MAX_STEPS + 2]
+    CK(cudaMemcpyAsync(hres_lh, ctx->d_lhist, (size_t)(G.nsteps + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(stream_sync(ctx));
+    const std::vector<unsigned long long> lh(hres_lh, hres_lh + G.nsteps + 1);
 
     // ---- replay of the adaptive-width control flow (callers.py:203-232) ------------------------
     unsigned long long total = 0;
@@ -928,9 +935,11 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
         ++launches;
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[3], st));
-        CK(cudaMemcpyAsync(cnt, ctx->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(small, ctx->d_small, sizeof(small), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->h_res + 2048, ctx->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->h_res + 2048 + 64, ctx->d_small, sizeof(small), cudaMemcpyDeviceToHost, st));
         CK(stream_sync(ctx));
+        memcpy(cnt, ctx->h_res + 2048, sizeof(cnt));
+        memcpy(small, ctx->h_res + 2048 + 64, sizeof(small));
         if (cnt[1] == 0) break;
         if (attempt == 1) return fail(ctx, HP_ERR_CAPACITY, "candidate buffer overflow");
         want = (size_t)total * P.npw + 1024;      // every pixel can be a candidate at most once per pair
@@ -1003,10 +1012,12 @@ extern "C" int hp_hiccups_fdr(hp_ctx* ctx, const int32_t* numbin_override, hp_hi
         k_filter<<<(ctx->ncand + 255) / 256, 256, 0, st>>>(A);
         ++launches;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(cnt, ctx->d_cnt + 4, sizeof(cnt), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(nrej, ctx->d_small + 32, sizeof(nrej), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->h_res + 4096, ctx->d_cnt + 4, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->h_res + 4096 + 64, ctx->d_small + 32, sizeof(nrej), cudaMemcpyDeviceToHost, st));
         if (attempt == 0) CK(cudaEventRecord(ctx->ev[5], st));
         CK(stream_sync(ctx));
+        memcpy(cnt, ctx->h_res + 4096, sizeof(cnt));
+        memcpy(nrej, ctx->h_res + 4096 + 64, sizeof(nrej));
         if (cnt[1] == 0) break;
         if (attempt == 1) return fail(ctx, HP_ERR_CAPACITY, "survivor buffer overflow");
         want = (size_t)ctx->ncand + 16;
