@@ -51,13 +51,20 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
+
+    nvidia-smi takes a few hundred ms to start and holds driver locks while it does: it is started BEFORE the warm-up
+    and the timed region only begins once its first sample has arrived (the warm-up keeps running meanwhile), so that
+    its start-up never lands inside a timed region that may be only tens of ms long.  Samples are selected by arrival
+    time: those inside [begin, end], or -- when the region is shorter than the 100 ms period -- the nearest one on each
+    side (same workload, the warm-up and the e2e legs run the same kernels)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu):
         self.gpu, self.proc, self.lines = gpu, None, []
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
@@ -70,16 +77,33 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line)
+            self.lines.append((time.perf_counter(), line))
+
+    def ready(self):
+        return self.proc is None or len(self.lines) > 0
+
+    def begin(self):
+        self.t_begin = time.perf_counter()
+
+    def end(self):
+        self.t_end = time.perf_counter()
+
+    def closed(self):
+        """A sample has arrived after the end of the region (the caller keeps the GPU under load until then)."""
+        return self.proc is None or (self.lines and self.lines[-1][0] > self.t_end)
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
+        inside = [ln for t, ln in self.lines if self.t_begin <= t <= self.t_end]
+        if not inside:
+            before = [ln for t, ln in self.lines if t < self.t_begin][-1:]
+            after = [ln for t, ln in self.lines if t > self.t_end][:1]
+            inside = before + after
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -237,12 +261,24 @@ def main():
         barrier()
         return res, ms_dev * 1e-3, time.perf_counter() - t0
 
+    # nvidia-smi polls the driver: one sampler per box (rank 0, its own GPU); see ClockSampler for the ordering
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for _ in range(args.warmup):
         resident_step()
-    sampler = ClockSampler(local)
-    sampler.start()
+    t_w = time.perf_counter()
+    while sampler and not sampler.ready() and time.perf_counter() - t_w < 5.0:
+        resident_step()                                         # keep the GPU under load until the sampler is up
+    if sampler:
+        sampler.begin()
     accs, dt, dt_host = timed(resident_step, args.steps)
-    clocks = sampler.stop()
+    if sampler:
+        sampler.end()
+        t_w = time.perf_counter()
+        while not sampler.closed() and time.perf_counter() - t_w < 0.5:
+            resident_step()                                     # still under load when the closing sample is taken
+    clocks = sampler.stop() if sampler else None
 
     # roofline leg: the same steps one chromosome at a time, so that the CUDA-event time of a score kernel is
     # that kernel alone (in the threaded region above kernels of different streams overlap)
@@ -265,6 +301,9 @@ def main():
     if dist is not None:
         import torch
         t = torch.tensor([dt, dt_e2e, dt_e2e_op], dtype=torch.float64, device="cuda")
+        per_rank = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(per_rank, t)
+        rank_ms = [[round(1e3 * float(v) / args.steps, 4) for v in pr.tolist()[:2]] for pr in per_rank]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt, dt_e2e, dt_e2e_op = t.tolist()
         c = torch.tensor([px_step], dtype=torch.float64, device="cuda")
@@ -272,6 +311,7 @@ def main():
         px_total = c.item()
     else:
         px_total = px_step
+        rank_ms = None
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -321,6 +361,8 @@ def main():
         "clocks": clocks,
         "survivors_per_step": accs[0]["surv"],
     }
+    if rank_ms is not None:
+        out["ms_per_step_by_rank"] = {"resident_e2e": rank_ms}          # the reported times are the max over ranks
     if world == 1 and not args.no_cpu_baseline:
         n_sample = 6000
         px, sec = oracle_rate(n_sample, 4242)
