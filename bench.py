@@ -7,7 +7,8 @@ Workload (`config.workload`): BASELINE.json configs[1] -- synthetic chromosome o
 5 Mb band (num = 511 stored diagonals), (p, w) = (2, 5), maxww 10, min_local_reads 16, sig 0.1,
 generator of SURVEY.md 8(d).  One step = one pass of the whole hot path (level kernel, frozen_w
 replay, score kernel, BH kernel, survivor filter) over a batch of `--chroms` (default 8) such chromosomes that
-are resident in HBM (batch > L2, so every step streams from HBM).  For N > 1 (torchrun, one rank
+are resident in HBM (batch > L2, so every step streams from HBM).  Each chromosome has its own host thread,
+context and stream and goes from one pass straight to the next (no host barrier between steps), as in a genome run.  For N > 1 (torchrun, one rank
 per GPU) every rank owns its own batch (weak scaling, chromosomes are independent: no collective
 on the data path); value = all pixels / max-over-ranks time.
 
@@ -227,11 +228,16 @@ def main():
     from concurrent.futures import ThreadPoolExecutor
     pool = ThreadPoolExecutor(len(ctxs))
 
-    def resident_step():
+    # One step = every chromosome of the batch through the hot path once.  The K timed steps run as they do in a genome
+    # run: each chromosome's host thread goes straight on to its next pass, so passes of different chromosomes overlap
+    # (levels of one under the score kernel of another) and there is no host barrier between steps -- only the
+    # device-synchronised points at both ends of the K steps.
+    def resident_steps(steps=1):
         acc = dict(px=0, launches=0, ms_levels=0.0, ms_score=0.0, ms_fdr=0.0, surv=0)
-        for S in pool.map(lambda c: c.hiccups(P), ctxs):     # each call returns after its stream is synchronised
-            acc["px"] += S.band_pixels; acc["launches"] += S.launches; acc["surv"] += S.n_survivors
-            acc["ms_levels"] += S.ms_levels; acc["ms_score"] += S.ms_score; acc["ms_fdr"] += S.ms_fdr
+        for per_ctx in pool.map(lambda c: [c.hiccups(P) for _ in range(steps)], ctxs):   # every call ends stream-synchronised
+            for S in per_ctx:
+                acc["px"] += S.band_pixels; acc["launches"] += S.launches; acc["surv"] += S.n_survivors
+                acc["ms_levels"] += S.ms_levels; acc["ms_score"] += S.ms_score; acc["ms_fdr"] += S.ms_fdr
         return acc
 
     def e2e_one(job, counts):
@@ -245,18 +251,18 @@ def main():
         g = ctx.gaps()
         return S.band_pixels, sv.nbytes + g.size * 4
 
-    def e2e_step(counts=True):
-        res = list(pool.map(lambda j: e2e_one(j, counts), zip(ctxs, batch, arrays)))
-        return sum(r[0] for r in res), sum(r[1] for r in res)
+    def e2e_steps(counts=True, steps=1):
+        res = list(pool.map(lambda j: [e2e_one(j, counts) for _ in range(steps)], zip(ctxs, batch, arrays)))
+        return sum(r[0] for per in res for r in per), sum(r[1] for per in res for r in per)
 
-    def timed(fn, steps):
-        """K steps between two device-synchronised points: milliseconds on the device clock (CUDA events on the first
-        context's stream: recorded before the first launch and after every context's last synchronise) and on the
-        host clock (cross-check; the two differ by the launch latency of the first kernel)."""
+    def timed(fn):
+        """fn runs the K steps between two device-synchronised points: seconds on the device clock (CUDA events on the
+        first context's stream: recorded before the first launch and after every context's last synchronise) and on
+        the host clock (cross-check; the two differ by the launch latency of the first kernel)."""
         barrier()
         t0 = time.perf_counter()
         ctxs[0].timer_start()
-        res = [fn() for _ in range(steps)]
+        res = fn()
         ms_dev = ctxs[0].timer_stop()
         barrier()
         return res, ms_dev * 1e-3, time.perf_counter() - t0
@@ -265,19 +271,18 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    for _ in range(args.warmup):
-        resident_step()
+    resident_steps(args.warmup)
     t_w = time.perf_counter()
     while sampler and not sampler.ready() and time.perf_counter() - t_w < 5.0:
-        resident_step()                                         # keep the GPU under load until the sampler is up
+        resident_steps()                                        # keep the GPU under load until the sampler is up
     if sampler:
         sampler.begin()
-    accs, dt, dt_host = timed(resident_step, args.steps)
+    acc, dt, dt_host = timed(lambda: resident_steps(args.steps))
     if sampler:
         sampler.end()
         t_w = time.perf_counter()
         while not sampler.closed() and time.perf_counter() - t_w < 0.5:
-            resident_step()                                     # still under load when the closing sample is taken
+            resident_steps()                                    # still under load when the closing sample is taken
     clocks = sampler.stop() if sampler else None
 
     # roofline leg: the same steps one chromosome at a time, so that the CUDA-event time of a score kernel is
@@ -288,16 +293,14 @@ def main():
             S = c.hiccups(P)
             seq.append((S.ms_levels, S.ms_score, S.ms_fdr))
 
-    for _ in range(2):
-        e2e_step(False)
-    _, dt_e2e_op, _ = timed(lambda: e2e_step(False), args.steps)
-    for _ in range(2):
-        e2e_step(True)
-    e2e_res, dt_e2e, dt_e2e_host = timed(lambda: e2e_step(True), args.steps)
+    e2e_steps(False, 2)
+    _, dt_e2e_op, _ = timed(lambda: e2e_steps(False, args.steps))
+    e2e_steps(True, 2)
+    e2e_res, dt_e2e, dt_e2e_host = timed(lambda: e2e_steps(True, args.steps))
     h2d_counts = sum(c.upload_bytes() for c in ctxs)          # counted by the library from the copies it issued
     host_counts = sum(sum(a.nbytes for a in Dg) + inp["weights"].nbytes for inp, (Dg, cD, ir) in zip(batch, arrays))
 
-    px_step = accs[0]["px"]
+    px_step = acc["px"] // args.steps
     if dist is not None:
         import torch
         t = torch.tensor([dt, dt_e2e, dt_e2e_op], dtype=torch.float64, device="cuda")
@@ -349,7 +352,7 @@ def main():
                      "alg_bytes_per_pixel": ALG_BYTES_PER_PIXEL, "pixels_per_launch": px_launch,
                      "avg_launch_ms": ms_score},
         "e2e": {"value": e2e_value, "unit": "pixels/s", "h2d_bytes_per_step": h2d_counts * world,
-                "d2h_bytes_per_step": int(np.mean([r[1] for r in e2e_res])) * world,
+                "d2h_bytes_per_step": int(e2e_res[1] // args.steps) * world,
                 "ms_per_step": 1e3 * dt_e2e / args.steps, "host_input_bytes_per_step": host_counts * world,
                 "boundary": "worker level: callers.hiccups_from_counts / hp_band_upload_counts (raw int32 diagonals + bin weights "
                             "from pageable host arrays; the library narrows each diagonal to u8/u16/i32 into pinned staging, "
@@ -357,9 +360,9 @@ def main():
         "e2e_operator": {"value": px_total * args.steps / dt_e2e_op, "unit": "pixels/s", "h2d_bytes_per_step": h2d * world,
                          "ms_per_step": 1e3 * dt_e2e_op / args.steps,
                          "boundary": "operator level: callers.hiccups / hp_band_upload (Diags + cDiags + IR + biases, 12 B/pixel)"},
-        "gpu_launches": int(sum(a["launches"] for a in accs)),
+        "gpu_launches": int(acc["launches"]),
         "clocks": clocks,
-        "survivors_per_step": accs[0]["surv"],
+        "survivors_per_step": acc["surv"] // args.steps,
     }
     if rank_ms is not None:
         out["ms_per_step_by_rank"] = {"resident_e2e": rank_ms}          # the reported times are the max over ranks
