@@ -639,51 +639,62 @@ struct FilterArgs {
     int bhfdr;
 };
 
+// The counters are bumped once per warp (ballot + popc), not once per record: tens of thousands of atomics on one
+// address serialise in L2 and used to be most of this kernel's time.
 __global__ void k_filter(FilterArgs A) {
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= A.ncand) return;
+    const bool live = idx < A.ncand;
+    const unsigned lane = threadIdx.x & 31u;
     const Chunks& c_chunks = A.tab->chunks;
-    const Cand c = A.cand[idx];
+    Cand c{};
+    if (live) c = A.cand[idx];
     hp_survivor sv;
     sv.r = c.r; sv.c = c.r + c.d; sv.pair = c.pair; sv.flags = c.flags;
     sv.obs = (double)c.obs;
     sv.e[0] = c.e_k; sv.e[1] = c.e_y;
-    bool any = false;
+    bool rej[2] = {false, false};
     if (A.bhfdr) {
         // per-pixel Poisson rate (callers.py:536-540); BH over the whole chromosome is finished by the caller on the
         // pixels with p <= sig (every rejected pixel has p <= sig), q is filled in there
-        const double p = poisson_sf((double)c.obs, c.e_k);
+        const double p = live ? poisson_sf((double)c.obs, c.e_k) : 1.0;
         sv.p[0] = p; sv.q[0] = 1.0; sv.p[1] = 1.0; sv.q[1] = 1.0;
-        if (p <= A.sig * (1.0 + 1e-9)) {
-            sv.flags |= HP_SF_REJECT_K;
-            atomicAdd(&A.nreject[c.pair * 2], 1ull);
-            any = true;
-        }
+        rej[0] = live && p <= A.sig * (1.0 + 1e-9);
     } else {
 #pragma unroll
+        for (int fl = 0; fl < 2; ++fl) {
+            const int lf = c.pair * 2 + fl;
+            const int ci = fl ? c.chunk_y : c.chunk_k;
+            double p = 1.0, q = 1.0;
+            if (live && ci >= 1 && ci <= A.numbin[lf]) {
+                const int w = c_chunks.hw[ci];
+                const int kb = c.obs < w - 1 ? c.obs : w - 1;
+                p = A.ptab[c_chunks.hoff[ci] + kb];
+                q = A.qtab[(size_t)lf * c_chunks.total_bins + c_chunks.hoff[ci] + kb];
+            }
+            sv.p[fl] = p; sv.q[fl] = q;
+            const bool valid = (c.flags & (fl ? HP_SF_VALID_Y : HP_SF_VALID_K)) != 0;
+            rej[fl] = live && valid && q <= A.sig;
+        }
+    }
+    if (rej[0]) sv.flags |= HP_SF_REJECT_K;
+    if (rej[1]) sv.flags |= HP_SF_REJECT_Y;
+    // rejected counts per (pair, background): lanes of a warp that share a pair add once
+#pragma unroll
     for (int fl = 0; fl < 2; ++fl) {
-        const int lf = c.pair * 2 + fl;
-        const int ci = fl ? c.chunk_y : c.chunk_k;
-        double p = 1.0, q = 1.0;
-        if (ci >= 1 && ci <= A.numbin[lf]) {
-            const int w = c_chunks.hw[ci];
-            const int kb = c.obs < w - 1 ? c.obs : w - 1;
-            p = A.ptab[c_chunks.hoff[ci] + kb];
-            q = A.qtab[(size_t)lf * c_chunks.total_bins + c_chunks.hoff[ci] + kb];
-        }
-        sv.p[fl] = p; sv.q[fl] = q;
-        const bool valid = (c.flags & (fl ? HP_SF_VALID_Y : HP_SF_VALID_K)) != 0;
-        if (valid && q <= A.sig) {
-            sv.flags |= (fl ? HP_SF_REJECT_Y : HP_SF_REJECT_K);
-            atomicAdd(&A.nreject[lf], 1ull);
-            any = true;
-        }
+        const unsigned peers = __match_any_sync(0xffffffffu, rej[fl] ? (int)c.pair : -1);
+        if (rej[fl] && lane == (unsigned)__ffs(peers) - 1u) atomicAdd(&A.nreject[c.pair * 2 + fl], (unsigned long long)__popc(peers));
     }
-    }
-    if (any) {
-        sv.ice = A.bal[qidx(c.d, c.r, A.pitch)];
-        const unsigned g = atomicAdd(&A.out_count[0], 1u);
-        if (g < A.out_cap) A.out[g] = sv; else atomicAdd(&A.out_count[1], 1u);
+    const bool any = rej[0] || rej[1];
+    const unsigned many = __ballot_sync(0xffffffffu, any);
+    if (many) {
+        unsigned base = 0;
+        if (lane == (unsigned)__ffs(many) - 1u) base = atomicAdd(&A.out_count[0], (unsigned)__popc(many));
+        base = __shfl_sync(0xffffffffu, base, __ffs(many) - 1);
+        if (any) {
+            sv.ice = A.bal[qidx(c.d, c.r, A.pitch)];
+            const unsigned g = base + __popc(many & ((1u << lane) - 1u));
+            if (g < A.out_cap) A.out[g] = sv; else atomicAdd(&A.out_count[1], 1u);
+        }
     }
 }
 
