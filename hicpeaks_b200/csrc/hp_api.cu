@@ -69,6 +69,8 @@ struct hp_ctx {
     std::vector<unsigned char> opy, opr;
     std::vector<unsigned short> ropi;
     bool scored = false, fdr_done = false;
+    bool kcand_valid = false, kcand_bhfdr = false;     // candidate thresholds cached per (sig, mode)
+    double kcand_sig = 0.0;
     hp_hiccups_summary sum{};
     int dlo = 0, dhi = -1;
     unsigned long long* d_lhist = nullptr;      // [HP_MAX_STEPS + 2]
@@ -870,16 +872,26 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     {
         // candidate thresholds for this sig (host copy of the universal Poisson table)
         Chunks& C = ctx->chunks;
-        const double lim = P.sig * (1.0 + 1e-9) + 1e-300;
-        for (int i = 1; i <= C.maxchunk; ++i) {
-            const double* p = ctx->h_ptab.data() + C.hoff[i];
-            int k = 0;
-            while (k < C.hw[i] && !(p[k] <= lim)) ++k;
-            C.kcand[i] = k;
-        }
-        if (bhfdr) {   // per-pixel rates: the tail at the LOWER edge of the chunk bounds p from below
-            for (int i = C.maxchunk; i >= 2; --i) C.kcand[i] = C.kcand[i - 1];
-            C.kcand[1] = 0;
+        // kcand[i] = first count k with p(i, k) <= sig.  The table has ~6e5 entries and a linear scan per call reads
+        // most of it (0.4 ms of host time per chromosome): the thresholds are kept per (sig, mode) and found by
+        // bisection (the tail is decreasing in k), with a walk back over ties / rounding wiggles.
+        if (!(ctx->kcand_valid && ctx->kcand_sig == P.sig && ctx->kcand_bhfdr == bhfdr)) {
+            const double lim = P.sig * (1.0 + 1e-9) + 1e-300;
+            for (int i = 1; i <= C.maxchunk; ++i) {
+                const double* p = ctx->h_ptab.data() + C.hoff[i];
+                int lo = 0, hi = C.hw[i];                          // answer in [lo, hi]; p[hw - 1] == 0 <= lim
+                while (lo < hi) {
+                    const int mid = (lo + hi) / 2;
+                    if (p[mid] <= lim) hi = mid; else lo = mid + 1;
+                }
+                while (lo > 0 && p[lo - 1] <= lim) --lo;
+                C.kcand[i] = lo;
+            }
+            if (bhfdr) {   // per-pixel rates: the tail at the LOWER edge of the chunk bounds p from below
+                for (int i = C.maxchunk; i >= 2; --i) C.kcand[i] = C.kcand[i - 1];
+                C.kcand[1] = 0;
+            }
+            ctx->kcand_valid = true; ctx->kcand_sig = P.sig; ctx->kcand_bhfdr = bhfdr;
         }
         HT.prog = G;                       // now with the executed steps and the resolve tables
         HT.chunks = C;
