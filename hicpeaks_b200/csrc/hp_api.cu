@@ -522,7 +522,6 @@ extern "C" int hp_band_upload_counts(hp_ctx* ctx, const hp_counts_desc* b) {
     const size_t plane = (size_t)num * pitch;
     cudaStream_t st = ctx->stream;
     int* hraw = (int*)((char*)ctx->h_stage + plane * 8);
-    int* traw = (int*)((char*)ctx->d_tmp + plane * 8);
     double* comp = ctx->d_tmp;                        // [num - bf][pitch] compaction scratch (the unused balanced landing zone)
     CK(ensure(&ctx->d_w, &ctx->cap_w, (size_t)n + 64));
     int depth = 0;                                     // levels of numpy's pairwise recursion below the root (hp_prep.cuh)
@@ -536,11 +535,11 @@ extern "C" int hp_band_upload_counts(hp_ctx* ctx, const hp_counts_desc* b) {
     int* tlist = (int*)(tval + (size_t)nb * nslot);
     CK(cudaMemcpyAsync(ctx->d_w, b->weights, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     // raw counts: worker threads narrow each diagonal to u8 / u16 / i32 (hp_hostpack.cpp) straight into the pinned
-    // staging buffer, chunk by chunk, while the copy engine uploads the chunks already done; the device widens
-    // them back into the plain int32 landing zone (k_unpack_counts).  A chunk owns the byte range its diagonals
+    // staging buffer, chunk by chunk, while the copy engine uploads the chunks already done; k_prep_band reads
+    // the narrowed form directly.  A chunk owns the byte range its diagonals
     // would take as int32, so chunks are packed independently and only the bytes used are sent.
     unsigned char* hpk = (unsigned char*)hraw;                       // pinned, plane * 4 bytes
-    unsigned char* dpk = (unsigned char*)ctx->d_tmp;                 // device: first plane * 4 bytes of the landing zone
+    unsigned char* dpk = (unsigned char*)ctx->d_tmp + plane * 8;     // device: the int32 part of the landing zone (comp owns the first plane * 8 bytes)
     PackedDiag* htab = (PackedDiag*)((char*)ctx->h_stage + plane * 12 + (size_t)num * 8);
     CK(ensure(&ctx->d_pk, &ctx->cap_pk, (size_t)num));
     const int per = std::max(1, (int)((size_t)(5u << 19) / ((size_t)pitch * 4)));      // ~2.5 MB of int32 per chunk
@@ -570,19 +569,17 @@ extern "C" int hp_band_upload_counts(hp_ctx* ctx, const hp_counts_desc* b) {
     if (cerr != cudaSuccess) return fail(ctx, HP_ERR_CUDA, std::string("band upload: ") + cudaGetErrorString(cerr));
     CK(cudaMemcpyAsync(ctx->d_pk, htab, (size_t)num * sizeof(PackedDiag), cudaMemcpyHostToDevice, st));
     ctx->h2d_bytes = (int64_t)(sent + (size_t)num * sizeof(PackedDiag) + (size_t)n * 8);
-    k_unpack_counts<<<dim3((pitch / 4 + 255) / 256, num), 256, 0, st>>>(dpk, ctx->d_pk, traw, pitch);
-    CK(cudaGetLastError());
     CK(cudaMemsetAsync(ctx->d_rownz, 0, (size_t)n * sizeof(unsigned int), st));
     CK(cudaMemsetAsync(ctx->d_ir, 0, (size_t)num * 8, st));
-    k_relayout<int><<<dim3((pitch + 255) / 256, num), 256, 0, st>>>(traw, ctx->d_raw, nullptr, pitch, num);
-    CK(cudaGetLastError());
     if (bf > 0) {
         const size_t cnt = (size_t)bf * pitch;
         k_zero_planes<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(ctx->d_bal, cnt);
+        k_unpack_quad<<<dim3((pitch / 4 + 255) / 256, bf), 256, 0, st>>>(dpk, ctx->d_pk, ctx->d_raw, pitch);
+        CK(cudaGetLastError());
     }
     const int prep_smem = nslot * 20 <= 40 * 1024 ? nslot * 20 : 0;
-    k_prep_band<<<nb, kPrepThreads, prep_smem, st>>>(traw, ctx->d_w, (int)n, num, pitch, bf, ctx->d_bal, ctx->d_rownz, ctx->d_ir, comp, leaf,
-                                                   tval, tlist, depth, nslot, prep_smem ? 1 : 0);
+    k_prep_band<<<nb, kPrepThreads, prep_smem, st>>>(dpk, ctx->d_pk, ctx->d_w, (int)n, num, pitch, bf, ctx->d_raw, ctx->d_bal, ctx->d_rownz,
+                                                   ctx->d_ir, comp, leaf, tval, tlist, depth, nslot, prep_smem ? 1 : 0);
     CK(cudaGetLastError());
     k_prep_bias<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_w, ctx->d_b1, ctx->d_b2, (int)n);
     CK(cudaGetLastError());

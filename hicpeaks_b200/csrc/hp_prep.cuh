@@ -16,20 +16,16 @@ namespace hp {
 constexpr int kPrepThreads = 256;
 
 // Count upload: the host narrows every diagonal to the smallest of u8 / u16 / i32 that holds its values
-// (hp_hostpack.cpp) so that ~1 byte per band pixel crosses PCIe; this widens them back into the plain
-// [num][pitch] int32 landing zone (zero tails) that k_relayout / k_prep_band read.  4 bins per thread.
+// (hp_hostpack.cpp) so that ~1 byte per band pixel crosses PCIe; k_prep_band / k_unpack_quad read that packed
+// form directly (4 bins per thread and load) and write the quad-interleaved planes.
 struct PackedDiag {
     unsigned long long off;      // byte offset of the diagonal in the packed buffer (16-byte aligned)
     unsigned int esize;          // 1, 2 or 4
     unsigned int len;            // n - d
 };
 
-__global__ void __launch_bounds__(256) k_unpack_counts(const unsigned char* __restrict__ packed, const PackedDiag* __restrict__ tab,
-                                                       int* __restrict__ raw_plain, int pitch) {
-    const int d = blockIdx.y;
-    const int rb = (blockIdx.x * 256 + threadIdx.x) * 4;
-    if (rb >= pitch) return;
-    const PackedDiag t = tab[d];
+// four consecutive counts of a narrowed diagonal, starting at bin rb (a multiple of 4); bins >= len read as 0
+__device__ __forceinline__ int4 packed_quad(const unsigned char* __restrict__ packed, const PackedDiag& t, int rb) {
     int4 v = make_int4(0, 0, 0, 0);
     if (rb < (int)t.len) {
         const unsigned char* src = packed + t.off;
@@ -46,75 +42,106 @@ __global__ void __launch_bounds__(256) k_unpack_counts(const unsigned char* __re
         if (rb + 2 >= (int)t.len) v.z = 0;
         if (rb + 3 >= (int)t.len) v.w = 0;
     }
-    *reinterpret_cast<int4*>(raw_plain + (size_t)d * pitch + rb) = v;
+    return v;
 }
 
-// one CTA per diagonal d in [bal_first, num).  comp: scratch [num][pitch] doubles.  The summation tree has `depth`
-// levels below the root and nslot = 2^(depth + 1) heap slots: in shared memory when it fits (use_smem), otherwise in
-// the scratch arrays tree / tval / tlist, [num][nslot] each.
-__global__ void __launch_bounds__(kPrepThreads) k_prep_band(const int* __restrict__ raw_plain, const double* __restrict__ w, int n, int num,
-                                                            int pitch, int bal_first, double* __restrict__ bal, unsigned int* __restrict__ rownz,
+// raw-count planes below bal_first (no balanced values there): narrowed diagonal -> quad-interleaved int32 plane
+__global__ void __launch_bounds__(256) k_unpack_quad(const unsigned char* __restrict__ packed, const PackedDiag* __restrict__ tab,
+                                                     int* __restrict__ raw, int pitch) {
+    const int d = blockIdx.y;
+    const int rb = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (rb >= pitch) return;
+    const int4 v = packed_quad(packed, tab[d], rb);
+    const size_t q = qidx(d, rb, pitch);                // rb & 3 == 0: the four bins sit at the same slot of the 4 sub-planes
+    const size_t sp = (size_t)(pitch >> 2);
+    raw[q] = v.x; raw[q + sp] = v.y; raw[q + 2 * sp] = v.z; raw[q + 3 * sp] = v.w;
+}
+
+// One CTA per diagonal d in [bal_first, num): reads the narrowed counts, writes the quad-interleaved raw and balanced
+// planes, the row flags, the NaN-compacted balanced values (comp: scratch [num][pitch] doubles) and IR[d].
+// Compaction: rounds of 2 x 1024 bins, 4 consecutive bins per thread and quad; warp scans + double-buffered warp totals
+// give every thread its output offset with one block barrier per round.
+// The summation tree has `depth` levels below the root and nslot = 2^(depth + 1) heap slots: in shared memory when
+// it fits (use_smem), otherwise in the scratch arrays tree / tval / tlist, [num][nslot] each.
+__global__ void __launch_bounds__(kPrepThreads) k_prep_band(const unsigned char* __restrict__ packed, const PackedDiag* __restrict__ tab,
+                                                            const double* __restrict__ w, int n, int num,
+                                                            int pitch, int bal_first, int* __restrict__ raw, double* __restrict__ bal,
+                                                            unsigned int* __restrict__ rownz,
                                                             double* __restrict__ ir, double* __restrict__ comp, int2* __restrict__ tree,
                                                             double* __restrict__ tval, int* __restrict__ tlist, int depth, int nslot,
                                                             int use_smem) {
     extern __shared__ __align__(16) unsigned char prep_smem[];     // use_smem: the summation tree (nodes, values, leaf list)
-    __shared__ int sh_scan[kPrepThreads / 32];
+    constexpr int kWarps = kPrepThreads / 32;
+    constexpr int kU = 2;                               // quads per thread and round: 2 x 1024 bins per round in flight
+    __shared__ int sh_scan[2][kU][kWarps];              // warp totals, double-buffered: one barrier per round
     __shared__ int sh_base, sh_nleaf;
     const int d = bal_first + blockIdx.x;
     const int len = n - d;
-    const int* src = raw_plain + (size_t)d * pitch;
+    const PackedDiag pd = tab[d];
     double* cp = comp + (size_t)blockIdx.x * pitch;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) sh_base = 0;
-    __syncthreads();
-    // ---- balanced values, NaN compaction (order preserved): 4 consecutive bins per thread and round ----------
-    for (int r0 = 0; r0 < pitch; r0 += kPrepThreads * 4) {
-        const int rb = r0 + threadIdx.x * 4;
-        double v[4];
-        bool keep[4];
-        int nk = 0;
-        int4 c4 = make_int4(0, 0, 0, 0);
-        if (rb < pitch) c4 = *reinterpret_cast<const int4*>(src + rb);          // pitch is a multiple of 32
-        const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
+    const size_t sp = (size_t)(pitch >> 2);
+    int base = 0;                                       // kept values before this round (same in every thread)
+    // ---- balanced values, planes, row flags, NaN compaction (order preserved) ----------------------------------
+    for (int r0 = 0, it = 0; r0 < pitch; r0 += kU * kPrepThreads * 4, ++it) {
+        double v[kU][4];
+        int cc[kU][4], nk[kU], inc[kU];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int r = rb + k;
-            const bool in = r < len;
-            v[k] = 0.0;
-            if (in) {                                   // weights loaded whether or not a count is stored: no load waits on another
-                const double p = __dmul_rn(__dmul_rn((double)cc[k], w[r]), w[r + d]);
-                if (cc[k] != 0) v[k] = p;
+        for (int u = 0; u < kU; ++u) {
+            const int rb = r0 + u * kPrepThreads * 4 + threadIdx.x * 4;
+            const int4 c4 = packed_quad(packed, pd, rb);                         // bins >= len read as 0
+            cc[u][0] = c4.x; cc[u][1] = c4.y; cc[u][2] = c4.z; cc[u][3] = c4.w;
+            nk[u] = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = rb + k;
+                v[u][k] = 0.0;
+                if (r < len) {                          // weights loaded whether or not a count is stored: no load waits on another
+                    // balanced value: count * w[r] * w[r + d] where a count is stored, evaluated left to right (:143)
+                    const double p = __dmul_rn(__dmul_rn((double)cc[u][k], w[r]), w[r + d]);
+                    if (cc[u][k] != 0) v[u][k] = p;
+                    nk[u] += (v[u][k] == v[u][k]);
+                }
             }
-            const bool isn = v[k] != v[k];
-            keep[k] = in && !isn;
-            nk += keep[k];
-            if (r < pitch) {
-                const double out = isn ? 0.0 : v[k];
-                bal[qidx(d, r, pitch)] = out;
-                if (out != 0.0) rownz[r] = 1u;
+            int x = nk[u];                              // inclusive scan over the lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += t;
+            }
+            inc[u] = x;
+            if (lane == 31) sh_scan[it & 1][u][wid] = x;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            int before = 0, total = 0;
+#pragma unroll
+            for (int k = 0; k < kWarps; ++k) {
+                const int t = sh_scan[it & 1][u][k];
+                total += t;
+                if (k < wid) before += t;
+            }
+            int pre = base + before + inc[u] - nk[u];
+            base += total;
+            const int rb = r0 + u * kPrepThreads * 4 + threadIdx.x * 4;
+            if (rb < pitch) {
+                const size_t q = qidx(d, rb, pitch);    // rb & 3 == 0: the four bins sit at the same slot of the 4 sub-planes
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int r = rb + k;
+                    const bool isn = v[u][k] != v[u][k];
+                    if (r < len && !isn) cp[pre++] = v[u][k];
+                    const double out = isn ? 0.0 : v[u][k];
+                    raw[q + k * sp] = cc[u][k];
+                    bal[q + k * sp] = out;
+                    if (out != 0.0) rownz[r] = 1u;
+                }
             }
         }
-        int inc = nk;                                                            // inclusive scan of nk over the block
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) sh_scan[wid] = inc;
-        __syncthreads();
-        int pre = sh_base + inc - nk;
-        for (int k = 0; k < wid; ++k) pre += sh_scan[k];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (keep[k]) cp[pre++] = v[k];
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int tot = 0;
-            for (int k = 0; k < kPrepThreads / 32; ++k) tot += sh_scan[k];
-            sh_base += tot;
-        }
-        __syncthreads();
     }
+    if (threadIdx.x == 0) sh_base = base;
+    __syncthreads();
     const int m = sh_base;
     // ---- numpy pairwise_sum(cp[0..m)) -------------------------------------------------------------------
     // numpy's recursion: a block of n <= 128 values is summed with 8 interleaved accumulators; a longer block is
@@ -156,8 +183,16 @@ __global__ void __launch_bounds__(kPrepThreads) k_prep_band(const int* __restric
         const int j = t & 7;
         double r = 0.0;
         if (L.y >= 8) {
-            r = cp[L.x + j];
-            for (int i = 8; i < L.y - (L.y % 8); i += 8) r = __dadd_rn(r, cp[L.x + i + j]);
+            // a leaf holds <= 128 values: this lane's <= 16 are fetched together (the adds are a dependent chain, the
+            // loads are not), then added in numpy's order
+            const int nfull = L.y - (L.y % 8);
+            double x[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) x[q] = (8 * q < nfull) ? cp[L.x + 8 * q + j] : 0.0;
+            r = x[0];
+#pragma unroll
+            for (int q = 1; q < 16; ++q)
+                if (8 * q < nfull) r = __dadd_rn(r, x[q]);
         }
         const unsigned grp = 0xffu << ((threadIdx.x & 31) & ~7);
         const int src = (threadIdx.x & 31) & ~7;
