@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -111,15 +112,22 @@ struct hp_ctx {
 //          waiting threads (one per chromosome in flight, times the ranks on the box) do not starve the ones that
 //          have launches to issue when they outnumber the cores
 //   block  a blocking-sync event: the thread sleeps; highest wake-up latency
+//   hybrid yield-poll for HP_SYNC_SPIN_US (40) microseconds, then sleep on the blocking event: short waits stay quick,
+//          long ones (a score kernel queued behind seven others) leave the core to the threads packing uploads
 static int sync_mode() {
     static const int mode = []() {
         const char* e = getenv("HP_SYNC");
         if (e && !strcmp(e, "spin")) return 0;
         if (e && !strcmp(e, "block")) return 1;
         if (e && !strcmp(e, "yield")) return 2;
+        if (e && !strcmp(e, "hybrid")) return 3;
         return HP_SYNC_DEFAULT;
     }();
     return mode;
+}
+static int hybrid_spin_us() {
+    static const int us = []() { const char* e = getenv("HP_SYNC_SPIN_US"); return e ? std::max(0, atoi(e)) : 40; }();
+    return us;
 }
 static cudaError_t stream_sync(hp_ctx* ctx) {
     const int m = sync_mode();
@@ -129,6 +137,17 @@ static cudaError_t stream_sync(hp_ctx* ctx) {
             if (q != cudaErrorNotReady) return q;
             sched_yield();
         }
+    }
+    if (m == 3 && ctx->ev_sync) {                      // hybrid: poll for a short while, then sleep on a blocking event
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            const cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q != cudaErrorNotReady) return q;
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(hybrid_spin_us())) break;
+            sched_yield();
+        }
+        cudaError_t e = cudaEventRecord(ctx->ev_sync, ctx->stream);
+        return e == cudaSuccess ? cudaEventSynchronize(ctx->ev_sync) : e;
     }
     if (m == 0 || !ctx->ev_sync) return cudaStreamSynchronize(ctx->stream);
     cudaError_t e = cudaEventRecord(ctx->ev_sync, ctx->stream);

@@ -1,5 +1,7 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-python bench.py --steps 10 --warmup 3 2>gpurun_out/bench.err > gpurun_out/bench.json; python scratch/show_bench.py gpurun_out/bench.json
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_ref.json | cut -c1-200
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --chroms 2 --no-cpu-baseline > gpurun_out/b_ncu.log 2>&1
+B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline"
+for m in yield hybrid block; do
+for c in "" "taskset -c 0-3"; do
+echo "$m [$c]"; HP_SYNC=$m LOCAL_WORLD_SIZE=$([ -z "$c" ] && echo 1 || echo 4) $c $B 2>/dev/null > gpurun_out/b.json; python scratch/show_bench.py gpurun_out/b.json | head -1
+done; done
