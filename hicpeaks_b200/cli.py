@@ -7,7 +7,8 @@ What replaces what:
 * ``prepare_chromosome``  <- the worker's input preparation, pyHICCUPS:142-166 (cooler fetch, band diagonals,
                              per-distance expected ``IR``, biases).  Host side, numpy, same arithmetic.
 * ``run``                 <- ``Pool(nproc).map(worker, Params)`` (pyHICCUPS:184-198): one host thread per GPU
-                             (``--gpus``), chromosomes handed out longest first; ``--nproc`` is accepted as an alias.
+                             (``--gpus``), chromosomes handed out longest first; ``--nproc`` = host worker threads
+                             (several chromosomes in flight per GPU when it exceeds the GPU count).
 * extra flags: ``--gpus N`` and, for pyHICCUPS, ``--fdr-scope {chrom,genome}`` (``chrom`` = the reference).
 
 ``cooler`` is imported lazily; anything with ``binsize``, ``chromnames``, ``matrix(balance=, sparse=True).fetch(c)``
@@ -59,7 +60,7 @@ def hiccups_parser(prog="pyHICCUPS"):
                     help='Minimum sum of contacts in the vicinity of a valid loop.')
     g2.add_argument('--only-anchors', action='store_true', help='Either of the peak loci must be an anchor.')
     g2.add_argument('--maxapart', type=int, default=10000000, help='Maximum genomic distance between two loci.')
-    g2.add_argument('--nproc', type=int, default=1, help='Accepted for compatibility (alias of --gpus when > 1).')
+    g2.add_argument('--nproc', type=int, default=1, help='Host worker threads (chromosomes in flight); spread over the GPUs in use, at least one per GPU.')
     g3 = p.add_argument_group(title='GPU engine:')
     g3.add_argument('--gpus', type=int, default=0, help='Number of GPUs (0 = all visible).')
     g3.add_argument('--fdr-scope', choices=['chrom', 'genome'], default='chrom',
@@ -86,7 +87,7 @@ def bhfdr_parser(prog="pyBHFDR"):
     g2.add_argument('--siglevel', type=float, default=0.05, help='Significant Level.')
     g2.add_argument('--maxapart', type=int, default=2000000, help='Maximum genomic distance between two loci.')
     g2.add_argument('--clr-weight-name', default='weight', help='Name of the weight column in the Cooler URI.')
-    g2.add_argument('--nproc', type=int, default=1, help='Accepted for compatibility (alias of --gpus when > 1).')
+    g2.add_argument('--nproc', type=int, default=1, help='Host worker threads (chromosomes in flight); spread over the GPUs in use, at least one per GPU.')
     g3 = p.add_argument_group(title='GPU engine:')
     g3.add_argument('--gpus', type=int, default=0, help='Number of GPUs (0 = all visible).')
     return p
@@ -174,8 +175,17 @@ def _n_gpus(args):
     return max(1, min(want, have))
 
 
-def _map_over_gpus(keys, sizes, ngpu, fn):
-    """Longest chromosome first, one host thread per GPU pulling from a shared list; returns {key: fn(key, gpu)}."""
+def _n_workers(args, ngpu):
+    """Host threads pulling chromosomes: at least one per GPU; ``--nproc`` beyond the GPU count puts several chromosomes
+    in flight per GPU (thread t drives GPU t % ngpu with its own context and stream), so that the host side of one
+    chromosome -- cooler read, diagonal extraction, upload packing, clustering -- overlaps the kernels of another, the
+    way ``Pool(nproc)`` overlaps whole chromosomes in the reference (scripts/pyHICCUPS:192-198)."""
+    return max(ngpu, min(int(getattr(args, "nproc", 1) or 1), 8 * ngpu))
+
+
+def _map_over_gpus(keys, sizes, ngpu, fn, nworkers=None):
+    """Longest chromosome first, host threads pulling from a shared list (thread t on GPU t % ngpu); returns
+    {key: fn(key, gpu)}."""
     order = sorted(keys, key=lambda k: -sizes[k])
     lock = threading.Lock()
     out, errors = {}, []
@@ -192,7 +202,7 @@ def _map_over_gpus(keys, sizes, ngpu, fn):
                 errors.append(e)
                 return
 
-    threads = [threading.Thread(target=loop, args=(g,)) for g in range(ngpu)]
+    threads = [threading.Thread(target=loop, args=(t % ngpu,)) for t in range(max(ngpu, nworkers or ngpu))]
     for t in threads:
         t.start()
     for t in threads:
@@ -246,7 +256,7 @@ def run_hiccups(argv=None, Lib=None):
                 b = prepare_counts(Lib, key, args.clr_weight_name, args.maxapart, args.maxww, res)
                 return callers.hiccups_from_counts(b["weights"], b["n"], b["Diags"], b["num"], key.lstrip('chr'), device=gpu, **kw)
             sizes = {k: 1 for k in keys}
-            tables = _map_over_gpus(keys, sizes, ngpu, one)
+            tables = _map_over_gpus(keys, sizes, ngpu, one, _n_workers(args, ngpu))
         with open(args.output, 'w') as OF:
             for key in keys:
                 write_table(OF, HICCUPS_LINE, key.lstrip('chr'), tables[key], res)
@@ -274,7 +284,8 @@ def run_bhfdr(argv=None, Lib=None):
                                              ww=args.ww, sig=args.siglevel, maxww=args.maxww, maxapart=args.maxapart, res=res,
                                              device=gpu)
 
-        tables = _map_over_gpus(keys, {k: 1 for k in keys}, _n_gpus(args), one)
+        ngpu = _n_gpus(args)
+        tables = _map_over_gpus(keys, {k: 1 for k in keys}, ngpu, one, _n_workers(args, ngpu))
         with open(args.output, 'w') as OF:
             for key in keys:
                 write_table(OF, BHFDR_LINE, key.lstrip('chr'), tables[key], res)

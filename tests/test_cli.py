@@ -109,3 +109,37 @@ def test_apa_analysis_end_to_end(tmp_path):
     assert nwin == len(exp) > 100
     assert np.array_equal(avg, e_avg) and score == e_score and zz == e_z and maxi == e_maxi
     assert os.path.exists(out)
+
+
+def test_worker_threads_spread_over_gpus():
+    """--nproc beyond the GPU count = several chromosomes in flight per GPU (thread t on GPU t % ngpu); every key is
+    computed exactly once and an exception in a worker propagates like Pool.map's (scripts/pyHICCUPS:192-198)."""
+    import threading
+    from types import SimpleNamespace
+    from hicpeaks_b200 import cli
+    assert cli._n_workers(SimpleNamespace(nproc=1), 2) == 2
+    assert cli._n_workers(SimpleNamespace(nproc=6), 2) == 6
+    assert cli._n_workers(SimpleNamespace(nproc=64), 2) == 16
+    seen, lock = [], threading.Lock()
+
+    def fn(key, gpu):
+        with lock:
+            seen.append((key, gpu, threading.get_ident()))
+        return key * 2
+
+    keys = list(range(40))
+    out = cli._map_over_gpus(keys, {k: k for k in keys}, 2, fn, nworkers=6)
+    assert out == {k: 2 * k for k in keys}
+    assert sorted(k for k, _, _ in seen) == keys and {g for _, g, _ in seen} <= {0, 1}
+    by_thread = {}
+    for _, g, t in seen:
+        by_thread.setdefault(t, set()).add(g)
+    assert all(len(g) == 1 for g in by_thread.values())          # a thread stays on its GPU
+
+    def boom(key, gpu):
+        if key == 7:
+            raise KeyError("chromosome 7")
+        return key
+
+    with pytest.raises(KeyError):
+        cli._map_over_gpus(keys, {k: 1 for k in keys}, 2, boom, nworkers=4)
