@@ -84,3 +84,32 @@ def test_narrowed_count_upload_restores_every_count():
         exp[np.isnan(exp)] = 0.0
         assert np.array_equal(bal[d, : n - d], exp), d
     assert sent < 2 * sum(a.size for a in Dg)          # most diagonals travelled as bytes
+
+
+def test_chromosomes_in_flight_match_one_at_a_time():
+    """Several host threads, each with its own context and stream, upload (shared pack pool) and score different
+    chromosomes at once -- the way the dispatcher and bench.py drive a GPU -- and get what a lone call gets."""
+    from concurrent.futures import ThreadPoolExecutor
+    from hicpeaks_b200 import _capi
+    inputs = [synth_chromosome(2500 + 37 * i, 300, 5, maxww=10, seed=40 + i) for i in range(6)]
+    P = _capi.Context.make_params([2], [5], 10, 0.1, 300, 16)
+
+    def one(ctx, inp):
+        Dg = [np.ascontiguousarray(d, dtype=np.int32) for d in inp["Diags"]]
+        ctx.upload_counts(inp["n"], inp["num"], 5, Dg, inp["weights"])
+        S = ctx.hiccups(P)
+        sv = ctx.survivors()
+        sv = sv[np.lexsort((sv["c"], sv["r"]))]
+        return (S.n_pixels, S.frozen_w, S.n_survivors), sv.tobytes(), ctx.gaps().tobytes()
+
+    ctxs = [_capi.Context(0) for _ in inputs]
+    try:
+        alone = [one(c, i) for c, i in zip(ctxs, inputs)]
+        with ThreadPoolExecutor(len(inputs)) as pool:
+            for _ in range(3):
+                together = list(pool.map(lambda a: one(*a), zip(ctxs, inputs)))
+                assert together == alone
+        assert alone[0][0][2] > 0
+    finally:
+        for c in ctxs:
+            c.close()
