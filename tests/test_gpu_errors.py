@@ -21,7 +21,14 @@ def test_call_order_and_arguments():
         with pytest.raises(_capi.EngineError) as e:
             ctx.score(P)                                        # nothing uploaded yet
         assert e.value.code == _capi.HP_ERR_STATE and "upload" in str(e.value)
+        for early in (ctx.upload_bytes, ctx.timer_stop):        # measurement aids keep the same conventions
+            with pytest.raises(_capi.EngineError) as e:
+                early()
+            assert e.value.code == _capi.HP_ERR_STATE
         _upload(ctx, inp)
+        assert 0 < ctx.upload_bytes() < 4 * sum(d.size for d in inp["Diags"]) + 8 * inp["n"] + 16 * inp["num"] + 1
+        ctx.timer_start()
+        assert ctx.timer_stop() >= 0.0
         with pytest.raises(_capi.EngineError) as e:
             ctx.fdr()                                           # fdr before score
         assert e.value.code == _capi.HP_ERR_STATE

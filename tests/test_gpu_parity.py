@@ -24,6 +24,8 @@ CASES = [
     (1000, 200, [2], [5], 10, 300.0, 1.08, 16, 7),       # several tiles in both directions
     (777, 150, [2], [5], 10, 12.0, 1.0, 16, 9),          # sparse: deep levels, many zero pixels
     (515, 100, [1, 2, 4], [3, 5, 7], 10, 15.0, 1.0, 16, 10),  # union, sparse
+    (800, 120, [2], [5], 20, 300.0, 1.08, 16, 11),       # the operator's default maxww = 20 (callers.py:45): freezes early,
+                                                         # the executed prefix is a compiled-in program
 ]
 
 
@@ -113,3 +115,28 @@ def test_chromosomes_in_flight_match_one_at_a_time():
     finally:
         for c in ctxs:
             c.close()
+
+
+def _staircase_chromosome(n=640, band=100, maxww=20, thr=16, seed=3):
+    """Counts whose density falls in steps with the distance, tuned so that every sweep step resolves >= 30 % of what is
+    left (callers.py:219-232) until w = 11: the adaptive width runs past the widths compiled into the library."""
+    from hicpeaks_b200.synth import _finish
+    num = band + maxww + 1
+    rng = np.random.default_rng(seed)
+    fr = np.array([0.30, 0.50, 0.64, 0.74, 0.81, 0.86, 0.90, 0.93, 0.95, 0.965, 0.975, 0.985, 1.0])
+    Diags = []
+    for d in range(num):
+        f = min(max((d - 5 + 8) / (band - 5), 0), 0.999)
+        wt = 5 + int(np.searchsorted(fr, f, side="right"))
+        Diags.append(rng.poisson(thr / (wt * wt - 4), n - d).astype(np.int32) + (1 if d < 5 else 0))
+    w = np.exp(rng.normal(0, 0.2, n))
+    w[rng.choice(n, 6, replace=False)] = np.nan
+    return _finish(n, num, 5, Diags, w)
+
+
+def test_sweep_beyond_compiled_widths(ctx):
+    """maxww = 20 (the operator's default, callers.py:45) with an input that keeps widening to w = 11: no compiled-in
+    program covers the executed steps, the table-driven kernel must take over and match the oracle at every cut point."""
+    inp = _staircase_chromosome()
+    st = compare_with_oracle(ctx, inp, [2], [5], 20, 0.1, 100, 16)
+    assert st["frozen"] > 10 and st["spec_kernel"] == 0 and st["n_pixels"] > 0
