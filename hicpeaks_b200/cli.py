@@ -398,6 +398,42 @@ def run_apa(argv=None, Lib=None):
     return avg, score, z, p, maxi, n_windows
 
 
+# ---------------------------------------------------------------------------------------------------------
+# combine-resolutions (/root/reference/scripts/combine-resolutions)
+def combine_parser(prog="combine-resolutions"):
+    p = argparse.ArgumentParser(prog=prog, usage='%(prog)s <-O output> [options]',
+                                description='Combine loop calls from different resolutions.',
+                                formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    p.add_argument('-v', '--version', action='version', version=' '.join(['%(prog)s', __version__]),
+                   help='Print version number and exit.')
+    p.add_argument('-O', '--output', help='Output peak file name.')
+    p.add_argument('-p', '--paths', nargs='+', help='List of peak file paths at different resolutions.')
+    p.add_argument('-R', '--resolutions', type=int, nargs='+',
+                   help='List of resolutions corresponding to the input peak files.')
+    p.add_argument('-S', '--skip-rows', type=int, default=0, help='Number of leading lines to skip.')
+    p.add_argument('-G', '--good-res', type=int, default=20000,
+                   help='Peaks detected at finer resolutions (less than this value) are likely to be false positives if '
+                        'there are no peak annotations at coarser resolutions in the neighborhood. We keep these peaks only '
+                        'if the two loci are <mindis apart.')
+    p.add_argument('-M', '--min-dis', type=int, default=200000, help='See --good-res.')
+    p.add_argument('--max-res', type=int, default=10000,
+                   help='Allowed largest resolution for output, i.e., only peaks originally at this or less than this '
+                        'resolution will be outputed.')
+    return p
+
+
+def run_combine(argv=None):
+    """combine-resolutions:52-73: one peak file per resolution in, merged BEDPE-style coordinates out."""
+    from .combine import combine_annotations
+    args = combine_parser().parse_args(argv if argv else ['-h'])
+    byres = {res: parse_peakfile(path, args.skip_rows) for res, path in zip(args.resolutions, args.paths)}
+    peak_list = combine_annotations(byres, good_res=args.good_res, mindis=args.min_dis, max_res=args.max_res)
+    with open(args.output, 'w') as out:
+        for t in peak_list:
+            out.write('\t'.join(('chr' + t[0], str(t[1]), str(t[2]), 'chr' + t[3], str(t[4]), str(t[5]))) + '\n')
+    return peak_list
+
+
 if __name__ == "__main__":
     (run_bhfdr if (len(sys.argv) > 1 and sys.argv[1] == "bhfdr") else run_hiccups)(sys.argv[2:] if len(sys.argv) > 1 and
                                                                                    sys.argv[1] in ("bhfdr", "hiccups") else sys.argv[1:])
