@@ -1,4 +1,5 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline"
-for c in 4 8 12 16; do echo "chroms=$c"; $B --chroms $c 2>/dev/null > gpurun_out/b.json; python scratch/show_bench.py gpurun_out/b.json 2>/dev/null | head -1; done
+timeout 1800 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; python scratch/show_bench.py gpurun_out/bench.json
