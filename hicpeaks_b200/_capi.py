@@ -34,7 +34,7 @@ LIB_PATH = os.environ.get("HICPEAKS_B200_LIB") or os.path.join(os.path.dirname(o
 # every symbol include/hicpeaks_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "hp_abi_version", "hp_device_count", "hp_ctx_create", "hp_ctx_destroy", "hp_last_error",
-    "hp_band_upload", "hp_band_upload_counts", "hp_upload_bytes", "hp_timer_start", "hp_timer_stop", "hp_dump_band", "hp_hiccups_score", "hp_hiccups_fdr", "hp_hiccups", "hp_get_survivors",
+    "hp_band_upload", "hp_band_upload_counts", "hp_upload_bytes", "hp_narrow_diagonal", "hp_timer_start", "hp_timer_stop", "hp_dump_band", "hp_hiccups_score", "hp_hiccups_fdr", "hp_hiccups", "hp_get_survivors",
     "hp_hist_bins", "hp_hist_export", "hp_hist_import", "hp_get_gaps", "hp_dump_levels", "hp_dump_plane", "hp_get_chunk_table", "hp_poisson_sf",
     "hp_apa_upload", "hp_apa_windows", "hp_apa_load_windows", "hp_apa_accumulate", "hp_apa_get_windows",
 ]
@@ -115,6 +115,7 @@ def load_library(path: str | None = None):
     lib.hp_band_upload_counts.argtypes = [vp, C.POINTER(CountsDesc)]
     lib.hp_dump_band.argtypes = [vp, i32, vp, i64]
     lib.hp_upload_bytes.argtypes = [vp, C.POINTER(i64)]
+    lib.hp_narrow_diagonal.argtypes = [vp, i64, vp, C.POINTER(i32)]
     lib.hp_timer_start.argtypes = [vp]
     lib.hp_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     lib.hp_hiccups_score.argtypes = [vp, C.POINTER(HiccupsParams), C.POINTER(HiccupsSummary)]
@@ -141,6 +142,18 @@ def load_library(path: str | None = None):
     if path is None:
         _lib = lib
     return lib
+
+
+def narrow_diagonal(counts) -> np.ndarray:
+    """Host-only: the narrowed form (uint8 / uint16 / int32 array) hp_band_upload_counts sends for one count diagonal."""
+    a = np.ascontiguousarray(counts, dtype=np.int32)
+    buf = np.empty(max(a.size, 1) * 4, dtype=np.uint8)
+    es = C.c_int32()
+    rc = load_library().hp_narrow_diagonal(_ptr(a), a.size, _ptr(buf), C.byref(es))
+    if rc != HP_OK:
+        raise EngineError(rc, "hp_narrow_diagonal failed")
+    dt = {1: np.uint8, 2: np.uint16, 4: np.int32}[es.value]
+    return buf[: a.size * es.value].view(dt).copy()
 
 
 def chunk_edges(max_chunks: int) -> np.ndarray:

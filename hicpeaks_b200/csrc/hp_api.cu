@@ -518,6 +518,13 @@ extern "C" int hp_timer_stop(hp_ctx* ctx, float* ms) {
     return HP_OK;
 }
 
+// host-only inspection hook (no GPU, no context): the narrowing hp_band_upload_counts applies to one count diagonal
+extern "C" int hp_narrow_diagonal(const int32_t* src, int64_t len, void* dst, int32_t* esize) {
+    if ((!src && len > 0) || !dst || !esize || len < 0) return fail(nullptr, HP_ERR_INVALID, "NULL argument");
+    *esize = narrow_diagonal(src, (size_t)len, dst);
+    return HP_OK;
+}
+
 extern "C" int hp_upload_bytes(hp_ctx* ctx, int64_t* bytes) {
     if (!ctx || !bytes) return fail(ctx, HP_ERR_INVALID, "NULL argument");
     if (!ctx->have_band) return fail(ctx, HP_ERR_STATE, "no band uploaded");

@@ -99,6 +99,11 @@ int hp_dump_band(hp_ctx* ctx, int32_t what, double* out, int64_t capacity);
  * PCIe (the device widens it again), so this is usually ~1 byte per band pixel.  Measurement aid (bench.py). */
 int hp_upload_bytes(hp_ctx* ctx, int64_t* bytes);
 
+/* Host-only inspection hook (needs neither a GPU nor a context): writes src[0..len) to dst in the narrowest of u8 / u16 /
+ * i32 that holds every value exactly -- what hp_band_upload_counts does to each count diagonal before it crosses PCIe --
+ * and returns the element size chosen (1, 2 or 4) in *esize.  dst must have room for len * 4 bytes. */
+int hp_narrow_diagonal(const int32_t* src, int64_t len, void* dst, int32_t* esize);
+
 /* Device-clock stopwatch (CUDA events on the context's stream).  hp_timer_stop returns the milliseconds since
  * hp_timer_start once the stream has drained.  Measurement aid (bench.py times its steps with it). */
 int hp_timer_start(hp_ctx* ctx);

@@ -68,3 +68,30 @@ def test_short_or_foreign_sequences():
     Dg = [np.zeros(4, dtype=np.int32)]
     assert _both(Dg, 3, 4, -1, 4, "i")[0] == 1          # fewer items than diagonals: the first missing index
     assert _both(iter(Dg), 1, 4, -1, 4, "i")[0] == 0    # not a list / tuple
+
+
+def test_upload_narrowing_is_lossless_on_the_host():
+    """hp_narrow_diagonal (host only, no GPU): every count diagonal is sent as the narrowest of u8 / u16 / i32 that
+    holds it exactly -- never clipped, whatever the length (SIMD body + scalar tail) and wherever the large value sits."""
+    rng = np.random.default_rng(7)
+    for trial in range(300):
+        n = int(rng.integers(0, 20000)) if trial else 0
+        a = rng.integers(0, 200, n).astype(np.int32)
+        kind = trial % 5
+        if n and kind == 1:
+            a[rng.integers(0, n)] = 255
+        if n and kind == 2:
+            a[rng.integers(0, n)] = 256 + int(rng.integers(0, 65280))
+        if n and kind == 3:
+            a[rng.integers(0, n)] = 65536 + int(rng.integers(0, 2 ** 30))
+        if n and kind == 4:
+            a[rng.integers(0, n)] = -1 - int(rng.integers(0, 1000))
+        out = _capi.narrow_diagonal(a)
+        want = np.int32 if (n and (a.min() < 0 or a.max() > 65535)) else np.uint16 if (n and a.max() > 255) else np.uint8
+        assert out.dtype == want, (trial, n, out.dtype, want)
+        assert np.array_equal(out.astype(np.int64), a.astype(np.int64))
+    edge = np.zeros(8192 * 3 + 5, dtype=np.int32)
+    edge[-1] = 70000                                     # the offending value in the scalar tail of the last block
+    assert _capi.narrow_diagonal(edge).dtype == np.int32
+    edge[-1] = 300
+    assert _capi.narrow_diagonal(edge).dtype == np.uint16
