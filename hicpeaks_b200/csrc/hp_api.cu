@@ -591,7 +591,10 @@ extern "C" int hp_band_upload_counts(hp_ctx* ctx, const hp_counts_desc* b) {
         if (e != cudaSuccess && cerr == cudaSuccess) cerr = e;
         sent += used[k];
     };
+    static const bool trace = getenv("HP_TRACE") != nullptr;          // phase times of the upload on stderr (development aid)
+    const auto t_begin = std::chrono::steady_clock::now();
     PackPool::get().run_ordered(nchunk, pack, send);
+    const auto t_packed = std::chrono::steady_clock::now();
     if (cerr != cudaSuccess) return fail(ctx, HP_ERR_CUDA, std::string("band upload: ") + cudaGetErrorString(cerr));
     CK(cudaMemcpyAsync(ctx->d_pk, htab, (size_t)num * sizeof(PackedDiag), cudaMemcpyHostToDevice, st));
     ctx->h2d_bytes = (int64_t)(sent + (size_t)num * sizeof(PackedDiag) + (size_t)n * 8);
@@ -609,7 +612,14 @@ extern "C" int hp_band_upload_counts(hp_ctx* ctx, const hp_counts_desc* b) {
     CK(cudaGetLastError());
     k_prep_bias<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_w, ctx->d_b1, ctx->d_b2, (int)n);
     CK(cudaGetLastError());
+    const auto t_launched = std::chrono::steady_clock::now();
     CK(stream_sync(ctx));
+    if (trace) {
+        const auto t_end = std::chrono::steady_clock::now();
+        auto us = [](auto a, auto b) { return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
+        fprintf(stderr, "hp_band_upload_counts: pack+send %ld us, launches %ld us, wait %ld us (%zu bytes over PCIe, %d chunks)\n",
+                us(t_begin, t_packed), us(t_packed, t_launched), us(t_launched, t_end), sent, nchunk);
+    }
     ctx->n = n; ctx->num = num; ctx->bal_first = bf; ctx->pitch = pitch; ctx->plane = plane;
     ctx->have_band = true;
     return HP_OK;
