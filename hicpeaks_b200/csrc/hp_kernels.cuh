@@ -278,23 +278,39 @@ __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem&
         const double ird = SM ? sh.tb_ir[d - sh.tb_d0] : A.ir[d];
         const double bb1 = SM ? sh.tb_b1[r - sh.tb_r0] : A.b1[r];
         const double bb2 = SM ? sh.tb_b2[r + d - sh.tb_r0 - sh.tb_d0] : A.b2[r + d];
+        // The donut (K) and lower-left (Y) halves of a record are independent until they touch the histograms.  They
+        // are evaluated side by side in straight-line code -- both divisions, then both chunk searches -- so that the
+        // two dependent chains (division: ~60 cycles) overlap instead of running one after the other behind branches;
+        // with four warps per scheduler the length of this tail, not its instruction count, is what keeps the fp64
+        // pipe idle.  Results of a half that turns out invalid are discarded, exactly as the branches did.
+        const bool two = !A.bhfdr;                  // the BH-FDR caller has no lower-left background (callers.py:440-540)
+        double Ef[2];
+        bool cnzf[2], validf[2], memf[2];
+        int cif[2];
+        int4 inff[2];
+        {
+            const double den0 = be[0] != 0.0 ? be[0] : 1.0, den1 = be[1] != 0.0 ? be[1] : 1.0;
+            const double ratio0 = __ddiv_rn(SK, den0), ratio1 = __ddiv_rn(SY, den1);
+            const double cem0 = __dmul_rn(ird, ratio0), cem1 = __dmul_rn(ird, ratio1);
+            Ef[0] = __dmul_rn(__dmul_rn(cem0, bb1), bb2);
+            Ef[1] = __dmul_rn(__dmul_rn(cem1, bb1), bb2);
+            cnzf[0] = (be[0] != 0.0) && (ratio0 != 0.0) && (cem0 != 0.0);
+            cnzf[1] = two && (be[1] != 0.0) && (ratio1 != 0.0) && (cem1 != 0.0);
+            validf[0] = cnzf[0] && (Ef[0] > 0.0);
+            validf[1] = cnzf[1] && (Ef[1] > 0.0);
+            cif[0] = find_chunk(sh.rv, mc, validf[0] ? Ef[0] : 0.5, memf[0]);
+            cif[1] = find_chunk(sh.rv, mc, validf[1] ? Ef[1] : 0.5, memf[1]);
+            inff[0] = sh.cinfo[cif[0]];             // cinfo / rv are padded beyond maxchunk (score_prologue)
+            inff[1] = sh.cinfo[cif[1]];
+        }
+        if (cnzf[1]) flags |= HP_SF_CEMY_NONZERO;
 #pragma unroll
         for (int fl = 0; fl < 2; ++fl) {
-            if (fl == 1 && A.bhfdr) break;
-            const double bs = fl ? SY : SK;
-            double E = 0.0;
-            bool valid = false;
-            if (be[fl] != 0.0) {
-                const double ratio = __ddiv_rn(bs, be[fl]);
-                const double cem = __dmul_rn(ird, ratio);
-                E = __dmul_rn(__dmul_rn(cem, bb1), bb2);
-                const bool cnz = (ratio != 0.0) && (cem != 0.0);
-                valid = cnz && (E > 0.0);
-                if (fl == 1 && cnz) flags |= HP_SF_CEMY_NONZERO;
-            }
-            if (A.dump) {
+            const double E = Ef[fl];
+            const bool valid = validf[fl];
+            if (A.dump && (fl == 0 || two)) {
                 double* dp = A.dump + (size_t)((pi * 2 + fl) * 3) * A.plane + (size_t)d * A.pitch + r;
-                dp[0] = bs;
+                dp[0] = fl ? SY : SK;
                 dp[A.plane] = be[fl];
                 dp[2 * A.plane] = valid ? E : 0.0;
             }
@@ -308,16 +324,15 @@ __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem&
                 } else {
                     if (eb > sh.emax[pi * 2 + fl]) smem_red_max(&sh.emax[pi * 2 + fl], eb);
                 }
-                bool member;
-                const int ci = find_chunk(sh.rv, mc, E, member);
+                const int ci = cif[fl];
                 if (ci > mc) atomicAdd(&A.cand_count[2], 1u);
                 if (A.bhfdr) {
                     // p = 1 - pdtr(O, E) grows with E: with E in [rv[ci-1], rv[ci]) it can only pass sig if the tail at
                     // the chunk's lower edge does; kcand was built from the lower edges (hp_hiccups_score)
-                    cand |= (ci <= mc) && (obs >= sh.cinfo[ci].z);
-                } else if (member) {
+                    cand |= (ci <= mc) && (obs >= inff[fl].z);
+                } else if (memf[fl]) {
                     chk[fl] = (unsigned)ci;
-                    const int4 inf = sh.cinfo[ci];
+                    const int4 inf = inff[fl];
                     const int kb = obs < inf.y - 1 ? obs : inf.y - 1;
                     if (pi < A.sh_pairs && ci <= kShI && kb < kShK)
                         smem_red_add(&sh.hist[((pi * 2 + fl) * kShI + (ci - 1)) * kShK + kb], 1u);
