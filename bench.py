@@ -208,9 +208,9 @@ def main():
 
     from hicpeaks_b200 import _capi
     W = WORKLOAD
+    ctxs = [_capi.Context(local) for _ in range(args.chroms)]      # first: no library / no B200 = EngineError right here
     batch = make_batch(rank, args.chroms)
     arrays = [engine_arrays(inp) for inp in batch]
-    ctxs = [_capi.Context(local) for _ in batch]
     P = _capi.Context.make_params(W["pw"], W["ww"], W["maxww"], W["sig"], W["band"], W["min_local_reads"])
     h2d = 0
     for ctx, inp, (Dg, cD, ir) in zip(ctxs, batch, arrays):
