@@ -24,6 +24,7 @@ cores, bounded sample, same metric.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -259,13 +260,18 @@ def main():
         """fn runs the K steps between two device-synchronised points: seconds on the device clock (CUDA events on the
         first context's stream: recorded before the first launch and after every context's last synchronise) and on
         the host clock (cross-check; the two differ by the launch latency of the first kernel)."""
-        barrier()
-        t0 = time.perf_counter()
-        ctxs[0].timer_start()
-        res = fn()
-        ms_dev = ctxs[0].timer_stop()
-        barrier()
-        return res, ms_dev * 1e-3, time.perf_counter() - t0
+        gc.collect()
+        gc.disable()                  # a collection pause inside a 30 ms window would be charged to one rank (max over ranks)
+        try:
+            barrier()
+            t0 = time.perf_counter()
+            ctxs[0].timer_start()
+            res = fn()
+            ms_dev = ctxs[0].timer_stop()
+            barrier()
+            return res, ms_dev * 1e-3, time.perf_counter() - t0
+        finally:
+            gc.enable()
 
     # nvidia-smi polls the driver: one sampler per box (rank 0, its own GPU); see ClockSampler for the ordering
     sampler = ClockSampler(local) if rank == 0 else None
