@@ -34,7 +34,7 @@ LIB_PATH = os.environ.get("HICPEAKS_B200_LIB") or os.path.join(os.path.dirname(o
 # every symbol include/hicpeaks_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "hp_abi_version", "hp_device_count", "hp_ctx_create", "hp_ctx_destroy", "hp_last_error",
-    "hp_band_upload", "hp_band_upload_counts", "hp_upload_bytes", "hp_narrow_diagonal", "hp_timer_start", "hp_timer_stop", "hp_dump_band", "hp_hiccups_score", "hp_hiccups_fdr", "hp_hiccups", "hp_get_survivors",
+    "hp_band_upload", "hp_band_upload_counts", "hp_upload_bytes", "hp_narrow_diagonal", "hp_program_dump", "hp_timer_start", "hp_timer_stop", "hp_dump_band", "hp_hiccups_score", "hp_hiccups_fdr", "hp_hiccups", "hp_get_survivors",
     "hp_hist_bins", "hp_hist_export", "hp_hist_import", "hp_get_gaps", "hp_dump_levels", "hp_dump_plane", "hp_get_chunk_table", "hp_poisson_sf",
     "hp_apa_upload", "hp_apa_windows", "hp_apa_load_windows", "hp_apa_accumulate", "hp_apa_get_windows",
 ]
@@ -116,6 +116,7 @@ def load_library(path: str | None = None):
     lib.hp_dump_band.argtypes = [vp, i32, vp, i64]
     lib.hp_upload_bytes.argtypes = [vp, C.POINTER(i64)]
     lib.hp_narrow_diagonal.argtypes = [vp, i64, vp, C.POINTER(i32)]
+    lib.hp_program_dump.argtypes = [C.POINTER(HiccupsParams), C.POINTER(i32), vp, vp, vp, i64, vp, vp, vp, vp, C.POINTER(i64)]
     lib.hp_timer_start.argtypes = [vp]
     lib.hp_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     lib.hp_hiccups_score.argtypes = [vp, C.POINTER(HiccupsParams), C.POINTER(HiccupsSummary)]
@@ -142,6 +143,32 @@ def load_library(path: str | None = None):
     if path is None:
         _lib = lib
     return lib
+
+
+def program_dump(pw, ww, maxww):
+    """Host-only: [(p, w, [(a, b, is_y, is_r), ...])] -- the sweep program the engine builds for (pw, ww, maxww)."""
+    lib = load_library()
+    P = Context.make_params(pw, ww, maxww, 0.1, 1, 1)
+    sp = np.zeros(HP_MAX_STEPS, dtype=np.int32)
+    sw = np.zeros(HP_MAX_STEPS, dtype=np.int32)
+    oe = np.zeros(HP_MAX_STEPS, dtype=np.int32)
+    ns, no = C.c_int32(), C.c_int64()
+    rc = lib.hp_program_dump(C.byref(P), C.byref(ns), _ptr(sp), _ptr(sw), _ptr(oe), 0, None, None, None, None, C.byref(no))
+    if rc != HP_OK:
+        raise EngineError(rc, (lib.hp_last_error(None) or b"").decode())
+    a = np.zeros(max(no.value, 1), dtype=np.int8)
+    b = np.zeros_like(a)
+    y = np.zeros(a.size, dtype=np.uint8)
+    r = np.zeros(a.size, dtype=np.uint8)
+    rc = lib.hp_program_dump(C.byref(P), C.byref(ns), _ptr(sp), _ptr(sw), _ptr(oe), a.size, _ptr(a), _ptr(b), _ptr(y), _ptr(r), C.byref(no))
+    if rc != HP_OK:
+        raise EngineError(rc, (lib.hp_last_error(None) or b"").decode())
+    out, lo = [], 0
+    for s in range(ns.value):
+        hi = int(oe[s])
+        out.append((int(sp[s]), int(sw[s]), [(int(a[i]), int(b[i]), bool(y[i]), bool(r[i])) for i in range(lo, hi)]))
+        lo = hi
+    return out
 
 
 def narrow_diagonal(counts) -> np.ndarray:

@@ -691,6 +691,30 @@ static int build_program(hp_ctx* ctx, const hp_hiccups_params& P) {
     return HP_OK;
 }
 
+// host-only inspection hook (no GPU, no context): the sweep program the engine derives from (pw, ww, maxww) -- steps in
+// execution order and, per step, the cells it adds in fp64 addition order with their lower-left / Reads flags
+extern "C" int hp_program_dump(const hp_hiccups_params* prm, int32_t* nsteps, int32_t* step_p, int32_t* step_w, int32_t* op_end,
+                               int64_t op_capacity, int8_t* opa, int8_t* opb, uint8_t* opy, uint8_t* opr, int64_t* nops) {
+    if (!prm || !nsteps || !step_p || !step_w || !op_end || !nops) return fail(nullptr, HP_ERR_INVALID, "NULL argument");
+    if (prm->npw < 1 || prm->npw > HP_MAX_PW || prm->maxww < 1 || prm->maxww > HP_MAX_WW)
+        return fail(nullptr, HP_ERR_INVALID, "npw / maxww out of range");
+    hp_ctx tmp;                                        // plain host object: build_program touches no device state
+    const int rc = build_program(&tmp, *prm);
+    if (rc) return rc;
+    *nsteps = tmp.prog.nsteps;
+    *nops = (int64_t)tmp.opa.size();
+    for (int s = 0; s < tmp.prog.nsteps; ++s) {
+        step_p[s] = tmp.prog.pw[tmp.prog.step_pi[s]];
+        step_w[s] = tmp.prog.step_w[s];
+        op_end[s] = tmp.prog.op_end[s];
+    }
+    if (opa && opb && opy && opr) {
+        if (op_capacity < *nops) return fail(nullptr, HP_ERR_CAPACITY, "op buffers too small");
+        for (size_t i = 0; i < tmp.opa.size(); ++i) { opa[i] = tmp.opa[i]; opb[i] = tmp.opb[i]; opy[i] = tmp.opy[i]; opr[i] = tmp.opr[i]; }
+    }
+    return HP_OK;
+}
+
 // quad-interleaved plane: dims (row quad, row & 3, diagonal)
 static int make_map_plane(hp_ctx* ctx, CUtensorMap* map, CUtensorMapDataType dt, int esize, void* base, int box_q, int box_d) {
     cuuint64_t dims[3] = {(cuuint64_t)ctx->pitch / 4, 4, (cuuint64_t)ctx->num};

@@ -157,6 +157,14 @@ typedef struct hp_hiccups_summary {
     int32_t spec_kernel;         /* 1: the score kernel specialised for this sweep program ran   */
 } hp_hiccups_summary;
 
+/* Host-only inspection hook (needs neither a GPU nor a context): the sweep program derived from prm->pw / ww / maxww
+ * (callers.py:15-23, 132-198).  nsteps steps in execution order with their (p, w); step s adds the cells
+ * [op_end[s-1], op_end[s]) of the op list, (opa, opb) = (row, column) offset in fp64 addition order, opy = the cell also
+ * feeds the lower-left sum, opr = its raw count feeds Reads.  step_p / step_w / op_end need HP_MAX_STEPS entries; the op
+ * arrays may be NULL to query *nops first. */
+int hp_program_dump(const hp_hiccups_params* prm, int32_t* nsteps, int32_t* step_p, int32_t* step_w, int32_t* op_end,
+                    int64_t op_capacity, int8_t* opa, int8_t* opb, uint8_t* opy, uint8_t* opr, int64_t* nops);
+
 /* sweep (levels + adaptive width) + expected values + lambda-chunk histograms            */
 int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hiccups_summary* out);
 /* Poisson + BH per lambda-chunk, survivor selection.  numbin_override: NULL, or [npw*2] chunk

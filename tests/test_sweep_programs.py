@@ -75,3 +75,33 @@ def test_compiled_program_equals_the_reference_sweep(compiled, name):
         assert all(is_y == (a > 0 and b < 0) for a, b, is_y, _ in ops)
         assert row[5] == last_of_pair.get(p, -1)
         last_of_pair[p] = s
+
+
+def _random_programs(n, seed):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    out = [([2], [5], 10), ([1, 2, 4], [3, 5, 7], 10), ([2], [5], 20), ([0], [1], 3), ([3, 1], [4, 6], 9), ([5], [5], 5)]
+    while len(out) < n:
+        npw = int(rng.integers(1, 5))
+        maxww = int(rng.integers(1, 21))
+        pw = [int(x) for x in rng.choice(8, npw, replace=False)]
+        ww = [int(rng.integers(1, maxww + 1)) for _ in pw]
+        if sum(maxww - w + 1 for w in ww) <= 160:
+            out.append((pw, ww, maxww))
+    return out
+
+
+def test_runtime_program_builder_equals_the_reference_sweep():
+    """hp_program_dump (host only): the op list the table-driven kernels walk -- any (pw, ww, maxww), including peak widths
+    at or above the window, unsorted pairs and the reference's re-added rings in union mode -- against the oracle."""
+    from hicpeaks_b200 import _capi
+    for pw, ww, maxww in _random_programs(60, 1):
+        try:
+            got = _capi.program_dump(pw, ww, maxww)
+        except _capi.EngineError as e:                      # longer than this build's op table: a declared limit, not a mismatch
+            assert e.code == _capi.HP_ERR_INVALID and "too long" in str(e), (pw, ww, maxww, str(e))
+            continue
+        exp = ho.step_program(pw, ww, maxww)
+        assert [(p, w) for p, w, _ in got] == [(p, w) for p, w, _ in exp], (pw, ww, maxww)
+        for (p, w, ops), (_, _, eops) in zip(got, exp):
+            assert ops == [(a, b, bool(y), bool(r)) for a, b, y, r in eops], (pw, ww, maxww, p, w)
