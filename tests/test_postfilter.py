@@ -56,3 +56,39 @@ def test_gap_filter_matches_loop_form():
         keep = gap_filter(x, y, gaps, m, n)
         ref = gap_keep(x, y, set(np.where(gaps)[0]), m, n)
         assert np.array_equal(np.where(keep)[0], np.array(ref, dtype=np.int64))
+
+
+def test_host_helpers_of_the_mirror_match_the_restated_reference():
+    """pw_ww_pairs (callers.py:15-23), lambdachunk (:25-41) and the truncated Benjamini-Hochberg used by the BH-FDR
+    caller (:545-547 on the pixels the GPU returns) against the oracle's restatements."""
+    from hicpeaks_b200 import callers
+    from oracle import hiccups_oracle as ho
+    rng = np.random.default_rng(3)
+    for pw, ww, maxww in [([2], [5], 10), ([1, 2, 4], [3, 5, 7], 10), ([4, 1], [7, 3], 12), ([2], [5], 20)]:
+        assert callers.pw_ww_pairs(pw, ww, maxww) == ho.pw_ww_steps(pw, ww, maxww)
+    E = np.exp(rng.uniform(np.log(0.05), np.log(3000.0), 5000))
+    E[:4] = [1.0, 2.0, 2 ** (1 / 3.), 4.0]                     # values sitting on chunk edges belong to no chunk
+    chunks = callers.lambdachunk(E)
+    edges = ho.chunk_edges(len(chunks))
+    assert len(chunks) == int(np.ceil(np.log(E.max()) / np.log(2) * 3 + 1))
+    seen = np.zeros(E.size, dtype=int)
+    for i, (lv, rv, idx) in enumerate(chunks):
+        assert (lv, rv) == tuple(edges[i])
+        assert np.all((E[idx] > lv) & (E[idx] < rv))
+        seen[idx] += 1
+    assert np.all(seen[4:] == 1) and np.all(seen[:4] == 0)
+    assert callers.lambdachunk(np.array([])) == []
+    # BH over n tests of which only the p-values <= alpha are known (what the GPU hands back, callers.py:536-547): every
+    # rejected test is among them, and a larger p-value can never lower the q of one that is rejected
+    for n, alpha, power in [(5000, 0.05, 3), (300, 0.1, 6), (1000, 0.05, 1), (50, 0.01, 8), (200, 1.0, 1)]:
+        p = rng.uniform(0, 1, n) ** power
+        q_full = ho.bh_fdr(p)
+        known = np.nonzero(p <= alpha)[0]
+        known = known[rng.permutation(known.size)]
+        if known.size == 0:
+            continue
+        reject, q = callers.bh_adjust(p[known], n, alpha)
+        full_rej = q_full[known] <= alpha
+        assert np.array_equal(reject, full_rej)
+        assert np.array_equal(q[reject], q_full[known][reject])
+        assert np.all(q >= q_full[known])
