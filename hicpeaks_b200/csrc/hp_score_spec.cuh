@@ -6,9 +6,9 @@
 // discontinuous in them.  That order leaves no algebraic reuse between pixels, so the kernel is
 // bound by fp64 add issue and by shared-memory operand bandwidth, not by HBM.  This kernel attacks
 // both: the whole program (which rings every step adds) is a template parameter, so each add is one
-// DADD fed by one LDS.64 with an immediate offset, and every thread owns a 4 x 4 block of pixels
-// (4 consecutive matrix rows x 4 consecutive columns) so that a loaded operand feeds up to
-// 4 x min(4, 2w) accumulators from registers.  The quad-interleaved plane layout (hp_device.cuh)
+// DADD fed by one LDS.64 with an immediate offset, and every thread owns a 4 x kTC block of pixels
+// (4 consecutive matrix rows x kTC = 2 consecutive columns) so that a loaded operand feeds up to
+// 4 x kTC accumulators from registers (0.26 loads per add; 4 x 4 blocks need 200+ registers and ran slower).  The quad-interleaved plane layout (hp_device.cuh)
 // makes those loads conflict-free: lane l owns rows 4l..4l+3, and for a fixed row offset the 32
 // lanes read 32 consecutive doubles.
 #pragma once
@@ -178,8 +178,8 @@ __device__ __forceinline__ void spec_dispatch(int s, const double* base, double 
     }
 }
 
-// CTA: kTR rows x TD diagonals of (row, column)-aligned 4 x 4 pixel blocks; warp w owns the blocks of
-// columns [dc, dc + 4) with dc = d0 + 4 (w + 8 t), lane l the rows 4l..4l+3.  Rows with (r & 3) = i
+// CTA: kTR rows x TD diagonals of (row, column)-aligned 4 x kTC pixel blocks; a warp claims the column block
+// [dc, dc + kTC), dc = d0 + kTC * kb, dynamically (deepest first), lane l owns the rows 4l..4l+3.  Rows with (r & 3) = i
 // cover the diagonals [d0 - i, d0 + TD - i): consecutive CTAs in d tile the band without overlap,
 // and the first / last CTA mask the <= 3 diagonals that stick out of [dlo, dhi].
 //
