@@ -26,6 +26,7 @@ HP_ERR_CAPACITY = -7
 
 PF_GENERIC_KERNEL = 1
 PF_BHFDR = 2
+PF_EXACT_SUMS = 4
 SF_VALID_K, SF_VALID_Y, SF_REJECT_K, SF_REJECT_Y, SF_CEMY_NONZERO = 1, 2, 4, 8, 16
 
 LIB_NAME = "libhicpeaks_b200.so"
@@ -76,7 +77,8 @@ class HiccupsSummary(C.Structure):
                 ("n_steps", C.c_int32), ("steps", StepStat * HP_MAX_STEPS),
                 ("lf", (LfStat * 2) * HP_MAX_PW), ("n_candidates", C.c_int64), ("n_survivors", C.c_int64),
                 ("ms_levels", C.c_float), ("ms_score", C.c_float), ("ms_fdr", C.c_float), ("ms_total", C.c_float),
-                ("launches", C.c_int32), ("spec_kernel", C.c_int32)]
+                ("launches", C.c_int32), ("spec_kernel", C.c_int32),
+                ("ms_exact", C.c_float), ("fast_kernel", C.c_int32), ("n_exact", C.c_int64)]
 
 
 SURVIVOR_DTYPE = np.dtype([("r", "<i4"), ("c", "<i4"), ("pair", "<i4"), ("flags", "<u4"), ("obs", "<f8"),
@@ -319,7 +321,8 @@ class Context:
 
     # -- scoring -------------------------------------------------------------------------------
     @staticmethod
-    def make_params(pw, ww, maxww, sig, maxapart_bins, min_local_reads, dump=False, generic_kernel=False, bhfdr=False):
+    def make_params(pw, ww, maxww, sig, maxapart_bins, min_local_reads, dump=False, generic_kernel=False, bhfdr=False,
+                    exact_sums=False):
         if len(pw) != len(ww) or not 1 <= len(pw) <= HP_MAX_PW:
             raise ValueError("need 1..%d (pw, ww) pairs" % HP_MAX_PW)
         P = HiccupsParams()
@@ -328,7 +331,8 @@ class Context:
             P.pw[i], P.ww[i] = int(p), int(w)
         P.maxww, P.min_local_reads = int(maxww), int(min_local_reads)
         P.maxapart_bins, P.sig, P.dump = int(maxapart_bins), float(sig), int(bool(dump))
-        P.flags = (PF_GENERIC_KERNEL if generic_kernel else 0) | (PF_BHFDR if bhfdr else 0)
+        P.flags = ((PF_GENERIC_KERNEL if generic_kernel else 0) | (PF_BHFDR if bhfdr else 0) |
+                   (PF_EXACT_SUMS if exact_sums else 0))
         return P
 
     def score(self, P):

@@ -19,6 +19,8 @@
 
 #include "hp_kernels.cuh"
 #include "hp_score_spec.cuh"
+#include "hp_score_fast.cuh"
+#include "hp_exact.cuh"
 #include "hp_apa.cuh"
 #include "hp_prep.cuh"
 #include "hp_hostpack.h"
@@ -34,7 +36,8 @@ static thread_local std::string g_err;
 struct hp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {};
+    cudaEvent_t ev[8] = {};
+    int sm_count = 148;
     cudaEvent_t ev_sync = nullptr;    // blocking-sync event (stream_sync)
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;      // hp_timer_start / hp_timer_stop
     std::string err;
@@ -82,6 +85,14 @@ struct hp_ctx {
     unsigned int* d_cnt = nullptr;              // [0..3] cand counters, [4..7] survivor counters
     int* d_numbin = nullptr;                    // [16]
     Cand* d_cand = nullptr; size_t cap_cand = 0;
+    // re-associated score kernel (hp_score_fast.cuh): classified candidates without E, records for k_exact, fp32 factors
+    FCand* d_fcand = nullptr; size_t cap_fcand = 0;
+    XRec* d_xrec = nullptr; size_t cap_xrec = 0;
+    float* d_ffac = nullptr; size_t cap_ffac = 0;
+    unsigned int nfcand = 0;
+    bool fast_used = false;
+    bool domain_ok = false;               // every balanced value is inside the domain of the fast kernel's error bound
+    int4* d_fscratch = nullptr;           // [2 * sm_count][kFScratch] E.max() contenders of the fast kernel's CTAs
     hp_survivor* d_surv = nullptr; size_t cap_surv = 0;
     double* d_dump = nullptr; size_t cap_dump = 0;
     int numbin[HP_MAX_PW * 2] = {};
@@ -192,6 +203,7 @@ static cudaError_t ensure(T** p, size_t* cap, size_t want) {
     if (*cap >= want && *p) return cudaSuccess;
     if (*p) cudaFree(*p);
     *p = nullptr; *cap = 0;
+    want += want / 4;                                  // slack: a slightly larger request next call does not reallocate
     cudaError_t e = cudaMalloc((void**)p, want * sizeof(T));
     if (e == cudaSuccess) *cap = want;
     return e;
@@ -249,6 +261,7 @@ extern "C" int hp_ctx_create(int device, int max_chunks, const double* edges, hp
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(fail(nullptr, HP_ERR_CUDA, "stream create failed"));
     for (auto& e : ctx->ev) cudaEventCreate(&e);
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming);
     cudaDriverEntryPointQueryResult qres;
     void* fn = nullptr;
@@ -264,7 +277,7 @@ extern "C" int hp_ctx_create(int device, int max_chunks, const double* edges, hp
               cudaHostAlloc((void**)&ctx->h_res, 8192, cudaHostAllocDefault) == cudaSuccess &&
               cudaMalloc(&ctx->d_lhist, (HP_MAX_STEPS + 2) * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&ctx->d_small, 48 * sizeof(unsigned long long)) == cudaSuccess &&
-              cudaMalloc(&ctx->d_cnt, 8 * sizeof(unsigned int)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_cnt, 16 * sizeof(unsigned int)) == cudaSuccess &&
               cudaMalloc(&ctx->d_numbin, 16 * sizeof(int)) == cudaSuccess;
     if (!ok) return bail(fail(nullptr, HP_ERR_CUDA, "device allocation failed"));
     // Poisson table (universal): p[i][k] = 1 - pdtr(k, rv_i)
@@ -291,7 +304,7 @@ extern "C" void hp_ctx_destroy(hp_ctx* ctx) {
     if (ctx->stream) stream_sync(ctx);
     void* ptrs[] = {ctx->d_ptab, ctx->d_raw, ctx->d_bal, ctx->d_lvl, ctx->d_ir, ctx->d_b1, ctx->d_b2, ctx->d_rownz,
                     ctx->d_lhist, ctx->d_betab, ctx->d_hist, ctx->d_qtab, ctx->d_small, ctx->d_cnt, ctx->d_numbin,
-                    ctx->d_cand, ctx->d_surv, ctx->d_dump, ctx->d_tmp, ctx->d_tab, ctx->d_w, ctx->d_pk, ctx->d_prep, ctx->d_apa_bal, ctx->d_apa_plan, ctx->d_apa_pos,
+                    ctx->d_cand, ctx->d_fcand, ctx->d_xrec, ctx->d_ffac, ctx->d_fscratch, ctx->d_surv, ctx->d_dump, ctx->d_tmp, ctx->d_tab, ctx->d_w, ctx->d_pk, ctx->d_prep, ctx->d_apa_bal, ctx->d_apa_plan, ctx->d_apa_pos,
                     ctx->d_apa_wins, ctx->d_apa_valid, ctx->d_apa_mean, ctx->d_apa_sel, ctx->d_apa_avg};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -484,14 +497,17 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
     PackPool::get().run_ordered(nchunk, [&](int k) { pack(k * per, std::min(num, (k + 1) * per)); }, send);
     if (cerr != cudaSuccess) return fail(ctx, HP_ERR_CUDA, std::string("band upload: ") + cudaGetErrorString(cerr));
     CK(cudaMemsetAsync(ctx->d_rownz, 0, (size_t)n * sizeof(unsigned int), ctx->stream));
-    k_relayout<double><<<dim3((pitch + 255) / 256, num), 256, 0, ctx->stream>>>(tbal, ctx->d_bal, ctx->d_rownz, pitch, num);
+    CK(cudaMemsetAsync(ctx->d_cnt + 12, 0, sizeof(unsigned int), ctx->stream));
+    k_relayout<double><<<dim3((pitch + 255) / 256, num), 256, 0, ctx->stream>>>(tbal, ctx->d_bal, ctx->d_rownz, pitch, num, ctx->d_cnt + 12);
     CK(cudaGetLastError());
-    k_relayout<int><<<dim3((pitch + 255) / 256, num), 256, 0, ctx->stream>>>(traw, ctx->d_raw, nullptr, pitch, num);
+    k_relayout<int><<<dim3((pitch + 255) / 256, num), 256, 0, ctx->stream>>>(traw, ctx->d_raw, nullptr, pitch, num, nullptr);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->d_ir, hir, (size_t)num * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_b1, b->b1, n * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_b2, b->b2, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_res + 6144, ctx->d_cnt + 12, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(stream_sync(ctx));
+    ctx->domain_ok = *(const unsigned int*)(ctx->h_res + 6144) == 0u;
     ctx->n = n; ctx->num = num; ctx->bal_first = bf; ctx->pitch = pitch; ctx->plane = plane;
     ctx->h2d_bytes = (int64_t)(plane * 12 + (size_t)num * 8 + (size_t)n * 16);
     ctx->have_band = true;
@@ -600,6 +616,7 @@ extern "C" int hp_band_upload_counts(hp_ctx* ctx, const hp_counts_desc* b) {
     ctx->h2d_bytes = (int64_t)(sent + (size_t)num * sizeof(PackedDiag) + (size_t)n * 8);
     CK(cudaMemsetAsync(ctx->d_rownz, 0, (size_t)n * sizeof(unsigned int), st));
     CK(cudaMemsetAsync(ctx->d_ir, 0, (size_t)num * 8, st));
+    CK(cudaMemsetAsync(ctx->d_cnt + 12, 0, sizeof(unsigned int), st));
     if (bf > 0) {
         const size_t cnt = (size_t)bf * pitch;
         k_zero_planes<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(ctx->d_bal, cnt);
@@ -608,12 +625,14 @@ extern "C" int hp_band_upload_counts(hp_ctx* ctx, const hp_counts_desc* b) {
     }
     const int prep_smem = nslot * 20 <= 40 * 1024 ? nslot * 20 : 0;
     k_prep_band<<<nb, kPrepThreads, prep_smem, st>>>(dpk, ctx->d_pk, ctx->d_w, (int)n, num, pitch, bf, ctx->d_raw, ctx->d_bal, ctx->d_rownz,
-                                                   ctx->d_ir, comp, leaf, tval, tlist, depth, nslot, prep_smem ? 1 : 0);
+                                                   ctx->d_ir, comp, leaf, tval, tlist, depth, nslot, prep_smem ? 1 : 0, ctx->d_cnt + 12);
     CK(cudaGetLastError());
     k_prep_bias<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_w, ctx->d_b1, ctx->d_b2, (int)n);
     CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_res + 6144, ctx->d_cnt + 12, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     const auto t_launched = std::chrono::steady_clock::now();
     CK(stream_sync(ctx));
+    ctx->domain_ok = *(const unsigned int*)(ctx->h_res + 6144) == 0u;
     if (trace) {
         const auto t_end = std::chrono::steady_clock::now();
         auto us = [](auto a, auto b) { return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
@@ -760,6 +779,33 @@ static const SpecKernel g_specs[] = {
 static const SpecKernel* find_spec(hp_ctx* ctx, int nexec) {
     for (const SpecKernel& k : g_specs)
         if (k.matches(ctx->prog, nexec, ctx->opa.data(), ctx->opb.data(), ctx->opy.data(), ctx->opr.data())) return &k;
+    return nullptr;
+}
+
+// ---- re-associated score kernels (hp_score_fast.cuh): single (p, w) programs, widths up to FM ----------------
+struct FastKernel {
+    int p, w0, fm;
+    int (*launch)(hp_ctx*, const CUtensorMap&, const FastArgs&, int, cudaStream_t);
+};
+template <int P, int W0, int FM>
+static int launch_fast(hp_ctx* ctx, const CUtensorMap& tm, const FastArgs& A, int grid, cudaStream_t st) {
+    static std::atomic<size_t> granted[64];
+    const size_t smem = FastLayout<FM, FM - W0 + 1>::bytes;
+    CK(want_smem(k_score_fast<P, W0, FM>, ctx->device, smem, granted));
+    k_score_fast<P, W0, FM><<<grid, kFThreads, smem, st>>>(tm, A);
+    return HP_OK;
+}
+static const FastKernel g_fast[] = {
+    {2, 5, 8, launch_fast<2, 5, 8>},
+#ifndef HP_FAST_BUILD
+    {2, 5, 10, launch_fast<2, 5, 10>},
+    {1, 3, 10, launch_fast<1, 3, 10>},
+    {4, 7, 10, launch_fast<4, 7, 10>},
+#endif
+};
+static const FastKernel* find_fast(int p, int w0, int frozen) {
+    for (const FastKernel& k : g_fast)
+        if (k.p == p && k.w0 == w0 && frozen <= k.fm) return &k;
     return nullptr;
 }
 
@@ -966,20 +1012,38 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     }
     size_t want = std::min<size_t>((size_t)total * P.npw, (size_t)((double)total * P.npw * std::max(0.15, 1.5 * P.sig)) + 65536);
     want = std::max<size_t>(want, 65536);
-    CUtensorMap tm_bal;
+    // the re-associated kernel: single pair, HiCCUPS mode, no per-pixel dump, widths the compiled kernels cover
+    static const bool no_fast_env = getenv("HP_NO_FAST") != nullptr;
+    const FastKernel* fast = nullptr;
+    if (spec_ok && !no_fast_env && !(P.flags & HP_PF_EXACT_SUMS) && !bhfdr && !P.dump && P.npw == 1 && P.pw[0] < P.ww[0] && ctx->domain_ok)
+        fast = find_fast(P.pw[0], P.ww[0], F);
+    size_t want_x = std::max<size_t>(65536, (size_t)total / 8);
+    CUtensorMap tm_bal, tm_rawf;
     // the specialised kernel loads its tile as kTileParts boxes of consecutive planes
     rc = make_map_plane(ctx, &tm_bal, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, ctx->d_bal, A.NQ,
                         spec ? (A.BD + kTileParts - 1) / kTileParts : A.BD);
     if (rc) return rc;
-    k_betab<<<dim3((num + 127) / 128, nexec, 1 + 2 * F), 128, 0, st>>>(ctx->d_tab, ctx->d_ir, ctx->d_betab, num, ctx->bal_first, nexec, F);
+    if (fast) {
+        rc = make_map_plane(ctx, &tm_rawf, CU_TENSOR_MAP_DATA_TYPE_INT32, 4, ctx->d_raw, kFTR / 4, kFTD);
+        if (rc) return rc;
+        CK(ensure(&ctx->d_ffac, &ctx->cap_ffac, (size_t)(1 + 2 * F) * 2 * nexec * num));
+        if (!ctx->d_fscratch) CK(cudaMalloc(&ctx->d_fscratch, (size_t)2 * ctx->sm_count * kFScratch * sizeof(int4)));
+    }
+    k_betab<<<dim3((num + 127) / 128, nexec, 1 + 2 * F), 128, 0, st>>>(ctx->d_tab, ctx->d_ir, ctx->d_betab, num, ctx->bal_first, nexec, F,
+                                                                     fast ? ctx->d_ffac : nullptr);
     ++launches;
-    unsigned int cnt[4] = {0, 0, 0, 0};
+    unsigned int cnt[16] = {0};
     unsigned long long small[48];
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        CK(ensure(&ctx->d_cand, &ctx->cap_cand, want));
+    bool use_fast = fast != nullptr;
+    for (int attempt = 0;; ++attempt) {
+        CK(ensure(&ctx->d_cand, &ctx->cap_cand, use_fast ? std::max<size_t>(65536, want_x) : want));
+        if (use_fast) {
+            CK(ensure(&ctx->d_fcand, &ctx->cap_fcand, want + (size_t)kFCandChunk * (kFThreads / 32) * 2 * ctx->sm_count));   // + every warp's last piece
+            CK(ensure(&ctx->d_xrec, &ctx->cap_xrec, want_x));
+        }
         CK(cudaMemsetAsync(ctx->d_hist, 0, (size_t)P.npw * 2 * tb * sizeof(unsigned int), st));
         CK(cudaMemsetAsync(ctx->d_small, 0, 48 * sizeof(unsigned long long), st));
-        CK(cudaMemsetAsync(ctx->d_cnt, 0, 8 * sizeof(unsigned int), st));
+        CK(cudaMemsetAsync(ctx->d_cnt, 0, 16 * sizeof(unsigned int), st));
         A.tab = ctx->d_tab; A.raw = ctx->d_raw; A.lvl = ctx->d_lvl; A.ir = ctx->d_ir; A.b1 = ctx->d_b1; A.b2 = ctx->d_b2;
         A.betab = ctx->d_betab; A.hist = ctx->d_hist; A.emax_bits = ctx->d_small; A.nvalid = ctx->d_small + 16;
         A.cand = ctx->d_cand; A.cand_count = ctx->d_cnt;
@@ -993,32 +1057,70 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
         for (int k = 0; k < nexec; ++k) { A.step_pi[k] = (unsigned char)G.step_pi[k]; A.step_lo[k] = G.step_lo[k]; }
         memcpy(A.last_need, G.last_need, sizeof(A.last_need));
         CK(cudaEventRecord(ctx->ev[2], st));      // ms_score = the score kernel alone (roofline leg of bench.py)
-        if (spec) {
-            rc = spec->launch(ctx, tm_bal, A, grid, smem, st);
+        if (use_fast) {
+            FastArgs FA{};
+            FA.bal = ctx->d_bal; FA.lvl = ctx->d_lvl; FA.b1 = ctx->d_b1; FA.b2 = ctx->d_b2;
+            FA.ffac = ctx->d_ffac; FA.tab = ctx->d_tab; FA.scratch = ctx->d_fscratch;
+            FA.hist = ctx->d_hist; FA.nvalid = ctx->d_small + 16;
+            FA.fcand = ctx->d_fcand; FA.xrec = ctx->d_xrec; FA.cnt = ctx->d_cnt;
+            FA.fcand_cap = (unsigned)std::min<size_t>(ctx->cap_fcand, 0xffffffffu);
+            FA.xrec_cap = (unsigned)std::min<size_t>(ctx->cap_xrec, 0xffffffffu);
+            FA.n = n; FA.num = num; FA.pitch = pitch; FA.dlo = dlo; FA.dhi = dhi; FA.F = F; FA.nexec = nexec;
+            FA.maxchunk = ctx->chunks.maxchunk; FA.total_bins = ctx->chunks.total_bins;
+            FA.nstrips = (dhi - dlo) / kFTD + 1; FA.ntr = (n + kFTR - 1) / kFTR;
+            FA.nchunks = (FA.ntr + kFChunkTiles - 1) / kFChunkTiles;
+            const int items = FA.nstrips * FA.nchunks;
+            rc = fast->launch(ctx, tm_rawf, FA, std::min(items, 2 * ctx->sm_count), st);
             if (rc) return rc;
+            ++launches;
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ctx->ev[3], st));
+            // the records the fast kernel could not settle + the E.max() contenders, in the reference's fp64 order
+            static std::atomic<size_t> granted_x[64];
+            const size_t smem_x = ((score_smem_bytes(0, 0, sh_pairs, 0, 0, 0, 0) + 127) & ~(size_t)127) +
+                                  (size_t)(kExThreads / 32) * 2 * kExChunk * sizeof(double);
+            CK(want_smem(k_exact, ctx->device, smem_x, granted_x));
+            k_exact<<<2 * ctx->sm_count, kExThreads, smem_x, st>>>(A, ctx->d_bal, ctx->d_xrec, ctx->d_cnt + 10, FA.xrec_cap);
+            ++launches;
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ctx->ev[6], st));
         } else {
-            static std::atomic<size_t> granted[64];
-            CK(want_smem(k_score, ctx->device, smem, granted));
-            k_score<<<grid, kThreads, smem, st>>>(tm_bal, A);
+            if (spec) {
+                rc = spec->launch(ctx, tm_bal, A, grid, smem, st);
+                if (rc) return rc;
+            } else {
+                static std::atomic<size_t> granted[64];
+                CK(want_smem(k_score, ctx->device, smem, granted));
+                k_score<<<grid, kThreads, smem, st>>>(tm_bal, A);
+            }
+            ++launches;
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ctx->ev[3], st));
         }
-        ++launches;
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->ev[3], st));
         CK(cudaMemcpyAsync(ctx->h_res + 2048, ctx->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(ctx->h_res + 2048 + 64, ctx->d_small, sizeof(small), cudaMemcpyDeviceToHost, st));
         CK(stream_sync(ctx));
         memcpy(cnt, ctx->h_res + 2048, sizeof(cnt));
         memcpy(small, ctx->h_res + 2048 + 64, sizeof(small));
+        if (attempt >= 4) return fail(ctx, HP_ERR_CAPACITY, "candidate buffer overflow");
+        if (use_fast) {
+            if (cnt[11]) { want_x = (size_t)total * P.npw + 1024; continue; }
+            if (cnt[9]) { want = (size_t)total * P.npw + 1024; continue; }
+        }
         if (cnt[1] == 0) break;
-        if (attempt == 1) return fail(ctx, HP_ERR_CAPACITY, "candidate buffer overflow");
         want = (size_t)total * P.npw + 1024;      // every pixel can be a candidate at most once per pair
+        want_x = std::max(want_x, want);
     }
-    ctx->spec_used = spec != nullptr;
+    ctx->fast_used = use_fast;
+    ctx->nfcand = use_fast ? (unsigned)std::min<size_t>(cnt[8], ctx->cap_fcand) : 0u;      // slots handed out (unused ones are marked)
+    ctx->spec_used = spec != nullptr || use_fast;
     if (cnt[2]) return fail(ctx, HP_ERR_CHUNK_OVERFLOW,
                             std::to_string(cnt[2]) + " expected values exceed the last lambda-chunk edge " +
                                 std::to_string(ctx->chunks.rv[ctx->chunks.maxchunk]) + "; create the context with a larger max_chunks");
     ctx->ncand = cnt[0];
-    S.n_candidates = cnt[0];
+    S.n_candidates = (int64_t)cnt[0] + ctx->nfcand;
+    S.fast_kernel = use_fast ? 1 : 0;
+    S.n_exact = use_fast ? (int64_t)cnt[10] : 0;
     for (int i = 0; i < P.npw; ++i)
         for (int fl = 0; fl < 2; ++fl) {
             hp_lf_stat& L = S.lf[i][fl];
@@ -1031,7 +1133,9 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); S.ms_levels = ms;
     cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); S.ms_score = ms;
-    S.ms_total = S.ms_levels + S.ms_score;
+    S.ms_exact = 0.f;
+    if (use_fast) { cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[6]); S.ms_exact = ms; }
+    S.ms_total = S.ms_levels + S.ms_score + S.ms_exact;
     S.launches = launches;
     S.spec_kernel = ctx->spec_used ? 1 : 0;
     ctx->scored = true;
@@ -1067,8 +1171,9 @@ extern "C" int hp_hiccups_fdr(hp_ctx* ctx, const int32_t* numbin_override, hp_hi
     }
     unsigned int cnt[4] = {0, 0, 0, 0};
     unsigned long long nrej[16] = {0};
-    size_t want = std::max<size_t>(65536, ctx->ncand / 4 + 1024);
-    for (int attempt = 0; attempt < 2 && ctx->ncand > 0; ++attempt) {
+    const size_t ncand_all = (size_t)ctx->ncand + ctx->nfcand;
+    size_t want = std::max<size_t>(65536, ncand_all / 4 + 1024);
+    for (int attempt = 0; attempt < 2 && ncand_all > 0; ++attempt) {
         CK(ensure(&ctx->d_surv, &ctx->cap_surv, want));
         CK(cudaMemsetAsync(ctx->d_cnt + 4, 0, 4 * sizeof(unsigned int), st));
         CK(cudaMemsetAsync(ctx->d_small + 32, 0, 16 * sizeof(unsigned long long), st));
@@ -1078,9 +1183,24 @@ extern "C" int hp_hiccups_fdr(hp_ctx* ctx, const int32_t* numbin_override, hp_hi
         A.out_cap = (unsigned)std::min<size_t>(ctx->cap_surv, 0xffffffffu);
         A.nreject = ctx->d_small + 32; A.sig = P.sig; A.pitch = ctx->pitch;
         A.bhfdr = (P.flags & HP_PF_BHFDR) ? 1 : 0;
-        k_filter<<<(ctx->ncand + 255) / 256, 256, 0, st>>>(A);
-        ++launches;
-        CK(cudaGetLastError());
+        if (ctx->ncand) {
+            k_filter<<<(ctx->ncand + 255) / 256, 256, 0, st>>>(A);
+            ++launches;
+            CK(cudaGetLastError());
+        }
+        if (ctx->nfcand) {
+            // the re-associated kernel's candidates: same selection, then the survivors' E in the reference's fp64 order
+            k_filter_fast<<<(ctx->nfcand + 255) / 256, 256, 0, st>>>(A, ctx->d_fcand, ctx->nfcand);
+            ++launches;
+            CK(cudaGetLastError());
+            FillArgs FA{};
+            FA.tab = ctx->d_tab; FA.bal = ctx->d_bal; FA.ir = ctx->d_ir; FA.b1 = ctx->d_b1; FA.b2 = ctx->d_b2; FA.betab = ctx->d_betab;
+            FA.surv = ctx->d_surv; FA.nsurv_ptr = ctx->d_cnt + 4; FA.cap = A.out_cap;
+            FA.n = (int)ctx->n; FA.num = ctx->num; FA.pitch = ctx->pitch; FA.bal_first = ctx->bal_first; FA.F = S.frozen_w; FA.nexec = S.n_steps;
+            k_fill_exact<<<4 * ctx->sm_count, kExThreads, 0, st>>>(FA);
+            ++launches;
+            CK(cudaGetLastError());
+        }
         CK(cudaMemcpyAsync(ctx->h_res + 4096, ctx->d_cnt + 4, sizeof(cnt), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(ctx->h_res + 4096 + 64, ctx->d_small + 32, sizeof(nrej), cudaMemcpyDeviceToHost, st));
         if (attempt == 0) CK(cudaEventRecord(ctx->ev[5], st));
@@ -1089,9 +1209,9 @@ extern "C" int hp_hiccups_fdr(hp_ctx* ctx, const int32_t* numbin_override, hp_hi
         memcpy(nrej, ctx->h_res + 4096 + 64, sizeof(nrej));
         if (cnt[1] == 0) break;
         if (attempt == 1) return fail(ctx, HP_ERR_CAPACITY, "survivor buffer overflow");
-        want = (size_t)ctx->ncand + 16;
+        want = ncand_all + 16;
     }
-    if (ctx->ncand == 0) {
+    if (ncand_all == 0) {
         CK(cudaEventRecord(ctx->ev[5], st));
         CK(stream_sync(ctx));
     }

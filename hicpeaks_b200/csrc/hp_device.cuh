@@ -3,7 +3,9 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
+#include <math.h>
 #include <stdint.h>
+#include <type_traits>
 
 #include "../../include/hicpeaks_b200.h"
 
@@ -66,6 +68,30 @@ struct Cand {                     // 32 B: a pixel whose Poisson p can pass sig 
 // every row offset, and a 3-D TMA box (row quads, 4, diagonals) lands a tile in that order.
 __host__ __device__ __forceinline__ size_t qidx(int d, int r, int pitch) {
     return (size_t)d * pitch + (size_t)(r & 3) * (pitch >> 2) + (r >> 2);
+}
+
+// fp32 factors of the re-associated score kernel (hp_score_fast.cuh): 0 = the pixel is certainly not valid
+// (bE == 0, IR == 0 / NaN, bias 0 / NaN), NaN = fp32 cannot hold the factor safely (the record is evaluated exactly)
+__host__ __device__ __forceinline__ float fast_factor(double ird, double be) {
+    if (!(be > 0.0) && !(be < 0.0)) return 0.f;          // bE == 0 (or NaN: E is NaN, never valid)
+    if (!(ird > 0.0) && !(ird < 0.0)) return 0.f;
+    const double q = ird / be;
+    const double aq = q < 0 ? -q : q;
+    if (!(aq >= 1e-30 && aq <= 1e30)) return NAN;
+    return (float)q;
+}
+__host__ __device__ __forceinline__ float fast_bias(double b) {
+    if (!(b > 0.0) && !(b < 0.0)) return 0.f;            // 0 or NaN: E is 0 / NaN, never valid
+    const double ab = b < 0 ? -b : b;
+    if (!(ab >= 1e-15 && ab <= 1e15)) return NAN;
+    return (float)b;
+}
+
+// Domain of the re-associated kernel's error bound: a balanced value is zero or a positive normal number in
+// [2^-100, 2^100) (no sign, no NaN / Inf, nothing fp32 would flush).  Checked once per upload (k_relayout / k_prep_band).
+__device__ __forceinline__ bool fast_domain_bad(double v) {
+    const unsigned hw = (unsigned)__double2hiint(v), lw = (unsigned)__double2loint(v);
+    return (hw - 0x39B00000u) >= 0x0C800000u && (hw | lw) != 0u;
 }
 
 // ---- mbarrier / TMA -------------------------------------------------------------------------

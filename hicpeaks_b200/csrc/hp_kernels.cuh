@@ -84,8 +84,9 @@ __global__ void __launch_bounds__(kThreads) k_levels(const __grid_constant__ CUt
 // Layout betab[z][fl][s][d]: z = 0 interior pixels; z = 1 + r for the rows r < F next to the start of the
 // chromosome (cells with row < 0 or column < 0 drop out); z = 1 + F + e for the columns c = n - 1 - e, e < F,
 // next to its end (cells with row >= n or column >= n drop out).  Pixels near both ends take edge_be().
+// ffac (optional): the same table as fp32 factors IR[d] / bE for the re-associated kernel (hp_score_fast.cuh)
 __global__ void k_betab(const Tables* __restrict__ tab, const double* __restrict__ ir, double* __restrict__ betab, int num,
-                        int bal_first, int nsteps_exec, int F) {
+                        int bal_first, int nsteps_exec, int F, float* __restrict__ ffac) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     const int s = blockIdx.y, z = blockIdx.z;
     if (d >= num || s >= nsteps_exec) return;
@@ -105,6 +106,11 @@ __global__ void k_betab(const Tables* __restrict__ tab, const double* __restrict
     }
     betab[((size_t)(z * 2 + 0) * nsteps_exec + s) * num + d] = ek;
     betab[((size_t)(z * 2 + 1) * nsteps_exec + s) * num + d] = ey;
+    if (ffac) {
+        const double ird = ir[d];
+        ffac[((size_t)(z * 2 + 0) * nsteps_exec + s) * num + d] = fast_factor(ird, ek);
+        ffac[((size_t)(z * 2 + 1) * nsteps_exec + s) * num + d] = fast_factor(ird, ey);
+    }
 }
 
 // same sum for a pixel next to a chromosome end (some offsets fall outside [0, n)^2)
@@ -245,13 +251,57 @@ struct TailAcc {                       // per-thread running totals of a single-
     unsigned int nval[2];
 };
 
+// bE of a record from the tables in global memory (interior / next to one chromosome end) or from the cell list
+// (next to both ends) -- callers.py:178,182,189-191
+struct BeArgs {
+    const Tables* tab;
+    const double* ir;
+    const double* betab;
+    int n, num, F, nexec, bal_first;
+};
+__device__ __forceinline__ void record_be(const BeArgs& A, int r, int d, int s, double (&be)[2]) {
+    const bool top = r < A.F, end = r + d >= A.n - A.F;
+    if (top && end) {                          // chromosome shorter than the band + two windows: walk the cell list
+        edge_be(A.tab, A.ir, r, d, A.n, A.num, A.bal_first, s, be[0], be[1]);
+    } else {
+        const int z = top ? 1 + r : end ? 1 + A.F + (A.n - 1 - r - d) : 0;
+        const double* bt = A.betab + ((size_t)(z * 2) * A.nexec + s) * A.num + d;
+        be[0] = bt[0];
+        be[1] = bt[(size_t)A.nexec * A.num];
+    }
+}
+
+// callers.py:244-253: E = ((IR[d] * (bS / bE)) * B1[r]) * B2[c] for the donut (0) and the lower-left (1) background,
+// cnz = the reference's cEM entry is stored (non-zero), valid = E > 0.  The two halves are independent and evaluated
+// side by side so that the two division chains overlap.  Shared by the score kernels, k_exact and k_fill_exact: one
+// sequence of operations, one result.
+struct RecVal {
+    double E[2];
+    bool cnz[2], valid[2];
+};
+__device__ __forceinline__ RecVal record_values(double SK, double SY, const double (&be)[2], double ird, double bb1, double bb2, bool two) {
+    RecVal R;
+    const double den0 = be[0] != 0.0 ? be[0] : 1.0, den1 = be[1] != 0.0 ? be[1] : 1.0;
+    const double ratio0 = __ddiv_rn(SK, den0), ratio1 = __ddiv_rn(SY, den1);
+    const double cem0 = __dmul_rn(ird, ratio0), cem1 = __dmul_rn(ird, ratio1);
+    R.E[0] = __dmul_rn(__dmul_rn(cem0, bb1), bb2);
+    R.E[1] = __dmul_rn(__dmul_rn(cem1, bb1), bb2);
+    R.cnz[0] = (be[0] != 0.0) && (ratio0 != 0.0) && (cem0 != 0.0);
+    R.cnz[1] = two && (be[1] != 0.0) && (ratio1 != 0.0) && (cem1 != 0.0);
+    R.valid[0] = R.cnz[0] && (R.E[0] > 0.0);
+    R.valid[1] = R.cnz[1] && (R.E[1] > 0.0);
+    return R;
+}
+
 // Per-pixel tail (callers.py:244-256 + chunk id + histograms), called by every lane of a converged warp.
 // `act`: this lane holds a pixel (r, r + d) that resolves pair `pi` at executed step `s` with donut /
 // lower-left sums SK, SY; s and pi may differ between lanes.  NPW == 1: single pair, totals kept in `acc`.
 // SM: the small tables come from the CTA's shared-memory copies and the raw count from `obs_in`.
+// kind (k_exact only): 0 = account the record; bit 0 / 1 = the record was accounted by the fast kernel, only
+// E.max() of K / Y takes its exact value.
 template <int NPW, bool SM>
 __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem& sh, TailAcc& acc, bool act, double SK, double SY,
-                                            int r, int d, int s, int pi, int lane, int obs_in) {
+                                            int r, int d, int s, int pi, int lane, int obs_in, unsigned kind = 0u) {
     const int nexec = A.nexec;
     const int mc = A.maxchunk;
     if (NPW == 1) pi = 0;
@@ -259,21 +309,17 @@ __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem&
     unsigned flags = 0, chk[2] = {0, 0};
     double Ev[2] = {0.0, 0.0};
     int obs = 0;
+    const bool acct = kind == 0u;
     if (act) {
         obs = SM ? obs_in : A.raw[qidx(d, r, A.pitch)];
         double be[2];
         const bool top = r < A.F, end = r + d >= A.n - A.F;
-        if (top && end) {                      // chromosome shorter than the band + two windows: walk the cell list
-            edge_be(A.tab, A.ir, r, d, A.n, A.num, A.bal_first, s, be[0], be[1]);
-        } else if (SM && !top && !end) {
+        if (SM && !top && !end) {
             const double* bt = sh.tb_be + (size_t)s * sh.tb_nd + (d - sh.tb_d0);
             be[0] = bt[0];
             be[1] = bt[(size_t)nexec * sh.tb_nd];
         } else {
-            const int z = top ? 1 + r : end ? 1 + A.F + (A.n - 1 - r - d) : 0;
-            const double* bt = A.betab + ((size_t)(z * 2) * nexec + s) * A.num + d;
-            be[0] = bt[0];
-            be[1] = bt[(size_t)nexec * A.num];
+            record_be(BeArgs{A.tab, A.ir, A.betab, A.n, A.num, A.F, A.nexec, A.bal_first}, r, d, s, be);
         }
         const double ird = SM ? sh.tb_ir[d - sh.tb_d0] : A.ir[d];
         const double bb1 = SM ? sh.tb_b1[r - sh.tb_r0] : A.b1[r];
@@ -284,30 +330,19 @@ __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem&
         // with four warps per scheduler the length of this tail, not its instruction count, is what keeps the fp64
         // pipe idle.  Results of a half that turns out invalid are discarded, exactly as the branches did.
         const bool two = !A.bhfdr;                  // the BH-FDR caller has no lower-left background (callers.py:440-540)
-        double Ef[2];
-        bool cnzf[2], validf[2], memf[2];
+        const RecVal V = record_values(SK, SY, be, ird, bb1, bb2, two);
+        bool memf[2];
         int cif[2];
         int4 inff[2];
-        {
-            const double den0 = be[0] != 0.0 ? be[0] : 1.0, den1 = be[1] != 0.0 ? be[1] : 1.0;
-            const double ratio0 = __ddiv_rn(SK, den0), ratio1 = __ddiv_rn(SY, den1);
-            const double cem0 = __dmul_rn(ird, ratio0), cem1 = __dmul_rn(ird, ratio1);
-            Ef[0] = __dmul_rn(__dmul_rn(cem0, bb1), bb2);
-            Ef[1] = __dmul_rn(__dmul_rn(cem1, bb1), bb2);
-            cnzf[0] = (be[0] != 0.0) && (ratio0 != 0.0) && (cem0 != 0.0);
-            cnzf[1] = two && (be[1] != 0.0) && (ratio1 != 0.0) && (cem1 != 0.0);
-            validf[0] = cnzf[0] && (Ef[0] > 0.0);
-            validf[1] = cnzf[1] && (Ef[1] > 0.0);
-            cif[0] = find_chunk(sh.rv, mc, validf[0] ? Ef[0] : 0.5, memf[0]);
-            cif[1] = find_chunk(sh.rv, mc, validf[1] ? Ef[1] : 0.5, memf[1]);
-            inff[0] = sh.cinfo[cif[0]];             // cinfo / rv are padded beyond maxchunk (score_prologue)
-            inff[1] = sh.cinfo[cif[1]];
-        }
-        if (cnzf[1]) flags |= HP_SF_CEMY_NONZERO;
+        cif[0] = find_chunk(sh.rv, mc, V.valid[0] ? V.E[0] : 0.5, memf[0]);
+        cif[1] = find_chunk(sh.rv, mc, V.valid[1] ? V.E[1] : 0.5, memf[1]);
+        inff[0] = sh.cinfo[cif[0]];                 // cinfo / rv are padded beyond maxchunk (score_prologue)
+        inff[1] = sh.cinfo[cif[1]];
+        if (V.cnz[1] && acct) flags |= HP_SF_CEMY_NONZERO;
 #pragma unroll
         for (int fl = 0; fl < 2; ++fl) {
-            const double E = Ef[fl];
-            const bool valid = validf[fl];
+            const double E = V.E[fl];
+            const bool valid = V.valid[fl];
             if (A.dump && (fl == 0 || two)) {
                 double* dp = A.dump + (size_t)((pi * 2 + fl) * 3) * A.plane + (size_t)d * A.pitch + r;
                 dp[0] = fl ? SY : SK;
@@ -315,15 +350,15 @@ __device__ __forceinline__ void emit_record(const ScoreArgs& A, const ScoreSmem&
                 dp[2 * A.plane] = valid ? E : 0.0;
             }
             if (valid) {
+                const unsigned long long eb = (unsigned long long)__double_as_longlong(E);
+                if (acct || ((kind >> fl) & 1u)) {
+                    if (NPW == 1) acc.emax[fl] = eb > acc.emax[fl] ? eb : acc.emax[fl];
+                    else if (eb > sh.emax[pi * 2 + fl]) smem_red_max(&sh.emax[pi * 2 + fl], eb);
+                }
+                if (!acct) continue;
                 flags |= (fl ? HP_SF_VALID_Y : HP_SF_VALID_K);
                 Ev[fl] = E;
-                const unsigned long long eb = (unsigned long long)__double_as_longlong(E);
-                if (NPW == 1) {
-                    acc.emax[fl] = eb > acc.emax[fl] ? eb : acc.emax[fl];
-                    ++acc.nval[fl];
-                } else {
-                    if (eb > sh.emax[pi * 2 + fl]) smem_red_max(&sh.emax[pi * 2 + fl], eb);
-                }
+                if (NPW == 1) ++acc.nval[fl];
                 const int ci = cif[fl];
                 if (ci > mc) atomicAdd(&A.cand_count[2], 1u);
                 if (A.bhfdr) {
@@ -524,13 +559,17 @@ __global__ void __launch_bounds__(kThreads) k_score(const __grid_constant__ CUte
 // "row has a non-zero stored balanced value" flags behind the gap mask (callers.py:238)
 // ============================================================================================
 template <typename T>
-__global__ void k_relayout(const T* __restrict__ src, T* __restrict__ dst, unsigned int* __restrict__ rownz, int pitch, int num) {
+__global__ void k_relayout(const T* __restrict__ src, T* __restrict__ dst, unsigned int* __restrict__ rownz, int pitch, int num,
+                           unsigned int* __restrict__ domain_bad) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const int d = blockIdx.y;
     if (r >= pitch || d >= num) return;
     const T v = src[(size_t)d * pitch + r];
     dst[qidx(d, r, pitch)] = v;
     if (rownz && v != T(0)) rownz[r] = 1u;
+    if constexpr (std::is_same<T, double>::value) {
+        if (domain_bad && fast_domain_bad(v)) *domain_bad = 1u;
+    }
 }
 
 // ============================================================================================

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kPrepThreads) k_prep_band(const unsigned char*
                                                             unsigned int* __restrict__ rownz,
                                                             double* __restrict__ ir, double* __restrict__ comp, int2* __restrict__ tree,
                                                             double* __restrict__ tval, int* __restrict__ tlist, int depth, int nslot,
-                                                            int use_smem) {
+                                                            int use_smem, unsigned int* __restrict__ domain_bad) {
     extern __shared__ __align__(16) unsigned char prep_smem[];     // use_smem: the summation tree (nodes, values, leaf list)
     constexpr int kWarps = kPrepThreads / 32;
     constexpr int kU = 2;                               // quads per thread and round: 2 x 1024 bins per round in flight
@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(kPrepThreads) k_prep_band(const unsigned char*
                     raw[q + k * sp] = cc[u][k];
                     bal[q + k * sp] = out;
                     if (out != 0.0) rownz[r] = 1u;
+                    if (fast_domain_bad(out)) *domain_bad = 1u;
                 }
             }
         }

@@ -1,0 +1,604 @@
+// k_score_fast: the re-associated score kernel with guard-band exact re-evaluation (single (p, w) programs).
+//
+// What must be bit-exact in the reference's output is every DECISION made on the fp64 donut / lower-left sums
+// (callers.py:132-198): is E > 0, which lambda-chunk does E fall in (strict edges, callers.py:38), is the pixel a
+// candidate -- and the E of the few pixels that are finally reported.  The sums themselves are only ever seen through
+// those.  So this kernel evaluates the sums in fp32 and in a convenient order, carries a RIGOROUS bound on the
+// difference to the reference's fp64 value (all summands are >= 0, so every partial sum is bounded by the span sum and
+// the rounding error of any summation order is bounded by ops * 2^-24 * span sum), and classifies each pixel only when
+// the whole interval [lo, hi] around its expected value lies strictly inside one lambda-chunk.  A pixel whose interval
+// touches a chunk edge or zero, a pixel next to both chromosome ends, and every pixel that could hold E.max() go to a
+// short list that k_exact (hp_exact.cuh) re-evaluates in the reference's exact fp64 order; the survivors of the FDR step
+// get their reported E the same way (k_fill_exact).  Histograms, counts, E.max(), survivors, E, p, q are therefore
+// bit-identical to the exact kernels (k_score_spec / k_score); tests/test_gpu_fast.py holds the two paths against each
+// other and against the oracle.  Inputs the bound does not cover (negative or non-finite balanced values, values
+// outside [1e-30, 1e30]) raise a flag and the chromosome is re-run through the exact kernel.
+//
+// Arithmetic: for a pixel (r, c) and half-width w the four quadrant boxes are
+//     Q_w = sum_{1<=|a|<=w} sum_{1<=|b|<=w} X[r+a, c+b],     LL_w = sum_{a=1..w} sum_{b=-w..-1} X[r+a, c+b]
+// and the reference's donut / lower-left sums of a pixel resolving at width w are K = Q_w - Q_p, Y = LL_w - LL_p
+// (cross and peak square excluded, callers.py:138-141).  A thread owns one matrix row and kFNPX = 8 consecutive
+// columns; it keeps, for the 2 FM + 8 matrix columns its pixels can reach, the column sums over rows r+1..r+g (dn) and
+// over rows r-g..r-1 plus r+1..r+g (W) in registers, extends them by one row pair per level g (two rows of 128-bit
+// shared-memory loads: the tile is stored row-major so a matrix row is contiguous), and slides the (2w+1)-wide window
+// over them at the levels some pixel of the warp resolves at.  ~110 fp32 adds per pixel instead of ~200 ordered fp64
+// adds, 128-bit conflict-free loads, no barrier inside a tile's compute phase.
+//
+// Data movement: the fp64 balanced plane is streamed from HBM with coalesced loads (32 consecutive matrix rows per
+// warp and plane), converted to fp32 and stored as the shared-memory tile; a CTA walks down a strip of row tiles and
+// keeps the 32 overlapping rows, so every plane element is read once per strip.  The raw counts of the tile (needed
+// only when a pixel's record is closed) arrive by TMA while the sums are computed.
+#pragma once
+#include "hp_kernels.cuh"
+
+namespace hp {
+
+constexpr int kFTR = 64;            // tile rows
+constexpr int kFTD = 64;            // tile diagonals
+constexpr int kFThreads = 256;
+constexpr int kFNPX = 8;            // pixels (consecutive columns of one row) per thread and pass
+constexpr int kFRowHalo = 16;       // tile row 0 is matrix row r0 - 16 (>= FM, and a multiple of 16: whole 32-byte sectors)
+constexpr int kFXR = kFTR + 2 * kFRowHalo;
+constexpr int kFChunkTiles = 4;     // row tiles per work item (a CTA keeps the overlapping rows between them)
+constexpr int kFQCap = 32 * kFNPX;  // per-warp record queue: every pixel of a pass
+constexpr unsigned kFScratch = 1024;            // E.max() contenders a CTA keeps until it knows its final lower bound
+constexpr unsigned kFCandChunk = 128;           // candidate slots a warp reserves at a time (unused ones are marked r = -1)
+constexpr float kFU = 5.9604645e-8f;           // 2^-24
+constexpr float kFCRel = 16.f * kFU;           // relative error of the fp32 factor chain f * b1 * b2 * S
+// |K' - K| <= fast_cerr_k(w) * (Fmax_w + Fmax_p), |Y' - Y| <= fast_cerr_y(w) * (LLmax_w + LLmax_p): Fmax / LLmax = the
+// largest window sum among the thread's 8 pixels at that width (every intermediate of the sliding sums is below it).
+// Derivation in DESIGN.md section 3 (inputs rounded once, 2w ordered adds per column sum, 2w adds for the first window,
+// two roundings per slide, one per difference); 5 % on top for the second-order terms.
+__host__ __device__ constexpr float fast_cerr_k(int w) { return (10.f * w + 17.f) * 1.05f * kFU; }
+__host__ __device__ constexpr float fast_cerr_y(int w) { return (4.f * w + 16.f) * 1.05f * kFU; }
+
+struct XRec {                       // a record for k_exact: kind 0 = evaluate and account the whole record,
+    int r, ds, obs, kind;           // kind bit 0 / 1 = only E.max() of K / Y needs the exact value.  ds = d | step << 16
+};
+struct FCand {                      // 16 B: a classified pixel whose Poisson p can pass sig (E is filled in later,
+    int r, ds, obs;                 // for survivors only).  ds = d | step << 16
+    unsigned info;                  // chunk_k | chunk_y << 8 | flags << 16 | pair << 24
+};
+
+struct FastArgs {
+    const double* bal;              // quad-interleaved balanced plane
+    const unsigned char* lvl;
+    const double* b1;
+    const double* b2;
+    const float* ffac;              // [1 + 2F][2][nexec][num]: fp32 IR[d] / bE, laid out like betab
+                                    // (0: the pixel is certainly invalid, NaN: fp32 cannot hold the factor)
+    const Tables* tab;
+    unsigned int* hist;             // [2][total_bins]
+    unsigned long long* nvalid;     // [2]
+    FCand* fcand;
+    XRec* xrec;
+    int4* scratch;                  // [gridDim.x][kFScratch] (r, d | step << 16, hi of K or 0, hi of Y or 0)
+    unsigned int* cnt;              // d_cnt: [2] chunk overflow, [8] fcand, [9] fcand dropped, [10] xrec, [11] xrec dropped,
+                                    //        [13] work counter, [14..15] running max of lo
+    unsigned int fcand_cap, xrec_cap;
+    int n, num, pitch, dlo, dhi, F, nexec, maxchunk, total_bins;
+    int nstrips, nchunks, ntr;
+};
+
+__host__ __device__ constexpr int fast_px(int FM) {        // tile pitch in floats: >= 64 + 4 FM and == 4 (mod 8), so that
+    int p = kFTD + 4 * FM;                                 // 32 lanes on consecutive rows read / write 128-bit words
+    while (p % 8 != 4) ++p;                                // without bank conflicts
+    return p;
+}
+
+template <int B, int E, class F>
+__host__ __device__ __forceinline__ void sfor(F&& f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        sfor<B + 1, E>(f);
+    }
+}
+
+__host__ __device__ __forceinline__ float fast_max(float a, float b) { return fmaxf(a, b); }
+
+__host__ __device__ __forceinline__ unsigned fast_pack_err(float ek, float ey) {           // two bf16, rounded up
+#ifdef __CUDA_ARCH__
+    const unsigned a = __float_as_uint(ek), b = __float_as_uint(ey);
+#else
+    unsigned a, b; { union { float f; unsigned u; } x; x.f = ek; a = x.u; x.f = ey; b = x.u; }
+#endif
+    return ((a + 0xFFFFu) >> 16) | ((b + 0xFFFFu) & 0xFFFF0000u);
+}
+
+// ---- the per-thread sums: one matrix row, kFNPX consecutive columns -------------------------------------------------
+template <int P, int W0, int FM>
+struct FastPass {
+    static constexpr int SPAN = 2 * FM + kFNPX;
+    static constexpr int PX = fast_px(FM);
+
+    // xrow = &tile[row of r][8 * column block]: element (r + a, c0 - FM + t) is xrow[a * PX + FM - a + t] (the tile is
+    // indexed by diagonal along a row: one matrix row down is one diagonal back)
+    template <int G>
+    static __host__ __device__ __forceinline__ void vert(const float* __restrict__ xrow, float (&dn)[SPAN], float (&W)[SPAN]) {
+        {
+            constexpr int c0 = FM - G, sh = c0 & 3, nv = (sh + SPAN + 3) / 4;
+            float f[4 * nv];
+            const float* p = xrow + G * PX + (c0 - sh);
+#ifdef __CUDA_ARCH__
+            sfor<0, nv>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                const float4 v = reinterpret_cast<const float4*>(p)[i];
+                f[4 * i] = v.x; f[4 * i + 1] = v.y; f[4 * i + 2] = v.z; f[4 * i + 3] = v.w;
+            });
+#else
+            for (int i = 0; i < 4 * nv; ++i) f[i] = p[i];
+#endif
+            sfor<0, SPAN>([&](auto T) {
+                constexpr int t = decltype(T)::value;
+                if constexpr (G == 1) { dn[t] = f[sh + t]; W[t] = f[sh + t]; }
+                else { dn[t] += f[sh + t]; W[t] += f[sh + t]; }
+            });
+        }
+        {
+            constexpr int c0 = FM + G, sh = c0 & 3, nv = (sh + SPAN + 3) / 4;
+            float f[4 * nv];
+            const float* p = xrow - G * PX + (c0 - sh);
+#ifdef __CUDA_ARCH__
+            sfor<0, nv>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                const float4 v = reinterpret_cast<const float4*>(p)[i];
+                f[4 * i] = v.x; f[4 * i + 1] = v.y; f[4 * i + 2] = v.z; f[4 * i + 3] = v.w;
+            });
+#else
+            for (int i = 0; i < 4 * nv; ++i) f[i] = p[i];
+#endif
+            sfor<0, SPAN>([&](auto T) {
+                constexpr int t = decltype(T)::value;
+                W[t] += f[sh + t];
+            });
+        }
+    }
+
+    // quadrant boxes of half-width w for the 8 pixels: Q[i] = Q_w(r, c0 + i), L[i] = LL_w(r, c0 + i); fq / fl = the largest
+    // full window sum / lower-left sum among them (bounds every intermediate of the slides)
+    template <int w>
+    static __host__ __device__ __forceinline__ void horiz(const float (&dn)[SPAN], const float (&W)[SPAN], float (&Q)[kFNPX],
+                                                          float (&L)[kFNPX], float& fq, float& fl) {
+        float full = W[FM - w];
+        sfor<FM - w + 1, FM + w + 1>([&](auto T) { full += W[decltype(T)::value]; });
+        float ll = dn[FM - w];
+        sfor<FM - w + 1, FM>([&](auto T) { ll += dn[decltype(T)::value]; });
+        float mq = full, ml = ll;
+        sfor<0, kFNPX>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            Q[i] = full - W[FM + i];
+            L[i] = ll;
+            if constexpr (i + 1 < kFNPX) {
+                full = (full - W[FM - w + i]) + W[FM + w + 1 + i];
+                ll = (ll - dn[FM - w + i]) + dn[FM + i];
+                mq = fast_max(mq, full);
+                ml = fast_max(ml, ll);
+            }
+        });
+        fq = mq;
+        fl = ml;
+    }
+
+    // lvpk: 8 nibbles, the level code (step index) of each pixel, 0xF = not a resolved pixel; lvmask: steps present in the
+    // warp; ft: largest half-width any pixel of the warp needs.  For every resolved pixel i the sink receives, at the
+    // pixel's own width w = W0 + code:  sink(i, code, K = Q_w - Q_p, Y = LL_w - LL_p, bounds on |K' - K| and |Y' - Y| as two bf16).
+    template <class Sink>
+    static __host__ __device__ __forceinline__ void run(const float* __restrict__ xrow, unsigned lvpk, unsigned lvmask, int ft,
+                                                        Sink&& sink) {
+        float dn[SPAN], W[SPAN];
+        float Qp[kFNPX], Lp[kFNPX], fqp = 0.f, flp = 0.f;
+        sfor<0, kFNPX>([&](auto I) { Qp[decltype(I)::value] = 0.f; Lp[decltype(I)::value] = 0.f; });
+        sfor<1, FM + 1>([&](auto GG) {
+            constexpr int g = decltype(GG)::value;
+            if (g <= ft) {
+                vert<g>(xrow, dn, W);
+                if constexpr (g == P) horiz<g>(dn, W, Qp, Lp, fqp, flp);
+                if constexpr (g >= W0) {
+                    if ((lvmask >> (g - W0)) & 1u) {
+                        float Q[kFNPX], L[kFNPX], fq, fl;
+                        horiz<g>(dn, W, Q, L, fq, fl);
+                        // the bounds of this width, kept as two bf16 rounded up (one word of the record)
+                        const unsigned epk = fast_pack_err(fast_cerr_k(g) * (fq + fqp), fast_cerr_y(g) * (fl + flp));
+                        sfor<0, kFNPX>([&](auto I) {
+                            constexpr int i = decltype(I)::value;
+                            if (((lvpk >> (4 * i)) & 0xFu) == (unsigned)(g - W0))
+                                sink(I, std::integral_constant<int, g - W0>{}, Q[i] - Qp[i], L[i] - Lp[i], epk);
+                        });
+                    }
+                }
+            }
+        });
+    }
+};
+
+// Classification of one background of one pixel from its fp32 sum S (|S - exact| <= es), the fp32 factor f = IR / bE
+// and bb = B1 * B2.  0: certainly not a valid pixel (E == 0), 1: certainly valid and strictly inside lambda-chunk
+// `chunk` (chunk == maxchunk + 1: beyond the last edge), 2: cannot tell -- evaluate exactly.
+__host__ __device__ __forceinline__ int fast_classify(float S, float es, float f, float bb, const float* __restrict__ rvlo,
+                                                      const float* __restrict__ rvhi, int mc, int& chunk, float& lo, float& hi) {
+    chunk = 0; lo = 0.f; hi = 0.f;
+    if (f == 0.f || bb == 0.f || es == 0.f) return 0;    // bE == 0 / IR == 0 / a zero bias, or every cell in reach is zero
+    const float fm = f * bb;
+    const float ea = S * fm;
+    const float err = es * fabsf(fm) + fabsf(ea) * kFCRel;
+    lo = ea - err;
+    hi = ea + err;
+    if (!(lo > 0.f) || !(hi < 1e37f)) return 2;
+#ifdef __CUDA_ARCH__
+    const int e = (__float_as_int(hi) >> 23) - 127;
+#else
+    int e; { union { float f; int i; } u; u.f = hi; e = (u.i >> 23) - 127; }
+#endif
+    int i0 = 3 * e + 2;                                 // hi in [2^e, 2^(e+1)): chunks 3e+2 .. 3e+4 (hi < 1: chunk 1)
+    i0 = i0 < 1 ? 1 : (i0 > mc + 1 ? mc + 1 : i0);
+    const int i = i0 + (hi >= rvlo[i0] ? 1 : 0) + (hi >= rvlo[i0 + 1] ? 1 : 0);
+    if (!(lo > rvhi[i - 1])) return 2;
+    if (i <= mc && !(hi < rvlo[i])) return 2;
+    chunk = i;
+    return 1;
+}
+
+// shared-memory layout of a k_score_fast CTA (offsets in bytes)
+template <int FM, int NEX>
+struct FastLayout {
+    static constexpr size_t al(size_t x) { return (x + 127) & ~(size_t)127; }
+    static constexpr int PX = fast_px(FM);
+    static constexpr size_t oXS = 0;                                             // float [kFXR][PX]
+    static constexpr size_t oOBS = al(oXS + (size_t)kFXR * PX * 4);              // int   [kFTD][4][kFTR / 4] raw counts (TMA)
+    static constexpr size_t oHIST = al(oOBS + (size_t)kFTD * kFTR * 4);          // u32   [2][kShI][kShK]
+    static constexpr size_t oQ = al(oHIST + (size_t)2 * kShI * kShK * 4);        // uint4 [warps][kFQCap] K, Y, err pack, meta
+    static constexpr size_t oFTAB = al(oQ + (size_t)(kFThreads / 32) * kFQCap * 16);   // float [2][NEX][kFTD]
+    static constexpr size_t oB1 = al(oFTAB + (size_t)2 * NEX * kFTD * 4);        // float [kFTR]
+    static constexpr size_t oB2 = al(oB1 + kFTR * 4);                            // float [kFTR + kFTD]
+    static constexpr size_t oCINFO = al(oB2 + (kFTR + kFTD) * 4);                // int4  [kChunkTab]
+    static constexpr size_t oRVLO = al(oCINFO + (size_t)kChunkTab * 16);         // float [kChunkTab] edges rounded down
+    static constexpr size_t oRVHI = al(oRVLO + (size_t)kChunkTab * 4);           // float [kChunkTab] edges rounded up
+    static constexpr size_t oLVL = al(oRVHI + (size_t)kChunkTab * 4);            // u8    [kFTD][4][kFTR / 4] levels of the tile
+    static constexpr size_t oMISC = al(oLVL + (size_t)kFTD * kFTR);              // runmax[2], work, mbarrier
+    static constexpr size_t bytes = oMISC + 128;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned smem_ld_volatile(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void smem_red_max32(unsigned* p, unsigned v) {
+    asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+template <int P, int W0, int FM>
+__global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_constant__ CUtensorMap tm_raw, const __grid_constant__ FastArgs A) {
+    using FP = FastPass<P, W0, FM>;
+    constexpr int PX = FP::PX;
+    constexpr int XC = kFTD + 4 * FM;                  // tile columns: diagonals d0 - 2 FM .. d0 + 63 + 2 FM
+    constexpr int NEX = FM - W0 + 1;
+    using LY = FastLayout<FM, NEX>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* const xs = reinterpret_cast<float*>(smem + LY::oXS);
+    int* const obs = reinterpret_cast<int*>(smem + LY::oOBS);
+    unsigned int* const shist = reinterpret_cast<unsigned int*>(smem + LY::oHIST);
+    float* const ftab = reinterpret_cast<float*>(smem + LY::oFTAB);
+    float* const b1t = reinterpret_cast<float*>(smem + LY::oB1);
+    float* const b2t = reinterpret_cast<float*>(smem + LY::oB2);
+    int4* const cinfo = reinterpret_cast<int4*>(smem + LY::oCINFO);
+    float* const rvlo = reinterpret_cast<float*>(smem + LY::oRVLO);
+    float* const rvhi = reinterpret_cast<float*>(smem + LY::oRVHI);
+    unsigned char* const lvt = smem + LY::oLVL;
+    unsigned int* const runmax = reinterpret_cast<unsigned int*>(smem + LY::oMISC);
+    int* const work = reinterpret_cast<int*>(smem + LY::oMISC + 8);
+    unsigned int* const nscr = reinterpret_cast<unsigned int*>(smem + LY::oMISC + 12);
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + LY::oMISC + 16);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+    const int nexec = A.nexec, n = A.n, num = A.num, pitch = A.pitch, mc = A.maxchunk;
+    const size_t sp = (size_t)(pitch >> 2);
+    uint4* const q = reinterpret_cast<uint4*>(smem + LY::oQ) + warp * kFQCap;
+    {
+        const Chunks& C = A.tab->chunks;
+        for (int i = tid; i < kChunkTab; i += kFThreads) {
+            const bool in = i <= C.maxchunk;
+            rvlo[i] = in ? __double2float_rd(C.rv[i]) : INFINITY;
+            rvhi[i] = in ? __double2float_ru(C.rv[i]) : INFINITY;
+            cinfo[i] = in ? make_int4(C.hoff[i], C.hw[i], C.kcand[i], 0) : make_int4(0, 1, 0x7fffffff, 0);
+        }
+        for (int i = tid; i < 2 * kShI * kShK; i += kFThreads) shist[i] = 0u;
+        if (tid == 0) {
+            runmax[0] = 0u; runmax[1] = 0u; *nscr = 0u;
+            mbar_init(bar, 1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+    }
+    __syncthreads();
+    unsigned obs_phase = 0;
+    unsigned nvk = 0, nvy = 0;                          // valid pixels this thread classified (K / Y)
+    unsigned cbase = 0, cused = kFCandChunk;            // this warp's piece of the candidate list (warp-uniform)
+    const int rl = 32 * (warp & 1) + lane;             // this thread's row of the tile
+
+    for (;;) {
+        if (tid == 0) {
+            *work = (int)atomicAdd(&A.cnt[13], 1u);
+            const unsigned g0 = A.cnt[14], g1 = A.cnt[15];          // other CTAs' running maxima (any value read is a valid bound)
+            if (g0 > runmax[0]) smem_red_max32(&runmax[0], g0);
+            if (g1 > runmax[1]) smem_red_max32(&runmax[1], g1);
+        }
+        __syncthreads();
+        const int item = *work;
+        if (item >= A.nstrips * A.nchunks) break;
+        // The strip next to the diagonal first: E.max() lives there, and once its lower bound is known no pixel of the other
+        // strips is sent to the exact list as a contender.  Then the far strips (the deepest levels, the longest tiles) first.
+        const int sk = item / A.nchunks;
+        const int strip = sk == 0 ? 0 : A.nstrips - sk;
+        const int chunk = item % A.nchunks;
+        const int d0 = A.dlo + strip * kFTD;
+        const int t0 = chunk * kFChunkTiles, t1 = min(A.ntr, t0 + kFChunkTiles);
+        for (int i = tid; i < 2 * nexec * kFTD; i += kFThreads) {
+            const int fs = i / kFTD, d = d0 + (i % kFTD);
+            ftab[i] = d < num ? A.ffac[(size_t)fs * num + d] : 0.f;            // z = 0: interior pixels
+        }
+        for (int tr = t0; tr < t1; ++tr) {
+            const int r0 = tr * kFTR;
+            if (tid == 0) {                             // raw counts of the tile: needed when the records are closed
+                mbar_expect_tx(bar, (uint32_t)(kFTD * kFTR * 4));
+                tma_load_3d(obs, &tm_raw, r0 / 4, 0, d0, bar);
+            }
+            // levels of the tile: one 16-byte row piece (16 row quads of one (diagonal, row & 3)) per thread, as two 8-byte
+            // loads (issued now, stored after the tile has been filled)
+            uint2 lva = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu), lvb = lva;
+            {
+                const int dl = tid >> 2, qq = tid & 3, d = d0 + dl;
+                if (d <= A.dhi && d < num) {
+                    const unsigned char* src = A.lvl + (size_t)d * pitch + (size_t)qq * sp + (r0 >> 2);
+                    if (r0 + 32 <= pitch) lva = *reinterpret_cast<const uint2*>(src);
+                    if (r0 + 64 <= pitch) lvb = *reinterpret_cast<const uint2*>(src + 8);
+                }
+            }
+            // ---- fill the fp32 tile ----------------------------------------------------------------------------
+            int xlo = 0;
+            if (tr > t0) {                              // rows r0 - 16 .. r0 + 15 are the previous tile's rows 64 .. 95
+                for (int i = tid; i < 32 * (PX / 4); i += kFThreads) {
+                    const int x = i / (PX / 4), c4 = i % (PX / 4);
+                    reinterpret_cast<float4*>(xs + (size_t)x * PX)[c4] = reinterpret_cast<const float4*>(xs + (size_t)(x + 64) * PX)[c4];
+                }
+                xlo = 32;
+                __syncthreads();
+            }
+            {
+                // a warp task: 32 consecutive matrix rows (one per lane: coalesced in every plane) x 4 planes -> one
+                // 128-bit store per lane.  Two tasks in flight per warp.
+                const int ntask = ((kFXR - xlo) / 32) * (XC / 4);
+                const unsigned nplanes = (unsigned)(num - A.dlo);           // planes below min(ww) hold no balanced values
+                auto body = [&](int task, double (&v)[4], int& at) {
+                    const int rg = task / (XC / 4), cg = task - rg * (XC / 4);
+                    const int x = xlo + 32 * rg + lane;
+                    const int rr = r0 - kFRowHalo + x;
+                    const int db = d0 - 2 * FM + 4 * cg;
+                    at = x * PX + 4 * cg;
+                    const bool rok = (unsigned)rr < (unsigned)pitch;
+                    const double* p = A.bal + ((ptrdiff_t)db * pitch + (ptrdiff_t)(rr & 3) * (ptrdiff_t)sp + (rr >> 2));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        v[j] = 0.0;
+                        if (rok && (unsigned)(db + j - A.dlo) < nplanes) v[j] = p[(ptrdiff_t)j * pitch];
+                    }
+                };
+                auto store = [&](const double (&v)[4], int at) {
+                    float4 o;
+                    o.x = (float)v[0]; o.y = (float)v[1]; o.z = (float)v[2]; o.w = (float)v[3];
+                    *reinterpret_cast<float4*>(xs + at) = o;
+                };
+                constexpr int NW = kFThreads / 32;
+                for (int task = warp; task < ntask; task += 3 * NW) {          // three tasks (12 loads) in flight per thread
+                    double va[4], vb[4], vc[4];
+                    int aa, ab = 0, ac = 0;
+                    const bool t2 = task + NW < ntask, t3 = task + 2 * NW < ntask;
+                    body(task, va, aa);
+                    if (t2) body(task + NW, vb, ab);
+                    if (t3) body(task + 2 * NW, vc, ac);
+                    store(va, aa);
+                    if (t2) store(vb, ab);
+                    if (t3) store(vc, ac);
+                }
+            }
+            reinterpret_cast<uint4*>(lvt)[tid] = make_uint4(lva.x, lva.y, lvb.x, lvb.y);
+            for (int i = tid; i < kFTR; i += kFThreads) b1t[i] = r0 + i < n ? fast_bias(A.b1[r0 + i]) : 0.f;
+            for (int i = tid; i < kFTR + kFTD; i += kFThreads) {
+                const int c = r0 + d0 + i;
+                b2t[i] = c < n ? fast_bias(A.b2[c]) : 0.f;
+            }
+            __syncthreads();
+            mbar_wait(bar, obs_phase);
+            obs_phase ^= 1u;
+
+            // ---- the sums: two passes of 8 columns per thread ------------------------------------------------------
+#pragma unroll 1
+            for (int ps = 0; ps < 2; ++ps) {
+                const int cb = 2 * (warp >> 1) + ps;
+                unsigned lvpk = 0, mine = 0, slotpk0 = 0, slotpk1 = 0;
+                int cnt = 0;                            // records of this warp and pass (warp-uniform)
+#pragma unroll
+                for (int i = 0; i < kFNPX; ++i) {
+                    // stale bytes beyond the chromosome or the band never reach here as levels: (r, d) is checked
+                    const int r = r0 + rl, d = d0 + kFNPX * cb + i;
+                    const unsigned lv = lvt[((kFNPX * cb + i) * 4 + (rl & 3)) * (kFTR / 4) + (rl >> 2)];
+                    const unsigned code = (lv < (unsigned)nexec && d <= A.dhi && r < n && r + d < n) ? lv : 0xFu;
+                    lvpk |= code << (4 * i);
+                    const bool e = code != 0xFu;
+                    if (e) mine |= 1u << code;
+                    const unsigned mb = __ballot_sync(full, e);
+                    const unsigned slot = (unsigned)cnt + __popc(mb & lt);       // < 256
+                    if (i < 4) slotpk0 |= slot << (8 * i); else slotpk1 |= slot << (8 * (i - 4));
+                    cnt += __popc(mb);
+                }
+                const unsigned lvmask = __reduce_or_sync(full, mine);
+                if (lvmask == 0u) continue;             // no resolved pixel in these 32 rows x 8 columns
+                const int ft = W0 + (31 - __clz((int)lvmask));
+                // element (r + a, c0 - FM + t) sits at tile column (d0 + 8 cb - FM + t - a) - (d0 - 2 FM) = 8 cb + FM + t - a
+                const float* xrow = xs + (size_t)(rl + kFRowHalo) * PX + kFNPX * cb;
+                const unsigned mbase = (unsigned)rl | ((unsigned)(kFNPX * cb) << 6);
+                FP::run(xrow, lvpk, lvmask, ft, [&](auto I, auto S, float kv, float yv, unsigned epk) {
+                    constexpr int i = decltype(I)::value, sc = decltype(S)::value;
+                    const unsigned slot = ((i < 4 ? slotpk0 : slotpk1) >> (8 * (i & 3))) & 0xffu;
+                    q[slot] = make_uint4(__float_as_uint(kv), __float_as_uint(yv), epk, mbase + ((unsigned)i << 6) + ((unsigned)sc << 12));
+                });
+                __syncwarp();
+                // ---- close the records: classify both backgrounds, account the certain ones ---------------------------
+#pragma unroll 1
+                for (int b0 = 0; b0 < cnt; b0 += 32) {
+                    const bool act = b0 + lane < cnt;
+                    const uint4 rec = act ? q[b0 + lane] : make_uint4(0u, 0u, 0u, 0u);
+                    const unsigned m = rec.w;
+                    const int rrl = m & 63, dl = (m >> 6) & 63, s = (m >> 12) & 15;
+                    const int r = r0 + rrl, d = d0 + dl;
+                    const int ob = obs[(dl * 4 + (rrl & 3)) * (kFTR / 4) + (rrl >> 2)];
+                    float fk = ftab[s * kFTD + dl], fy = ftab[(nexec + s) * kFTD + dl];
+                    const bool top = r < A.F, end = r + d >= n - A.F;
+                    if (act && (top || end)) {          // next to a chromosome end: the factor tables of that row / column
+                        const int z = top ? 1 + r : 1 + A.F + (n - 1 - r - d);
+                        const size_t at = ((size_t)(z * 2) * nexec + s) * num + d;
+                        fk = (top && end) ? NAN : A.ffac[at];                    // next to both: bE is a walk over the cell list
+                        fy = (top && end) ? NAN : A.ffac[at + (size_t)nexec * num];
+                    }
+                    const float bb = b1t[rrl] * b2t[rrl + dl];
+                    int ck, cy;
+                    float lo0, hi0, lo1, hi1;
+                    const int c0 = fast_classify(__uint_as_float(rec.x), __uint_as_float(rec.z << 16), fk, bb, rvlo, rvhi, mc, ck, lo0, hi0);
+                    const int c1 = fast_classify(__uint_as_float(rec.y), __uint_as_float(rec.z & 0xFFFF0000u), fy, bb, rvlo, rvhi, mc, cy, lo1, hi1);
+                    const bool ex = act && (c0 == 2 || c1 == 2 || !(bb == bb));
+                    const bool ok = act && !ex;
+                    unsigned flags = 0, emk = 0;
+                    bool cand = false;
+                    if (ok && c0 == 1) {
+                        flags |= HP_SF_VALID_K;
+                        ++nvk;
+                        if (ck > mc) {
+                            atomicAdd(&A.cnt[2], 1u);
+                        } else {
+                            const int4 inf = cinfo[ck];
+                            const int kb = ob < inf.y - 1 ? ob : inf.y - 1;
+                            if (ck <= kShI && kb < kShK) smem_red_add(&shist[(ck - 1) * kShK + kb], 1u);
+                            else atomicAdd(&A.hist[(size_t)inf.x + kb], 1u);
+                            cand |= ob >= inf.z;
+                        }
+                        // E.max(): a record whose interval reaches the largest lower bound seen so far is evaluated exactly
+                        const unsigned cur = smem_ld_volatile(&runmax[0]);
+                        if (__float_as_uint(hi0) >= cur) emk |= 1u;
+                        if (__float_as_uint(lo0) > cur) smem_red_max32(&runmax[0], __float_as_uint(lo0));
+                    }
+                    if (ok && c1 == 1) {
+                        flags |= HP_SF_VALID_Y | HP_SF_CEMY_NONZERO;
+                        ++nvy;
+                        if (cy > mc) {
+                            atomicAdd(&A.cnt[2], 1u);
+                        } else {
+                            const int4 inf = cinfo[cy];
+                            const int kb = ob < inf.y - 1 ? ob : inf.y - 1;
+                            if (cy <= kShI && kb < kShK) smem_red_add(&shist[(kShI + cy - 1) * kShK + kb], 1u);
+                            else atomicAdd(&A.hist[(size_t)A.total_bins + inf.x + kb], 1u);
+                            cand |= ob >= inf.z;
+                        }
+                        const unsigned cur = smem_ld_volatile(&runmax[1]);
+                        if (__float_as_uint(hi1) >= cur) emk |= 2u;
+                        if (__float_as_uint(lo1) > cur) smem_red_max32(&runmax[1], __float_as_uint(lo1));
+                    }
+                    // candidates (classified records whose Poisson tail can pass sig) go to the warp's own piece of the
+                    // list: one global atomic per kFCandChunk records instead of one (with its round trip) per batch
+                    const unsigned mcand = __ballot_sync(full, cand);
+                    if (mcand) {
+                        const unsigned nc = __popc(mcand);
+                        if (cused + nc > kFCandChunk) {
+                            if (cused < kFCandChunk && lane < kFCandChunk - cused && cbase + cused + lane < A.fcand_cap)
+                                A.fcand[cbase + cused + lane].r = -1;            // (a warp leaves at most 31 slots behind)
+                            if (cused < kFCandChunk && kFCandChunk - cused > 32 && lane + 32 < kFCandChunk - cused &&
+                                cbase + cused + lane + 32 < A.fcand_cap)
+                                A.fcand[cbase + cused + lane + 32].r = -1;
+                            unsigned nb = 0;
+                            if (lane == 0) nb = atomicAdd(&A.cnt[8], kFCandChunk);
+                            cbase = __shfl_sync(full, nb, 0);
+                            cused = 0;
+                        }
+                        if (cand) {
+                            const unsigned slot = cbase + cused + __popc(mcand & lt);
+                            if (slot < A.fcand_cap)
+                                *reinterpret_cast<int4*>(&A.fcand[slot]) =
+                                    make_int4(r, d | (s << 16), ob, (int)((unsigned)ck | ((unsigned)cy << 8) | (flags << 16)));
+                            else atomicAdd(&A.cnt[9], 1u);
+                        }
+                        cused += nc;
+                    }
+                    // records the exact kernel must evaluate and account
+                    const unsigned mx = __ballot_sync(full, ex);
+                    if (mx) {
+                        unsigned base = 0;
+                        if (lane == 0) base = atomicAdd(&A.cnt[10], (unsigned)__popc(mx));
+                        base = __shfl_sync(full, base, 0);
+                        if (ex) {
+                            const unsigned slot = base + __popc(mx & lt);
+                            if (slot < A.xrec_cap) *reinterpret_cast<int4*>(&A.xrec[slot]) = make_int4(r, d | (s << 16), ob, 0);
+                            else atomicAdd(&A.cnt[11], 1u);
+                        }
+                    }
+                    // E.max() contenders wait in the CTA's scratch list: most of them fall below the bound the CTA ends with
+                    const unsigned me = __ballot_sync(full, emk != 0u);
+                    if (me) {
+                        unsigned base = 0;
+                        if (lane == 0) base = smem_atom_add(nscr, (unsigned)__popc(me));
+                        base = __shfl_sync(full, base, 0);
+                        if (emk) {
+                            const unsigned slot = base + __popc(me & lt);
+                            const int hk = (emk & 1u) ? __float_as_int(hi0) : 0, hy = (emk & 2u) ? __float_as_int(hi1) : 0;
+                            if (slot < kFScratch) {
+                                A.scratch[(size_t)blockIdx.x * kFScratch + slot] = make_int4(r, d | (s << 16), hk, hy);
+                            } else {                       // scratch full: straight to the exact list
+                                const unsigned g = atomicAdd(&A.cnt[10], 1u);
+                                if (g < A.xrec_cap) *reinterpret_cast<int4*>(&A.xrec[g]) = make_int4(r, d | (s << 16), ob, (int)emk);
+                                else atomicAdd(&A.cnt[11], 1u);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            __syncthreads();                            // tile, count tile and bias tables are free again
+        }
+        if (tid == 0) {
+            if (runmax[0]) atomicMax(&A.cnt[14], runmax[0]);
+            if (runmax[1]) atomicMax(&A.cnt[15], runmax[1]);
+        }
+    }
+    // ---- E.max() contenders that still reach the largest lower bound known now -> exact list ---------------------------
+    __syncthreads();
+    {
+        const unsigned m0 = max(runmax[0], A.cnt[14]), m1 = max(runmax[1], A.cnt[15]);
+        const unsigned ns = min(*nscr, kFScratch);
+        for (unsigned i = tid; i < ns; i += kFThreads) {
+            const int4 c = A.scratch[(size_t)blockIdx.x * kFScratch + i];
+            const int kind = ((c.z != 0 && (unsigned)c.z >= m0) ? 1 : 0) | ((c.w != 0 && (unsigned)c.w >= m1) ? 2 : 0);
+            if (kind) {
+                const unsigned g = atomicAdd(&A.cnt[10], 1u);
+                if (g < A.xrec_cap) *reinterpret_cast<int4*>(&A.xrec[g]) = make_int4(c.x, c.y, 0, kind);
+                else atomicAdd(&A.cnt[11], 1u);
+            }
+        }
+    }
+    // ---- flush: the unused rest of the warp's candidate piece, valid counts, privatised histogram ----------------------
+    for (unsigned k = cused + lane; k < kFCandChunk; k += 32)
+        if (cbase + k < A.fcand_cap) A.fcand[cbase + k].r = -1;
+    {
+        const unsigned a = __reduce_add_sync(full, nvk), b = __reduce_add_sync(full, nvy);
+        if (lane == 0 && a) atomicAdd(&A.nvalid[0], (unsigned long long)a);
+        if (lane == 0 && b) atomicAdd(&A.nvalid[1], (unsigned long long)b);
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * kShI * kShK; i += kFThreads) {
+        const unsigned v = shist[i];
+        if (v) {
+            const int kb = i % kShK, ci = (i / kShK) % kShI + 1, fl = i / (kShK * kShI);
+            atomicAdd(&A.hist[(size_t)fl * A.total_bins + cinfo[ci].x + kb], v);
+        }
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace hp

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define HP_ABI_VERSION 1
+#define HP_ABI_VERSION 2
 #define HP_MAX_PW 8        /* (pw, ww) pairs per run                                   */
 #define HP_MAX_WW 20       /* largest supported maxww (reference function default: 20) */
 #define HP_MAX_STEPS 160   /* sweep steps: sum over pairs of (maxww - ww + 1)          */
@@ -125,6 +125,11 @@ typedef struct hp_hiccups_params {
                                     rate = the pixel's own E, no lambda-chunks.  hp_hiccups_fdr then returns the
                                     pixels with p <= sig (flags REJECT_K, q = 1): the chromosome-wide BH over them and
                                     summary.lf[0][0].n_valid tests is finished by the caller (<= 1e5 records)      */
+#define HP_PF_EXACT_SUMS 4       /* evaluate every pixel's sums in the reference's fp64 order (k_score_spec / k_score).
+                                    Default for single-pair runs with maxww <= 10: the re-associated fp32 kernel
+                                    classifies the pixels and only those it cannot settle (interval around E touches a
+                                    lambda-chunk edge), E.max() and the survivors are evaluated in that order -- the
+                                    results are bit-identical either way (tests/test_gpu_fast.py)                 */
 #define HP_PF_GENERIC_KERNEL 1   /* use the table-driven score kernel even when a compiled-in sweep
                                     program matches (tests exercise both kernels)               */
 
@@ -154,7 +159,10 @@ typedef struct hp_hiccups_summary {
     float ms_levels, ms_score, ms_fdr, ms_total; /* device time (CUDA events on the ctx stream): level kernel, score
                                                     kernel, BH + survivor kernels, their sum                      */
     int32_t launches;            /* kernels launched by this call                               */
-    int32_t spec_kernel;         /* 1: the score kernel specialised for this sweep program ran   */
+    int32_t spec_kernel;         /* 1: a score kernel specialised for this sweep program ran     */
+    float ms_exact;              /* device time of the exact re-evaluation after the re-associated kernel */
+    int32_t fast_kernel;         /* 1: the re-associated kernel + exact re-evaluation ran (HP_PF_EXACT_SUMS off) */
+    int64_t n_exact;             /* records the exact re-evaluation kernel took (0 without the fast kernel) */
 } hp_hiccups_summary;
 
 /* Host-only inspection hook (needs neither a GPU nor a context): the sweep program derived from prm->pw / ww / maxww

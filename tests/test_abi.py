@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(decl):
         assert hasattr(lib, name), "missing export: " + name
     assert decl == set(_capi.SYMBOLS), decl ^ set(_capi.SYMBOLS)
-    assert _capi.load_library().hp_abi_version() == 1
+    assert _capi.load_library().hp_abi_version() == 2
 
 
 def test_struct_sizes_match_header():
