@@ -35,7 +35,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(_capi.HiccupsParams) == 104
     assert ctypes.sizeof(_capi.StepStat) == 32
     assert ctypes.sizeof(_capi.LfStat) == 32
-    assert ctypes.sizeof(_capi.HiccupsSummary) == 24 + 160 * 32 + 16 * 32 + 16 + 16 + 8
+    assert ctypes.sizeof(_capi.HiccupsSummary) == 24 + 160 * 32 + 16 * 32 + 16 + 16 + 8 + 16
     assert _capi.SURVIVOR_DTYPE.itemsize == 80
 
 
