@@ -91,6 +91,7 @@ struct hp_ctx {
     float* d_ffac = nullptr; size_t cap_ffac = 0;
     unsigned int nfcand = 0;
     bool fast_used = false;
+    bool edges_regular = false;           // every chunk edge is 2^e times rv[2] or rv[3]: the fast kernel's mantissa compares apply
     bool domain_ok = false;               // every balanced value is inside the domain of the fast kernel's error bound
     int4* d_fscratch = nullptr;           // [2 * sm_count][kFScratch] E.max() contenders of the fast kernel's CTAs
     hp_survivor* d_surv = nullptr; size_t cap_surv = 0;
@@ -239,6 +240,14 @@ static int build_chunks(hp_ctx* ctx, int max_chunks, const double* edges) {
     }
     C.hoff[max_chunks + 1] = off;
     C.total_bins = off;
+    // the re-associated kernel finds a chunk from the exponent and two mantissa compares: edges 3e+2, 3e+3 must be 2^e times
+    // the in-octave edges rv[2], rv[3] (to 1e-12; the kernel's thresholds carry a 1e-9 margin)
+    ctx->edges_regular = max_chunks >= 3;
+    for (int i = 2; i <= max_chunks && ctx->edges_regular; ++i) {
+        if (i % 3 == 1) continue;
+        const double ref = ldexp(C.rv[i % 3 == 2 ? 2 : 3], (i - 2) / 3);
+        if (!(fabs(C.rv[i] / ref - 1.0) < 1e-12)) ctx->edges_regular = false;
+    }
     return HP_OK;
 }
 
@@ -1015,7 +1024,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     // the re-associated kernel: single pair, HiCCUPS mode, no per-pixel dump, widths the compiled kernels cover
     static const bool no_fast_env = getenv("HP_NO_FAST") != nullptr;
     const FastKernel* fast = nullptr;
-    if (spec_ok && !no_fast_env && !(P.flags & HP_PF_EXACT_SUMS) && !bhfdr && !P.dump && P.npw == 1 && P.pw[0] < P.ww[0] && ctx->domain_ok)
+    if (spec_ok && !no_fast_env && !(P.flags & HP_PF_EXACT_SUMS) && !bhfdr && !P.dump && P.npw == 1 && P.pw[0] < P.ww[0] && ctx->domain_ok && ctx->edges_regular)
         fast = find_fast(P.pw[0], P.ww[0], F);
     size_t want_x = std::max<size_t>(65536, (size_t)total / 8);
     CUtensorMap tm_bal, tm_rawf;
@@ -1069,6 +1078,16 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
             FA.maxchunk = ctx->chunks.maxchunk; FA.total_bins = ctx->chunks.total_bins;
             FA.nstrips = (dhi - dlo) / kFTD + 1; FA.ntr = (n + kFTR - 1) / kFTR;
             FA.nchunks = (FA.ntr + kFChunkTiles - 1) / kFChunkTiles;
+            {   // mantissa bits of the in-octave edges, rounded down / up with margin (fast_classify)
+                auto mant = [](double x, bool up) {
+                    float f = (float)(x * (up ? 1.0 + 1e-9 : 1.0 - 1e-9));
+                    f = nextafterf(f, up ? 4.0f : 0.0f);
+                    unsigned u; memcpy(&u, &f, 4);
+                    return u & 0x7fffffu;
+                };
+                FA.c1dn = mant(ctx->chunks.rv[2], false); FA.c2dn = mant(ctx->chunks.rv[3], false);
+                FA.c1up = mant(ctx->chunks.rv[2], true); FA.c2up = mant(ctx->chunks.rv[3], true);
+            }
             const int items = FA.nstrips * FA.nchunks;
             rc = fast->launch(ctx, tm_rawf, FA, std::min(items, 2 * ctx->sm_count), st);
             if (rc) return rc;
@@ -1197,7 +1216,7 @@ extern "C" int hp_hiccups_fdr(hp_ctx* ctx, const int32_t* numbin_override, hp_hi
             FA.tab = ctx->d_tab; FA.bal = ctx->d_bal; FA.ir = ctx->d_ir; FA.b1 = ctx->d_b1; FA.b2 = ctx->d_b2; FA.betab = ctx->d_betab;
             FA.surv = ctx->d_surv; FA.nsurv_ptr = ctx->d_cnt + 4; FA.cap = A.out_cap;
             FA.n = (int)ctx->n; FA.num = ctx->num; FA.pitch = ctx->pitch; FA.bal_first = ctx->bal_first; FA.F = S.frozen_w; FA.nexec = S.n_steps;
-            k_fill_exact<<<4 * ctx->sm_count, kExThreads, 0, st>>>(FA);
+            k_fill_exact<<<16 * ctx->sm_count, kFillThreads, 0, st>>>(FA);
             ++launches;
             CK(cudaGetLastError());
         }

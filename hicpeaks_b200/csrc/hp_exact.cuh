@@ -21,14 +21,26 @@ __device__ __forceinline__ void exact_sums_warp(const Tables* __restrict__ tab, 
     double sk = 0.0, sy = 0.0;
     for (int base = 0; base < nops; base += kExChunk) {
         const int m = min(kExChunk, nops - base);
-        for (int i = lane; i < m; i += 32) {
-            const int k = base + i;
-            const int a = tab->opa[k], b = tab->opb[k];
-            const int rr = r + a, cc = r + d + b, dd = d + b - a;
-            double v = 0.0;
-            if (rr >= 0 && rr < n && cc >= 0 && cc < n && dd >= bal_first && dd < num) v = bal[qidx(dd, rr, pitch)];
-            buf[i] = v;
-            bufy[i] = tab->opy[k] ? v : 0.0;
+        for (int i0 = lane; i0 < m; i0 += 128) {          // four independent loads in flight per lane
+            double v[4];
+            bool y[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + 32 * u;
+                v[u] = 0.0; y[u] = false;
+                if (i < m) {
+                    const int k = base + i;
+                    const int a = tab->opa[k], b = tab->opb[k];
+                    const int rr = r + a, cc = r + d + b, dd = d + b - a;
+                    y[u] = tab->opy[k] != 0;
+                    if (rr >= 0 && rr < n && cc >= 0 && cc < n && dd >= bal_first && dd < num) v[u] = bal[qidx(dd, rr, pitch)];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + 32 * u;
+                if (i < m) { buf[i] = v[u]; bufy[i] = y[u] ? v[u] : 0.0; }
+            }
         }
         __syncwarp();
         if (lane == 0) {
@@ -49,6 +61,12 @@ __global__ void __launch_bounds__(kExThreads) k_exact(const __grid_constant__ Sc
                                                       const XRec* __restrict__ rec, const unsigned int* __restrict__ nrec_ptr,
                                                       unsigned int cap) {
     extern __shared__ __align__(128) unsigned char smem[];
+    {
+        unsigned nr = *nrec_ptr;
+        if (nr > cap) nr = cap;
+        const unsigned nw = gridDim.x * (kExThreads / 32), pw = (nr + nw - 1) / nw;
+        if ((unsigned long long)blockIdx.x * (kExThreads / 32) * pw >= nr) return;      // no record for this CTA
+    }
     const ScoreSmem sh = score_smem(smem, 0, 0, 0, 0, 0, 0);
     const int sh_bins = A.sh_pairs * 2 * kShI * kShK;
     double* bufs = reinterpret_cast<double*>(smem + ((score_smem_bytes(0, 0, A.sh_pairs, 0, 0, 0, 0) + 127) & ~(size_t)127));
@@ -96,15 +114,16 @@ struct FillArgs {
 };
 constexpr int kSurvNeedsE = 1 << 30;
 
-__global__ void __launch_bounds__(kExThreads) k_fill_exact(const FillArgs A) {
-    __shared__ double bufs[(kExThreads / 32) * 2 * kExChunk];
+constexpr int kFillThreads = 128;
+__global__ void __launch_bounds__(kFillThreads) k_fill_exact(const FillArgs A) {
+    __shared__ double bufs[(kFillThreads / 32) * 2 * kExChunk];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* buf = bufs + (size_t)warp * 2 * kExChunk;
     double* bufy = buf + kExChunk;
     unsigned ns = *A.nsurv_ptr;
     if (ns > A.cap) ns = A.cap;
-    const unsigned nwarps = gridDim.x * (kExThreads / 32);
-    for (unsigned k = blockIdx.x * (kExThreads / 32) + warp; k < ns; k += nwarps) {
+    const unsigned nwarps = gridDim.x * (kFillThreads / 32);
+    for (unsigned k = blockIdx.x * (kFillThreads / 32) + warp; k < ns; k += nwarps) {
         hp_survivor* sv = A.surv + k;
         const int pr = sv->pair;
         if (!(pr & kSurvNeedsE)) continue;               // warp-uniform: every lane reads the same record

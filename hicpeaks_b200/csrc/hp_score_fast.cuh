@@ -78,6 +78,7 @@ struct FastArgs {
     unsigned int fcand_cap, xrec_cap;
     int n, num, pitch, dlo, dhi, F, nexec, maxchunk, total_bins;
     int nstrips, nchunks, ntr;
+    unsigned c1dn, c2dn, c1up, c2up;   // FastEdges (host: fast_edges())
 };
 
 __host__ __device__ constexpr int fast_px(int FM) {        // tile pitch in floats: >= 64 + 4 FM and == 4 (mod 8), so that
@@ -211,11 +212,32 @@ struct FastPass {
     }
 };
 
+// lambda-chunk edges inside one octave: chunk i has the upper edge 2^((i-1)/3), so for x in [2^e, 2^(e+1)) the chunk is
+// 3e + 2 + (mantissa >= 2^(1/3)) + (mantissa >= 2^(2/3)) -- an exponent and two mantissa compares, no table.  c?dn / c?up:
+// mantissa bits of the two edges rounded down / up (with a 1e-9 margin for the edges the caller's pow() produced;
+// hp_ctx_create checks that every edge is 2^e times one of the two within 1e-12).
+struct FastEdges { unsigned c1dn, c2dn, c1up, c2up; };
+__host__ __device__ __forceinline__ unsigned fast_bits(float x) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(x);
+#else
+    union { float f; unsigned u; } v; v.f = x; return v.u;
+#endif
+}
+__host__ __device__ __forceinline__ int fast_chunk_index(unsigned bits, unsigned c1, unsigned c2) {      // bits of a positive float
+    const int e = (int)(bits >> 23) - 127;
+    const unsigned m = bits & 0x7fffffu;
+    const int i = 3 * e + 2 + (m >= c1 ? 1 : 0) + (m >= c2 ? 1 : 0);
+    return i < 1 ? 1 : i;                               // below 1: chunk 1 = (0, 1)
+}
+
 // Classification of one background of one pixel from its fp32 sum S (|S - exact| <= es), the fp32 factor f = IR / bE
 // and bb = B1 * B2.  0: certainly not a valid pixel (E == 0), 1: certainly valid and strictly inside lambda-chunk
 // `chunk` (chunk == maxchunk + 1: beyond the last edge), 2: cannot tell -- evaluate exactly.
-__host__ __device__ __forceinline__ int fast_classify(float S, float es, float f, float bb, const float* __restrict__ rvlo,
-                                                      const float* __restrict__ rvhi, int mc, int& chunk, float& lo, float& hi) {
+// Certain means: the chunk of the float just below lo (edges rounded up) equals the chunk of hi (edges rounded down);
+// then edge(chunk - 1) < lo <= E <= hi < edge(chunk) for every E the bound allows.
+__host__ __device__ __forceinline__ int fast_classify(float S, float es, float f, float bb, const FastEdges& ed, int mc, int& chunk,
+                                                      float& lo, float& hi) {
     chunk = 0; lo = 0.f; hi = 0.f;
     if (f == 0.f || bb == 0.f || es == 0.f) return 0;    // bE == 0 / IR == 0 / a zero bias, or every cell in reach is zero
     const float fm = f * bb;
@@ -224,17 +246,10 @@ __host__ __device__ __forceinline__ int fast_classify(float S, float es, float f
     lo = ea - err;
     hi = ea + err;
     if (!(lo > 0.f) || !(hi < 1e37f)) return 2;
-#ifdef __CUDA_ARCH__
-    const int e = (__float_as_int(hi) >> 23) - 127;
-#else
-    int e; { union { float f; int i; } u; u.f = hi; e = (u.i >> 23) - 127; }
-#endif
-    int i0 = 3 * e + 2;                                 // hi in [2^e, 2^(e+1)): chunks 3e+2 .. 3e+4 (hi < 1: chunk 1)
-    i0 = i0 < 1 ? 1 : (i0 > mc + 1 ? mc + 1 : i0);
-    const int i = i0 + (hi >= rvlo[i0] ? 1 : 0) + (hi >= rvlo[i0 + 1] ? 1 : 0);
-    if (!(lo > rvhi[i - 1])) return 2;
-    if (i <= mc && !(hi < rvlo[i])) return 2;
-    chunk = i;
+    const int il = fast_chunk_index(fast_bits(lo) - 1u, ed.c1up, ed.c2up);
+    const int ih = fast_chunk_index(fast_bits(hi), ed.c1dn, ed.c2dn);
+    if (il != ih) return 2;
+    chunk = ih > mc ? mc + 1 : ih;
     return 1;
 }
 
@@ -251,9 +266,7 @@ struct FastLayout {
     static constexpr size_t oB1 = al(oFTAB + (size_t)2 * NEX * kFTD * 4);        // float [kFTR]
     static constexpr size_t oB2 = al(oB1 + kFTR * 4);                            // float [kFTR + kFTD]
     static constexpr size_t oCINFO = al(oB2 + (kFTR + kFTD) * 4);                // int4  [kChunkTab]
-    static constexpr size_t oRVLO = al(oCINFO + (size_t)kChunkTab * 16);         // float [kChunkTab] edges rounded down
-    static constexpr size_t oRVHI = al(oRVLO + (size_t)kChunkTab * 4);           // float [kChunkTab] edges rounded up
-    static constexpr size_t oLVL = al(oRVHI + (size_t)kChunkTab * 4);            // u8    [kFTD][4][kFTR / 4] levels of the tile
+    static constexpr size_t oLVL = al(oCINFO + (size_t)kChunkTab * 16);          // u8    [kFTD][4][kFTR / 4] levels of the tile
     static constexpr size_t oMISC = al(oLVL + (size_t)kFTD * kFTR);              // runmax[2], work, mbarrier
     static constexpr size_t bytes = oMISC + 128;
 };
@@ -263,6 +276,9 @@ __device__ __forceinline__ unsigned smem_ld_volatile(const unsigned* p) {
     unsigned v;
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
     return v;
+}
+__device__ __forceinline__ void gmem_red_add(unsigned* p, unsigned v) {
+    asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void smem_red_max32(unsigned* p, unsigned v) {
     asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
@@ -283,24 +299,22 @@ __global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_consta
     float* const b1t = reinterpret_cast<float*>(smem + LY::oB1);
     float* const b2t = reinterpret_cast<float*>(smem + LY::oB2);
     int4* const cinfo = reinterpret_cast<int4*>(smem + LY::oCINFO);
-    float* const rvlo = reinterpret_cast<float*>(smem + LY::oRVLO);
-    float* const rvhi = reinterpret_cast<float*>(smem + LY::oRVHI);
     unsigned char* const lvt = smem + LY::oLVL;
     unsigned int* const runmax = reinterpret_cast<unsigned int*>(smem + LY::oMISC);
     int* const work = reinterpret_cast<int*>(smem + LY::oMISC + 8);
     unsigned int* const nscr = reinterpret_cast<unsigned int*>(smem + LY::oMISC + 12);
+    unsigned int* const npass = reinterpret_cast<unsigned int*>(smem + LY::oMISC + 24);
     uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + LY::oMISC + 16);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
     const int nexec = A.nexec, n = A.n, num = A.num, pitch = A.pitch, mc = A.maxchunk;
     const size_t sp = (size_t)(pitch >> 2);
     uint4* const q = reinterpret_cast<uint4*>(smem + LY::oQ) + warp * kFQCap;
+    const FastEdges ed{A.c1dn, A.c2dn, A.c1up, A.c2up};
     {
         const Chunks& C = A.tab->chunks;
         for (int i = tid; i < kChunkTab; i += kFThreads) {
             const bool in = i <= C.maxchunk;
-            rvlo[i] = in ? __double2float_rd(C.rv[i]) : INFINITY;
-            rvhi[i] = in ? __double2float_ru(C.rv[i]) : INFINITY;
             cinfo[i] = in ? make_int4(C.hoff[i], C.hw[i], C.kcand[i], 0) : make_int4(0, 1, 0x7fffffff, 0);
         }
         for (int i = tid; i < 2 * kShI * kShK; i += kFThreads) shist[i] = 0u;
@@ -314,7 +328,6 @@ __global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_consta
     unsigned obs_phase = 0;
     unsigned nvk = 0, nvy = 0;                          // valid pixels this thread classified (K / Y)
     unsigned cbase = 0, cused = kFCandChunk;            // this warp's piece of the candidate list (warp-uniform)
-    const int rl = 32 * (warp & 1) + lane;             // this thread's row of the tile
 
     for (;;) {
         if (tid == 0) {
@@ -337,9 +350,40 @@ __global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_consta
             const int fs = i / kFTD, d = d0 + (i % kFTD);
             ftab[i] = d < num ? A.ffac[(size_t)fs * num + d] : 0.f;            // z = 0: interior pixels
         }
+        const unsigned nplanes = (unsigned)(num - A.dlo);                   // planes below min(ww) hold no balanced values
+        const unsigned long long pstep = (unsigned long long)pitch * 8ull;     // bytes from one plane to the next
+        auto fill_load = [&](int rg, int cg, int xlo, int r0, double (&v)[4], int& at, bool on) {
+            const int x = xlo + 32 * rg + lane;
+            const int rr = r0 - kFRowHalo + x;
+            const int db = d0 - 2 * FM + 4 * cg;
+            at = x * PX + 4 * cg;
+            const bool rok = on && (unsigned)rr < (unsigned)pitch;
+            // one 64-bit address per task, then a step of one plane per load
+            const char* p = reinterpret_cast<const char*>(A.bal) +
+                            ((long long)db * pitch + (long long)(rr & 3) * (long long)sp + (rr >> 2)) * 8ll;
+            const unsigned pl = (unsigned)(db - A.dlo);
+            v[0] = (rok && pl < nplanes) ? __ldg(reinterpret_cast<const double*>(p)) : 0.0;
+            p += pstep;
+            v[1] = (rok && pl + 1u < nplanes) ? __ldg(reinterpret_cast<const double*>(p)) : 0.0;
+            p += pstep;
+            v[2] = (rok && pl + 2u < nplanes) ? __ldg(reinterpret_cast<const double*>(p)) : 0.0;
+            p += pstep;
+            v[3] = (rok && pl + 3u < nplanes) ? __ldg(reinterpret_cast<const double*>(p)) : 0.0;
+        };
+        auto fill_store = [&](const double (&v)[4], int at) {
+            float4 o;
+            o.x = (float)v[0]; o.y = (float)v[1]; o.z = (float)v[2]; o.w = (float)v[3];
+            *reinterpret_cast<float4*>(xs + at) = o;
+        };
+        constexpr int NW = kFThreads / 32;
+        constexpr int NPF = 2 * ((XC / 4 + NW - 1) / NW);                  // tasks per warp for the 64 new rows of a tile:
+                                                                            // task k = row group k & 1, column group warp + 8 (k >> 1)
+        double nx[NPF][4];                                                  // the next tile's new rows, in flight across the tile barrier
+        int nat[NPF];
         for (int tr = t0; tr < t1; ++tr) {
             const int r0 = tr * kFTR;
             if (tid == 0) {                             // raw counts of the tile: needed when the records are closed
+                *npass = 0u;
                 mbar_expect_tx(bar, (uint32_t)(kFTD * kFTR * 4));
                 tma_load_3d(obs, &tm_raw, r0 / 4, 0, d0, bar);
             }
@@ -355,50 +399,27 @@ __global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_consta
                 }
             }
             // ---- fill the fp32 tile ----------------------------------------------------------------------------
-            int xlo = 0;
-            if (tr > t0) {                              // rows r0 - 16 .. r0 + 15 are the previous tile's rows 64 .. 95
+            // A warp task: 32 consecutive matrix rows (one per lane: coalesced in every plane) x 4 planes -> one 128-bit
+            // store per lane.  The first tile of a work item loads all 96 rows here; for the others, rows 0 .. 31 are the
+            // previous tile's rows 64 .. 95 and the 64 new rows were requested at the end of the previous tile (below).
+            if (tr > t0) {
                 for (int i = tid; i < 32 * (PX / 4); i += kFThreads) {
                     const int x = i / (PX / 4), c4 = i % (PX / 4);
                     reinterpret_cast<float4*>(xs + (size_t)x * PX)[c4] = reinterpret_cast<const float4*>(xs + (size_t)(x + 64) * PX)[c4];
                 }
-                xlo = 32;
                 __syncthreads();
-            }
-            {
-                // a warp task: 32 consecutive matrix rows (one per lane: coalesced in every plane) x 4 planes -> one
-                // 128-bit store per lane.  Two tasks in flight per warp.
-                const int ntask = ((kFXR - xlo) / 32) * (XC / 4);
-                const unsigned nplanes = (unsigned)(num - A.dlo);           // planes below min(ww) hold no balanced values
-                auto body = [&](int task, double (&v)[4], int& at) {
-                    const int rg = task / (XC / 4), cg = task - rg * (XC / 4);
-                    const int x = xlo + 32 * rg + lane;
-                    const int rr = r0 - kFRowHalo + x;
-                    const int db = d0 - 2 * FM + 4 * cg;
-                    at = x * PX + 4 * cg;
-                    const bool rok = (unsigned)rr < (unsigned)pitch;
-                    const double* p = A.bal + ((ptrdiff_t)db * pitch + (ptrdiff_t)(rr & 3) * (ptrdiff_t)sp + (rr >> 2));
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        v[j] = 0.0;
-                        if (rok && (unsigned)(db + j - A.dlo) < nplanes) v[j] = p[(ptrdiff_t)j * pitch];
-                    }
-                };
-                auto store = [&](const double (&v)[4], int at) {
-                    float4 o;
-                    o.x = (float)v[0]; o.y = (float)v[1]; o.z = (float)v[2]; o.w = (float)v[3];
-                    *reinterpret_cast<float4*>(xs + at) = o;
-                };
-                constexpr int NW = kFThreads / 32;
-                for (int task = warp; task < ntask; task += 3 * NW) {          // three tasks (12 loads) in flight per thread
-                    double va[4], vb[4], vc[4];
-                    int aa, ab = 0, ac = 0;
-                    const bool t2 = task + NW < ntask, t3 = task + 2 * NW < ntask;
-                    body(task, va, aa);
-                    if (t2) body(task + NW, vb, ab);
-                    if (t3) body(task + 2 * NW, vc, ac);
-                    store(va, aa);
-                    if (t2) store(vb, ab);
-                    if (t3) store(vc, ac);
+                for (int k = 0; k < NPF; ++k)
+                    if (warp + (k >> 1) * NW < XC / 4) fill_store(nx[k], nat[k]);
+            } else {
+#pragma unroll 1
+                for (int cg = warp; cg < XC / 4; cg += NW) {                   // three tasks (12 loads) in flight per thread
+                    double va[3][4];
+                    int aa[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) fill_load(k, cg, 0, r0, va[k], aa[k], true);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) fill_store(va[k], aa[k]);
                 }
             }
             reinterpret_cast<uint4*>(lvt)[tid] = make_uint4(lva.x, lva.y, lvb.x, lvb.y);
@@ -412,9 +433,15 @@ __global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_consta
             obs_phase ^= 1u;
 
             // ---- the sums: two passes of 8 columns per thread ------------------------------------------------------
+            // the 16 (row half, column block) passes of the tile are claimed by the warps as they get free
 #pragma unroll 1
-            for (int ps = 0; ps < 2; ++ps) {
-                const int cb = 2 * (warp >> 1) + ps;
+            for (;;) {
+                int ps = 0;
+                if (lane == 0) ps = (int)smem_atom_add(npass, 1u);
+                ps = __shfl_sync(full, ps, 0);
+                if (ps >= 2 * (kFTD / kFNPX)) break;
+                const int cb = ps >> 1;
+                const int rl = 32 * (ps & 1) + lane;   // this thread's row of the tile
                 unsigned lvpk = 0, mine = 0, slotpk0 = 0, slotpk1 = 0;
                 int cnt = 0;                            // records of this warp and pass (warp-uniform)
 #pragma unroll
@@ -463,8 +490,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_consta
                     const float bb = b1t[rrl] * b2t[rrl + dl];
                     int ck, cy;
                     float lo0, hi0, lo1, hi1;
-                    const int c0 = fast_classify(__uint_as_float(rec.x), __uint_as_float(rec.z << 16), fk, bb, rvlo, rvhi, mc, ck, lo0, hi0);
-                    const int c1 = fast_classify(__uint_as_float(rec.y), __uint_as_float(rec.z & 0xFFFF0000u), fy, bb, rvlo, rvhi, mc, cy, lo1, hi1);
+                    const int c0 = fast_classify(__uint_as_float(rec.x), __uint_as_float(rec.z << 16), fk, bb, ed, mc, ck, lo0, hi0);
+                    const int c1 = fast_classify(__uint_as_float(rec.y), __uint_as_float(rec.z & 0xFFFF0000u), fy, bb, ed, mc, cy, lo1, hi1);
                     const bool ex = act && (c0 == 2 || c1 == 2 || !(bb == bb));
                     const bool ok = act && !ex;
                     unsigned flags = 0, emk = 0;
@@ -473,12 +500,12 @@ __global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_consta
                         flags |= HP_SF_VALID_K;
                         ++nvk;
                         if (ck > mc) {
-                            atomicAdd(&A.cnt[2], 1u);
+                            gmem_red_add(&A.cnt[2], 1u);
                         } else {
                             const int4 inf = cinfo[ck];
                             const int kb = ob < inf.y - 1 ? ob : inf.y - 1;
                             if (ck <= kShI && kb < kShK) smem_red_add(&shist[(ck - 1) * kShK + kb], 1u);
-                            else atomicAdd(&A.hist[(size_t)inf.x + kb], 1u);
+                            else gmem_red_add(&A.hist[(size_t)inf.x + kb], 1u);
                             cand |= ob >= inf.z;
                         }
                         // E.max(): a record whose interval reaches the largest lower bound seen so far is evaluated exactly
@@ -490,12 +517,12 @@ __global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_consta
                         flags |= HP_SF_VALID_Y | HP_SF_CEMY_NONZERO;
                         ++nvy;
                         if (cy > mc) {
-                            atomicAdd(&A.cnt[2], 1u);
+                            gmem_red_add(&A.cnt[2], 1u);
                         } else {
                             const int4 inf = cinfo[cy];
                             const int kb = ob < inf.y - 1 ? ob : inf.y - 1;
                             if (cy <= kShI && kb < kShK) smem_red_add(&shist[(kShI + cy - 1) * kShK + kb], 1u);
-                            else atomicAdd(&A.hist[(size_t)A.total_bins + inf.x + kb], 1u);
+                            else gmem_red_add(&A.hist[(size_t)A.total_bins + inf.x + kb], 1u);
                             cand |= ob >= inf.z;
                         }
                         const unsigned cur = smem_ld_volatile(&runmax[1]);
@@ -523,7 +550,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_consta
                             if (slot < A.fcand_cap)
                                 *reinterpret_cast<int4*>(&A.fcand[slot]) =
                                     make_int4(r, d | (s << 16), ob, (int)((unsigned)ck | ((unsigned)cy << 8) | (flags << 16)));
-                            else atomicAdd(&A.cnt[9], 1u);
+                            else gmem_red_add(&A.cnt[9], 1u);
                         }
                         cused += nc;
                     }
@@ -536,7 +563,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_consta
                         if (ex) {
                             const unsigned slot = base + __popc(mx & lt);
                             if (slot < A.xrec_cap) *reinterpret_cast<int4*>(&A.xrec[slot]) = make_int4(r, d | (s << 16), ob, 0);
-                            else atomicAdd(&A.cnt[11], 1u);
+                            else gmem_red_add(&A.cnt[11], 1u);
                         }
                     }
                     // E.max() contenders wait in the CTA's scratch list: most of them fall below the bound the CTA ends with
@@ -560,6 +587,12 @@ __global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_consta
                 }
                 __syncwarp();
             }
+            // This warp is done with the tile: request its share of the next tile's new rows now, so that the loads fly while
+            // the other warps finish (no register is needed for anything else until the barrier)
+            // (unconditional definitions: the registers are dead during the sums)
+#pragma unroll
+            for (int k = 0; k < NPF; ++k)
+                fill_load(k & 1, warp + (k >> 1) * NW, 32, r0 + kFTR, nx[k], nat[k], tr + 1 < t1 && warp + (k >> 1) * NW < XC / 4);
             __syncthreads();                            // tile, count tile and bias tables are free again
         }
         if (tid == 0) {

@@ -104,27 +104,28 @@ static int run_case(unsigned seed, double sparsity, double spike, double* worst)
 static int check_classify() {
     const int mc = 52;
     std::vector<double> rv(mc + 4);
-    std::vector<float> lo(mc + 4), hi(mc + 4);
     rv[0] = 0.0;
     for (int i = 1; i <= mc; ++i) rv[i] = i == 1 ? 1.0 : pow(2.0, (i - 1) / 3.0);
-    for (int i = 0; i < mc + 4; ++i) {
-        if (i <= mc) { lo[i] = nextafterf((float)rv[i], -INFINITY); hi[i] = nextafterf((float)rv[i], INFINITY); }
-        else lo[i] = hi[i] = INFINITY;
-    }
-    lo[0] = hi[0] = 0.f;
+    auto mant = [](double x, bool up) {                // as hp_hiccups_score builds the thresholds
+        float f = (float)(x * (up ? 1.0 + 1e-9 : 1.0 - 1e-9));
+        f = nextafterf(f, up ? 4.0f : 0.0f);
+        union { float f; unsigned u; } v; v.f = f;
+        return v.u & 0x7fffffu;
+    };
+    const FastEdges ed{mant(rv[2], false), mant(rv[3], false), mant(rv[2], true), mant(rv[3], true)};
     std::mt19937_64 rng(7);
     std::uniform_real_distribution<double> U(0.0, 1.0);
     int bad = 0, certain = 0, total = 0;
     for (int it = 0; it < 2000000; ++it) {
         // expected values spread over the chunks, many of them hugging an edge
         double E;
-        if (U(rng) < 0.5) { const int k = 1 + (int)(U(rng) * (mc + 2)); E = (k <= mc ? rv[k] : rv[mc] * 2.7) * (1.0 + (U(rng) - 0.5) * 1e-4); }
+        if (U(rng) < 0.5) { const int k = 1 + (int)(U(rng) * (mc + 2)); E = (k <= mc ? rv[k] : rv[mc] * 2.7) * (1.0 + (U(rng) - 0.5) * (it % 3 ? 1e-4 : 2e-7)); }
         else E = exp(log(1e-3) + U(rng) * (log(3e5) - log(1e-3)));
         const float f = 0.37f, bb = 1.9f;
         const float S = (float)(E / ((double)f * bb));
         const float es = S * 1e-5f * (float)U(rng) + 1e-30f;
         int chunk; float l, h;
-        const int code = fast_classify(S, es, f, bb, lo.data(), hi.data(), mc, chunk, l, h);
+        const int code = fast_classify(S, es, f, bb, ed, mc, chunk, l, h);
         ++total;
         if (code != 1) continue;
         ++certain;
