@@ -1,8 +1,9 @@
 // K0 -- the worker's input preparation on the device (/root/reference/scripts/pyHICCUPS:143-166).
 //
 // From raw counts and the balancing weights it builds what the reference's worker hands to hiccups():
-//   balanced diagonal d   = count * w[r] * w[r + d] where a count is stored (cooler's `balance=` transform,
-//                           evaluated left to right), 0 elsewhere, NaN -> 0                  (:143, :153-157)
+//   balanced diagonal d   = (w[r] * w[r + d]) * count where a count is stored (cooler's `balance=` transform,
+//                           api.py: mat.data = bias1[mat.row] * bias2[mat.col] * mat.data, evaluated left to right),
+//                           0 elsewhere, NaN -> 0                                             (:143, :153-157)
 //   IR[d]                 = mean of the non-NaN entries of that diagonal, zeros included     (:154-156)
 //   biases                = 1 / w, 0 where w is 0 or NaN                                     (:163-166)
 // so that only 4 bytes per band pixel cross PCIe instead of 12.  `ndarray.mean()` is numpy's pairwise
@@ -97,8 +98,8 @@ __global__ void __launch_bounds__(kPrepThreads) k_prep_band(const unsigned char*
                 const int r = rb + k;
                 v[u][k] = 0.0;
                 if (r < len) {                          // weights loaded whether or not a count is stored: no load waits on another
-                    // balanced value: count * w[r] * w[r + d] where a count is stored, evaluated left to right (:143)
-                    const double p = __dmul_rn(__dmul_rn((double)cc[u][k], w[r]), w[r + d]);
+                    // balanced value where a count is stored: cooler's `bias1[row] * bias2[col] * data`, left to right (:143)
+                    const double p = __dmul_rn(__dmul_rn(w[r], w[r + d]), (double)cc[u][k]);
                     if (cc[u][k] != 0) v[u][k] = p;
                     nk[u] += (v[u][k] == v[u][k]);
                 }

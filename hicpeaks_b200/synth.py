@@ -4,7 +4,7 @@ Produces exactly the objects the reference worker hands to ``hiccups()``
 (/root/reference/scripts/pyHICCUPS:146-166) without going through cooler:
 
 * ``Diags[d]``  -- raw counts on diagonal ``d`` (int32, length ``n - d``), ``d in [0, num)``
-* ``cDiags[i]`` -- balanced values ``count * w[r] * w[c]`` on diagonal ``min(ww) + i`` with
+* ``cDiags[i]`` -- balanced values ``(w[r] * w[c]) * count`` (cooler: ``bias1[row] * bias2[col] * data``) on diagonal ``min(ww) + i`` with
   NaN -> 0 (cooler yields NaN only where a *stored* count meets a NaN weight)
 * ``IR[d]``     -- mean of the non-NaN entries of balanced diagonal ``d`` (zeros count)
 * ``biases``    -- ``1 / w`` (0 where ``w`` is 0 or NaN)
@@ -43,7 +43,7 @@ def _finish(n, num, min_ww, Diags, weights):
         wr = w[: n - d]
         wc = w[d:]
         with np.errstate(invalid="ignore"):
-            bal = raw.astype(np.float64) * wr * wc
+            bal = wr * wc * raw.astype(np.float64)   # cooler's order: bias1[row] * bias2[col] * data, left to right
         bal[raw == 0] = 0.0                      # unstored pixels read back as 0, never NaN
         mask = np.isnan(bal)
         notnan = bal[~mask]

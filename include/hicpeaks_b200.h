@@ -80,7 +80,7 @@ int hp_band_upload(hp_ctx* ctx, const hp_band_desc* band);
 
 /* Worker-level input (replaces the whole input preparation of scripts/pyHICCUPS:143-166): raw count
  * diagonals and the balancing weight of every bin (cooler's `bins[weight]`, NaN for masked bins).  The
- * balanced band (count * w[r] * w[c], NaN -> 0), IR[d] (mean of the non-NaN entries of balanced diagonal d,
+ * balanced band ((w[r] * w[c]) * count as cooler evaluates bias1[row] * bias2[col] * data, NaN -> 0), IR[d] (mean of the non-NaN entries of balanced diagonal d,
  * bit-identical to numpy's mean) and the biases (1 / w, 0 where w is 0 or NaN) are computed on the device:
  * 4 bytes per band pixel cross PCIe instead of 12. */
 typedef struct hp_counts_desc {

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference APA path on dense diagonal arrays.
 
 * ``balanced_diags``  <- cooler's ``matrix(balance=name, sparse=True)`` as consumed at
-                         /root/reference/scripts/apa-analysis:94: ``count * w[r] * w[c]``, NaN where a stored
+                         /root/reference/scripts/apa-analysis:94: ``(w[r] * w[c]) * count`` (cooler: ``bias1[row] * bias2[col] * data``), NaN where a stored
                          count meets a NaN weight, 0 where nothing is stored
 * ``apa_submatrix``   <- /root/reference/hicpeaks/apa.py:11-28
 * ``apa_analysis``    <- apa.py:30-46
@@ -28,7 +28,7 @@ def balanced_diags(Diags, weights, num=None):
     for d in range(num):
         raw = np.asarray(Diags[d])
         with np.errstate(invalid="ignore"):
-            bal = raw.astype(np.float64) * w[: n - d] * w[d:]
+            bal = w[: n - d] * w[d:] * raw.astype(np.float64)      # cooler: bias1[row] * bias2[col] * data
         bal[raw == 0] = 0.0
         out.append(bal)
     return out

@@ -3,7 +3,7 @@
 
     python oracle/make_golden_apa.py
 
-Inputs are stored as raw band counts + weights (the balanced matrix is ``count * w[r] * w[c]``, rebuilt
+Inputs are stored as raw band counts + weights (the balanced matrix is ``(w[r] * w[c]) * count`` (cooler: ``bias1[row] * bias2[col] * data``), rebuilt
 identically by ``oracle.apa_oracle.balanced_diags``); outputs are the reference's valid-window flags,
 per-window means, averaged window and the four summary numbers.
 """

@@ -1,6 +1,7 @@
 """In-memory stand-in for the slice of the cooler API the front ends use (the image has no cooler / h5py):
 ``binsize``, ``chromnames``, ``matrix(balance=, sparse=True).fetch(chrom)``, ``bins().fetch(chrom)[name].values``.
-Balanced values follow cooler: ``count * w[i] * w[j]`` for stored pixels, NaN where a weight is NaN."""
+Balanced values follow cooler (api.py, sparse branch of ``matrix``): ``bias1[row] * bias2[col] * data`` evaluated left to
+right, i.e. ``(w[i] * w[j]) * count`` for stored pixels, NaN where a weight is NaN."""
 import numpy as np
 from scipy import sparse
 
@@ -18,7 +19,7 @@ class _Matrix:
             x = v[nz].astype(np.float64 if self.balance else v.dtype)
             if self.balance:
                 with np.errstate(invalid="ignore"):
-                    x = x * w[nz] * w[nz + d]
+                    x = w[nz] * w[nz + d] * x            # cooler/api.py: mat.data = bias1[mat.row] * bias2[mat.col] * mat.data
             rows.append(nz); cols.append(nz + d); vals.append(x)
             if d:
                 rows.append(nz + d); cols.append(nz); vals.append(x)

@@ -107,3 +107,50 @@ def compare_with_oracle(ctx, inp, pw, ww, maxww, sig, maxapart_bins, min_local_r
     gaps = bal.sum(axis=0) == 0
     assert np.array_equal(ctx.gaps(), gaps)
     return stats
+
+
+def compare_survivor_path_with_oracle(ctx, inp, pw, ww, maxww, sig, maxapart_bins, min_local_reads, q_tol=1e-6, counts=False,
+                                      expect_fast=None):
+    """The cut points of ``compare_with_oracle`` that do not need the per-pixel dump planes: pixel count, frozen width,
+    valid counts, E.max, numbin, (chunk, O) histograms, rejected counts, survivor coordinates / O / ice / E (bit-exact)
+    and p / q within ``q_tol``.  Without the dump the engine takes its default path -- for single-pair programs the
+    re-associated kernel with exact re-evaluation -- so this is the oracle check of that path."""
+    sw, res = ho.score(inp, pw, ww, maxww=maxww, sig=sig, maxapart_bins=maxapart_bins, min_local_reads=min_local_reads)
+    Diags, cDiags, ir = engine_inputs(inp)
+    if counts:
+        ctx.upload_counts(inp["n"], inp["num"], inp["min_ww"], Diags, inp["weights"])
+    else:
+        ctx.upload(inp["n"], inp["num"], inp["min_ww"], Diags, cDiags, ir, inp["biases"], inp["biases"])
+    P = ctx.make_params(pw, ww, maxww, sig, maxapart_bins, min_local_reads)
+    S1 = ctx.score(P)
+    S = ctx.fdr()
+    if expect_fast is not None:
+        assert bool(S1.fast_kernel) == expect_fast
+    assert S.n_pixels == sw["total"] and S.frozen_w == sw["frozen"] and S.n_steps == len(sw["executed"])
+    sv = ctx.survivors()
+    for pi, (p, w0) in enumerate(zip(pw, ww)):
+        for fl, rbit in enumerate((_capi.SF_REJECT_K, _capi.SF_REJECT_Y)):
+            r = res[(p, fl)]
+            L = S.lf[pi][fl]
+            assert L.n_valid == r["x"].size
+            assert L.e_max == (r["E"].max() if r["E"].size else 0.0)
+            assert L.numbin == r["numbin"]
+            nb, widths, off, hist, ptab, qtab = ctx.chunk_table(pi, fl)
+            assert nb == max(0, r["numbin"])
+            for ci in range(1, nb + 1):
+                m = r["chunk"] == ci
+                W = int(widths[ci - 1])
+                kb = np.minimum(r["O"][m].astype(np.int64), W - 1)
+                assert np.array_equal(np.bincount(kb, minlength=W), hist[off[ci - 1]:off[ci]]), "hist chunk %d" % ci
+            assert L.n_reject == int(r["reject"].sum())
+            s = sv[(sv["pair"] == pi) & ((sv["flags"] & rbit) != 0)]
+            s = s[np.lexsort((s["c"], s["r"]))]
+            rej = r["reject"]
+            assert np.array_equal(s["r"], r["x"][rej]) and np.array_equal(s["c"], r["y"][rej]), "survivor coordinates"
+            assert np.array_equal(s["e"][:, fl], r["E"][rej]), "survivor E is not the reference's fp64 value"
+            assert np.array_equal(s["obs"], r["O"][rej]) and np.array_equal(s["ice"], r["ice"][rej])
+            if s.size:
+                assert np.abs(s["q"][:, fl] - r["q"][rej]).max() <= q_tol
+                assert np.abs(s["p"][:, fl] - r["p"][rej]).max() <= q_tol
+    return dict(n_pixels=int(S.n_pixels), frozen=int(S.frozen_w), n_survivors=int(sv.size), fast=int(S1.fast_kernel),
+                n_exact=int(S1.n_exact), ms_score=float(S1.ms_score))

@@ -1,7 +1,12 @@
-"""GPU, BASELINE.json sizes (configs[1]: 20 000-bin chromosome, 5 Mb band): the oracle is far too slow here, so the CUDA
-path is pinned through size-independent properties -- the specialised and the table-driven kernels (independent code,
-different tiling, different summation machinery) must agree bit for bit, the worker-level upload must equal the
-operator-level one, conservation laws of the histograms must hold, and a second run must reproduce the first."""
+"""GPU, BASELINE.json sizes.  Two kinds of checks:
+
+* against the ORACLE on one chromosome of every BASELINE shape (the numpy port needs 15 - 40 s for each): cfg2 (20 000
+  bins, 5 Mb band, (2,5)) at every cut point including the per-pixel fp64 sums, the same chromosome through the default
+  (re-associated + exact re-evaluation) path, a cfg3-shaped union chromosome, a cfg4-shaped (num = 2011, (4,7)) one, and
+  the cfg5 APA pile-up (50 000 anchors, w = 20) against apa_oracle;
+* size-independent properties: the specialised and the table-driven kernels (different tiling, different summation
+  machinery; they share the per-pixel tail) agree bit for bit, the worker-level upload equals the operator-level one,
+  conservation laws of the histograms hold, and a second run reproduces the first."""
 import numpy as np
 import pytest
 
@@ -92,3 +97,62 @@ def test_cfg3_shape_chr1_union_worker_input():
         b = _run(c2, inp, [1, 2, 4], [3, 5, 7])
         assert a[0].spec_kernel == 1 and a[0].band_pixels == band_pixels(n, 3, BAND)
         _same(a, b)
+
+
+# ---- one chromosome of every BASELINE shape against the oracle ------------------------------------------------------
+def test_cfg2_chromosome_matches_oracle_at_every_cut_point(big):
+    """configs[1] at full size: levels, per-pixel bS / bE / E (bit-exact), histograms, p / q, survivors (exact-order kernel,
+    the dump planes need it), then the same chromosome through the default path."""
+    from helpers import compare_survivor_path_with_oracle, compare_with_oracle
+    with _capi.Context(0) as ctx:
+        st = compare_with_oracle(ctx, big, [2], [5], 10, 0.1, BAND, 16)
+        assert st["spec_kernel"] == 1 and st["n_pixels"] > 5_000_000
+        st2 = compare_survivor_path_with_oracle(ctx, big, [2], [5], 10, 0.1, BAND, 16, counts=True, expect_fast=True)
+        assert st2["n_survivors"] == st["n_survivors"]
+
+
+def test_cfg3_shape_union_chromosome_matches_oracle():
+    from helpers import compare_with_oracle
+    inp = synth_chromosome(8200, BAND, 3, maxww=10, seed=31)
+    with _capi.Context(0) as ctx:
+        st = compare_with_oracle(ctx, inp, [1, 2, 4], [3, 5, 7], 10, 0.1, BAND, 16)
+        assert st["spec_kernel"] == 1 and st["n_pixels"] > 2_000_000
+
+
+def test_cfg4_shape_chromosome_matches_oracle():
+    from helpers import compare_survivor_path_with_oracle, compare_with_oracle
+    n, band = 4100, 2000
+    inp = synth_chromosome(n, band, 7, maxww=10, seed=5)
+    with _capi.Context(0) as ctx:
+        st = compare_with_oracle(ctx, inp, [4], [7], 10, 0.1, band, 16)
+        assert st["spec_kernel"] == 1
+        compare_survivor_path_with_oracle(ctx, inp, [4], [7], 10, 0.1, band, 16, expect_fast=True)
+
+
+def test_cfg5_apa_50000_anchors_matches_oracle():
+    """configs[4]: 41 x 41 pile-up over 50 000 anchors @10 kb against the numpy restatement of apa.py:11-46."""
+    import time
+    from hicpeaks_b200 import apa as hapa
+    from oracle import apa_oracle as ao
+    from test_gpu_apa import BandMatrix
+    n, band, w, cw = 20000, 500, 20, 3
+    inp = synth_chromosome(n, band + 2 * w, 5, maxww=10, seed=41)
+    rng = np.random.default_rng(7)
+    i = rng.integers(w, n - band - w - 1, 50000)
+    d = rng.integers(10 + w, band - w, 50000)
+    pos = [(int(a), int(a + b)) for a, b in zip(i, d)]
+    diags = ao.balanced_diags(inp["Diags"], inp["weights"])
+    t0 = time.perf_counter()
+    exp, valid = ao.apa_submatrix(diags, n, pos, w=w)
+    ref = ao.apa_analysis(np.asarray(exp), w=w, cw=cw)
+    t_cpu = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    got = hapa.apa_submatrix(BandMatrix(diags, n), pos, w=w)
+    res = hapa.apa_analysis(got, w=w, cw=cw)
+    t_gpu = time.perf_counter() - t0
+    assert len(got) == len(exp) > 10000
+    assert np.array_equal(got.mean_arr, np.array([x.mean() for x in exp]))          # numpy's pairwise mean, bit for bit
+    assert np.array_equal(res[0], ref[0])                                           # the 41 x 41 pile-up
+    assert tuple(float(x) for x in res[1:]) == tuple(float(x) for x in ref[1:])     # score, z, p, maxi
+    print("cfg5 APA: %d of %d windows kept, numpy port %.2f s, engine %.3f s (upload + kernels + download)" % (
+        len(got), len(pos), t_cpu, t_gpu))
