@@ -36,7 +36,7 @@ LIB_PATH = os.environ.get("HICPEAKS_B200_LIB") or os.path.join(os.path.dirname(o
 SYMBOLS = [
     "hp_abi_version", "hp_device_count", "hp_ctx_create", "hp_ctx_destroy", "hp_last_error",
     "hp_band_upload", "hp_band_upload_counts", "hp_upload_bytes", "hp_narrow_diagonal", "hp_program_dump", "hp_timer_start", "hp_timer_stop", "hp_dump_band", "hp_hiccups_score", "hp_hiccups_fdr", "hp_hiccups", "hp_get_survivors",
-    "hp_hist_bins", "hp_hist_export", "hp_hist_import", "hp_get_gaps", "hp_dump_levels", "hp_dump_plane", "hp_get_chunk_table", "hp_poisson_sf",
+    "hp_hist_bins", "hp_hist_export", "hp_hist_import", "hp_get_summary", "hp_comm_unique_id", "hp_comm_init", "hp_comm_destroy", "hp_allreduce_hist", "hp_ctx_trim", "hp_get_gaps", "hp_dump_levels", "hp_dump_plane", "hp_get_chunk_table", "hp_poisson_sf",
     "hp_apa_upload", "hp_apa_windows", "hp_apa_load_windows", "hp_apa_accumulate", "hp_apa_get_windows",
 ]
 
@@ -128,6 +128,12 @@ def load_library(path: str | None = None):
     lib.hp_hist_bins.argtypes = [vp, C.POINTER(i64)]
     lib.hp_hist_export.argtypes = [vp, vp, i64]
     lib.hp_hist_import.argtypes = [vp, vp, i64]
+    lib.hp_get_summary.argtypes = [vp, C.POINTER(HiccupsSummary)]
+    lib.hp_comm_unique_id.argtypes = [vp]
+    lib.hp_comm_init.argtypes = [vp, i32, i32, vp]
+    lib.hp_comm_destroy.argtypes = [vp]
+    lib.hp_allreduce_hist.argtypes = [vp, vp, i32, C.POINTER(C.c_float)]
+    lib.hp_ctx_trim.argtypes = [vp]
     lib.hp_get_gaps.argtypes = [vp, vp, i64]
     lib.hp_dump_levels.argtypes = [vp, vp, i64]
     lib.hp_dump_plane.argtypes = [vp, i32, i32, i32, vp, i64]
@@ -375,6 +381,38 @@ class Context:
         h = np.ascontiguousarray(hist, dtype=np.int64)
         self._check(self.lib.hp_hist_import(self._h, _ptr(h), h.size))
 
+    # -- genome-wide FDR: one NCCL all-reduce of the histograms (include/hicpeaks_b200.h) ----------------------------
+    def comm_init(self, nranks=1, rank=0, unique_id=None):
+        """Bind this context to rank ``rank`` of an ``nranks``-GPU communicator (``unique_id``: bytes from
+        ``comm_unique_id()`` on rank 0; not needed for nranks == 1)."""
+        buf = None
+        if nranks > 1:
+            if unique_id is None or len(unique_id) != COMM_ID_BYTES:
+                raise ValueError("unique_id must be the %d bytes of comm_unique_id()" % COMM_ID_BYTES)
+            buf = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        self._check(self.lib.hp_comm_init(self._h, int(nranks), int(rank), buf))
+
+    def comm_destroy(self):
+        self._check(self.lib.hp_comm_destroy(self._h))
+
+    def allreduce_hist(self, ctxs):
+        """Merge the histograms / E.max / valid counts of the scored contexts ``ctxs`` (this process, this GPU) and of all
+        ranks; returns the device milliseconds of the merge.  Every rank calls it, ``ctxs`` may be empty."""
+        arr = (C.c_void_p * max(1, len(ctxs)))(*[c._h for c in ctxs])
+        ms = C.c_float()
+        self._check(self.lib.hp_allreduce_hist(self._h, arr, len(ctxs), C.byref(ms)))
+        return float(ms.value)
+
+    def summary(self):
+        """Summary of the last score() as it stands now (after allreduce_hist: genome-wide e_max / numbin / n_valid)."""
+        S = HiccupsSummary()
+        self._check(self.lib.hp_get_summary(self._h, C.byref(S)))
+        return S
+
+    def trim(self):
+        """Give back the upload scratch (landing zone, pinned staging); the band and the last results stay valid."""
+        self._check(self.lib.hp_ctx_trim(self._h))
+
     def gaps(self):
         out = np.empty(self.n, dtype=np.bool_)
         self._check(self.lib.hp_get_gaps(self._h, _ptr(out), self.n))
@@ -451,6 +489,19 @@ class Context:
         out = np.empty_like(k)
         self._check(self.lib.hp_poisson_sf(self._h, _ptr(k), _ptr(mu), _ptr(out), k.size))
         return out
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """NCCL unique id (rank 0 creates it and hands it to the other ranks)."""
+    lib = load_library()
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = lib.hp_comm_unique_id(buf)
+    if rc != HP_OK:
+        raise EngineError(rc, (lib.hp_last_error(None) or b"").decode())
+    return buf.raw
 
 
 def device_count() -> int:

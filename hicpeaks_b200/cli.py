@@ -148,6 +148,44 @@ def prepare_chromosome(Lib, key, weight_name, maxapart, maxww, min_ww, res):
     return dict(n=int(chromLen), num=int(num), min_ww=int(min_ww), Diags=Diags, cDiags=cDiags, IR=IR, biases=biases)
 
 
+# weight columns cooler treats as divisive (cooler/api.py: `divisive_weights` defaults to True for these names): the
+# balanced value is count / (w_i w_j), while the reference's biases stay 1 / column (scripts/pyHICCUPS:163-166)
+DIVISIVE_WEIGHT_NAMES = ("KR", "VC", "VC_SQRT")
+
+
+def worker_input(Lib, key, weight_name, maxapart, maxww, min_ww, res):
+    """Input of one chromosome for the engine.  The fast boundary -- raw int32 count diagonals + the weight column, the
+    balanced band / IR / biases derived on the GPU -- applies when that derivation is what cooler + the reference's worker
+    do: multiplicative weights (balanced = bias1[row] * bias2[col] * data) and integer counts.  Otherwise (a divisive
+    weight column, float or out-of-range counts) the containers are built on the host exactly as the worker builds
+    them, through ``Lib.matrix(balance=name)`` (``prepare_chromosome``), and the operator-level entry is used."""
+    if weight_name not in DIVISIVE_WEIGHT_NAMES:
+        b = prepare_counts(Lib, key, weight_name, maxapart, maxww, res)
+        ok = True
+        for d in b["Diags"]:
+            a = np.asarray(d)
+            if not (np.issubdtype(a.dtype, np.integer) and a.dtype.itemsize <= 4 and a.dtype != np.uint32):
+                if not (np.issubdtype(a.dtype, np.integer) and a.size and np.abs(a).max() < 2 ** 31) and a.size:
+                    ok = False
+                    break
+        if ok:
+            return b
+    return prepare_chromosome(Lib, key, weight_name, maxapart, maxww, min_ww, res)
+
+
+def chrom_sizes(Lib, keys, res, num):
+    """{key: (bins, stored diagonals)} for the longest-first order / the LPT partition."""
+    sizes = {}
+    cs = getattr(Lib, "chromsizes", None)
+    for k in keys:
+        try:
+            n = int(-(-int(cs[k]) // res))
+        except Exception:
+            n = 1
+        sizes[k] = (n, num)
+    return sizes
+
+
 def prepare_counts(Lib, key, weight_name, maxapart, maxww, res):
     """Worker-level input for the engine: the raw count diagonals and the bin weights only; the balanced band, ``IR``
     and the biases of pyHICCUPS:149-166 are derived on the GPU (``hicpeaks_b200.callers.hiccups_from_counts``)."""
@@ -171,7 +209,7 @@ def _n_gpus(args):
     have = _capi.device_count()
     if have == 0:
         raise _capi.EngineError(_capi.HP_ERR_NO_DEVICE, "no CUDA device (this engine has no CPU fallback)")
-    want = args.gpus or (args.nproc if args.nproc > 1 else 0) or have
+    want = args.gpus or have                 # --gpus 0: all visible; --nproc only sets the number of host threads
     return max(1, min(want, have))
 
 
@@ -243,20 +281,49 @@ def run_hiccups(argv=None, Lib=None):
                   use_raw=args.use_raw, min_marginal_peaks=args.min_marginal_peaks, onlyanchor=args.only_anchors,
                   min_local_reads=args.min_local_reads)
 
-        def load(key):
-            return prepare_chromosome(Lib, key, args.clr_weight_name, args.maxapart, args.maxww, min(args.ww), res)
-
         ngpu = _n_gpus(args)
+        num = args.maxapart // res + args.maxww + 1
+        sizes = chrom_sizes(Lib, keys, res, num)
+
+        def load_any(key):
+            return worker_input(Lib, key, args.clr_weight_name, args.maxapart, args.maxww, min(args.ww), res)
+
         if args.fdr_scope == 'genome':
-            sizes = {k: (1, 1) for k in keys}
-            runner = dispatch.GenomeRunner(engine=dispatch.CudaEngine(0), fdr_scope='genome')
-            tables = runner.run({k: (lambda k=k: load(k)) for k in keys}, sizes, **kw)
+            # one host thread (= rank) per GPU; chromosomes LPT-partitioned over them; the lambda-chunk histograms are
+            # merged on the devices with one NCCL all-reduce (hp_allreduce_hist) before BH
+            comms = dispatch.ThreadComm.group(ngpu) if ngpu > 1 else [dispatch.LocalComm()]
+            results, errors = [None] * ngpu, []
+
+            def rank_main(g):
+                eng = dispatch.CudaEngine(g)
+                try:
+                    runner = dispatch.GenomeRunner(comm=comms[g], engine=eng, fdr_scope='genome')
+                    results[g] = runner.run({k: (lambda k=k: load_any(k)) for k in keys}, sizes, **kw)
+                    if g == 0 and runner.merge_ms is not None:
+                        log.info('Genome-wide lambda-chunk histograms merged over %d GPU(s) in %.3f ms (device)', ngpu, runner.merge_ms)
+                except BaseException as e:
+                    errors.append(e)
+                    if ngpu > 1:
+                        comms[g].shared.barrier.abort()
+                finally:
+                    eng.close()
+
+            threads = [threading.Thread(target=rank_main, args=(g,)) for g in range(ngpu)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            if errors:
+                raise errors[0]
+            tables = results[0]
         else:
             def one(key, gpu):
-                b = prepare_counts(Lib, key, args.clr_weight_name, args.maxapart, args.maxww, res)
+                b = load_any(key)
+                if "cDiags" in b:
+                    return callers.hiccups(None, None, b["biases"], b["biases"], b["IR"], b["n"], b["Diags"], b["cDiags"], b["num"],
+                                           key.lstrip('chr'), device=gpu, **kw)
                 return callers.hiccups_from_counts(b["weights"], b["n"], b["Diags"], b["num"], key.lstrip('chr'), device=gpu, **kw)
-            sizes = {k: 1 for k in keys}
-            tables = _map_over_gpus(keys, sizes, ngpu, one, _n_workers(args, ngpu))
+            tables = _map_over_gpus(keys, {k: sizes[k][0] * sizes[k][1] for k in keys}, ngpu, one, _n_workers(args, ngpu))
         with open(args.output, 'w') as OF:
             for key in keys:
                 write_table(OF, HICCUPS_LINE, key.lstrip('chr'), tables[key], res)
@@ -279,13 +346,16 @@ def run_bhfdr(argv=None, Lib=None):
         log.info('Calling Peaks ...')
 
         def one(key, gpu):
-            b = prepare_counts(Lib, key, args.clr_weight_name, args.maxapart, args.maxww, res)
-            return callers.bhfdr_from_counts(b["weights"], b["n"], b["Diags"], b["num"], key.lstrip('chr'), pw=args.pw,
-                                             ww=args.ww, sig=args.siglevel, maxww=args.maxww, maxapart=args.maxapart, res=res,
-                                             device=gpu)
+            b = worker_input(Lib, key, args.clr_weight_name, args.maxapart, args.maxww, args.ww, res)
+            kwb = dict(pw=args.pw, ww=args.ww, sig=args.siglevel, maxww=args.maxww, maxapart=args.maxapart, res=res, device=gpu)
+            if "cDiags" in b:
+                return callers.bhfdr(None, None, b["biases"], b["biases"], b["IR"], b["n"], b["Diags"], b["cDiags"], b["num"],
+                                     key.lstrip('chr'), **kwb)
+            return callers.bhfdr_from_counts(b["weights"], b["n"], b["Diags"], b["num"], key.lstrip('chr'), **kwb)
 
         ngpu = _n_gpus(args)
-        tables = _map_over_gpus(keys, {k: 1 for k in keys}, ngpu, one, _n_workers(args, ngpu))
+        sizes = chrom_sizes(Lib, keys, res, args.maxapart // res + args.maxww + 1)
+        tables = _map_over_gpus(keys, {k: sizes[k][0] * sizes[k][1] for k in keys}, ngpu, one, _n_workers(args, ngpu))
         with open(args.output, 'w') as OF:
             for key in keys:
                 write_table(OF, BHFDR_LINE, key.lstrip('chr'), tables[key], res)

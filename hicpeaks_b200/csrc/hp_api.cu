@@ -1,7 +1,9 @@
 // Host side of the C ABI declared in include/hicpeaks_b200.h: context, band upload, the sweep
 // program builder (callers.py:15-23,132-198), the frozen_w replay (callers.py:203-232) and the
 // launch sequence  K1 levels -> replay -> bE table -> K2 score -> K3 BH -> survivor filter.
+#include <dlfcn.h>
 #include <math.h>
+#include <nccl.h>
 #include <pthread.h>
 #include <sched.h>
 #include <stdio.h>
@@ -93,6 +95,10 @@ struct hp_ctx {
     bool fast_used = false;
     bool edges_regular = false;           // every chunk edge is 2^e times rv[2] or rv[3]: the fast kernel's mantissa compares apply
     bool domain_ok = false;               // every balanced value is inside the domain of the fast kernel's error bound
+    // genome-wide FDR (hp_comm_init / hp_allreduce_hist): NCCL communicator + the u64 accumulator of the histograms
+    ncclComm_t comm = nullptr;
+    int comm_nranks = 0, comm_rank = 0;
+    unsigned long long* d_acc = nullptr; size_t cap_acc = 0;
     int4* d_fscratch = nullptr;           // [2 * sm_count][kFScratch] E.max() contenders of the fast kernel's CTAs
     hp_survivor* d_surv = nullptr; size_t cap_surv = 0;
     double* d_dump = nullptr; size_t cap_dump = 0;
@@ -307,13 +313,15 @@ extern "C" int hp_ctx_create(int device, int max_chunks, const double* edges, hp
     return HP_OK;
 }
 
+static void comm_release(hp_ctx* ctx);
 extern "C" void hp_ctx_destroy(hp_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) stream_sync(ctx);
+    comm_release(ctx);
     void* ptrs[] = {ctx->d_ptab, ctx->d_raw, ctx->d_bal, ctx->d_lvl, ctx->d_ir, ctx->d_b1, ctx->d_b2, ctx->d_rownz,
                     ctx->d_lhist, ctx->d_betab, ctx->d_hist, ctx->d_qtab, ctx->d_small, ctx->d_cnt, ctx->d_numbin,
-                    ctx->d_cand, ctx->d_fcand, ctx->d_xrec, ctx->d_ffac, ctx->d_fscratch, ctx->d_surv, ctx->d_dump, ctx->d_tmp, ctx->d_tab, ctx->d_w, ctx->d_pk, ctx->d_prep, ctx->d_apa_bal, ctx->d_apa_plan, ctx->d_apa_pos,
+                    ctx->d_cand, ctx->d_fcand, ctx->d_xrec, ctx->d_ffac, ctx->d_fscratch, ctx->d_acc, ctx->d_surv, ctx->d_dump, ctx->d_tmp, ctx->d_tab, ctx->d_w, ctx->d_pk, ctx->d_prep, ctx->d_apa_bal, ctx->d_apa_plan, ctx->d_apa_pos,
                     ctx->d_apa_wins, ctx->d_apa_valid, ctx->d_apa_mean, ctx->d_apa_sel, ctx->d_apa_avg};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -1249,6 +1257,13 @@ extern "C" int hp_hiccups_fdr(hp_ctx* ctx, const int32_t* numbin_override, hp_hi
     return HP_OK;
 }
 
+extern "C" int hp_get_summary(hp_ctx* ctx, hp_hiccups_summary* out) {
+    if (!ctx || !out) return fail(ctx, HP_ERR_INVALID, "NULL argument");
+    if (!ctx->scored) return fail(ctx, HP_ERR_STATE, "hp_hiccups_score must come first");
+    *out = ctx->sum;
+    return HP_OK;
+}
+
 extern "C" int hp_hiccups(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hiccups_summary* out) {
     int rc = hp_hiccups_score(ctx, prm, nullptr);
     if (rc) return rc;
@@ -1547,5 +1562,197 @@ extern "C" int hp_apa_get_windows(hp_ctx* ctx, const int64_t* sel, int64_t nsel,
                            ctx->stream));
     }
     CK(stream_sync(ctx));
+    return HP_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Genome-wide FDR across chromosomes and GPUs (BASELINE.json's north star; NOT the reference's behaviour, which corrects
+// per chromosome -- scripts/pyHICCUPS:139-198 + callers.py:263-275).  Replaces nothing in the reference; it is the one
+// collective of the path: the (pair, background, lambda-chunk, observed) histograms are summed on the device over the
+// contexts of this process and all-reduced over the ranks with NCCL, E.max() with a max, the valid counts with a sum.
+// NCCL is bound at run time (dlopen of libnccl.so.2): a process that already holds a copy (torch's) shares it, and the
+// library loads on a box without NCCL as long as nobody asks for a multi-rank communicator.
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+};
+static NcclApi* nccl_api() {
+    static NcclApi* api = []() {
+        NcclApi* a = new NcclApi();
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            a->lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (a->lib) break;
+        }
+        if (!a->lib) { a->err = std::string("cannot load libnccl.so.2: ") + dlerror(); return a; }
+        auto sym = [&](const char* n) { void* p = dlsym(a->lib, n); if (!p) a->err = std::string("libnccl lacks ") + n; return p; };
+        a->GetUniqueId = (decltype(a->GetUniqueId))sym("ncclGetUniqueId");
+        a->CommInitRank = (decltype(a->CommInitRank))sym("ncclCommInitRank");
+        a->CommDestroy = (decltype(a->CommDestroy))sym("ncclCommDestroy");
+        a->AllReduce = (decltype(a->AllReduce))sym("ncclAllReduce");
+        a->GroupStart = (decltype(a->GroupStart))sym("ncclGroupStart");
+        a->GroupEnd = (decltype(a->GroupEnd))sym("ncclGroupEnd");
+        a->GetErrorString = (decltype(a->GetErrorString))sym("ncclGetErrorString");
+        return a;
+    }();
+    return api;
+}
+#define NCK(call)                                                                                               \
+    do {                                                                                                        \
+        ncclResult_t r_ = (call);                                                                               \
+        if (r_ != ncclSuccess) return fail(ctx, HP_ERR_CUDA, std::string(#call) + ": " + N->GetErrorString(r_)); \
+    } while (0)
+
+static void comm_release(hp_ctx* ctx) {
+    if (ctx->comm) {
+        NcclApi* N = nccl_api();
+        if (N->CommDestroy) N->CommDestroy(ctx->comm);
+        ctx->comm = nullptr;
+    }
+    ctx->comm_nranks = 0;
+}
+
+extern "C" int hp_comm_unique_id(void* id) {
+    hp_ctx* ctx = nullptr;
+    if (!id) return fail(ctx, HP_ERR_INVALID, "NULL id");
+    NcclApi* N = nccl_api();
+    if (!N->err.empty()) return fail(ctx, HP_ERR_CUDA, N->err);
+    static_assert(sizeof(ncclUniqueId) == HP_COMM_ID_BYTES, "HP_COMM_ID_BYTES must be sizeof(ncclUniqueId)");
+    NCK(N->GetUniqueId((ncclUniqueId*)id));
+    return HP_OK;
+}
+
+extern "C" int hp_comm_init(hp_ctx* ctx, int32_t nranks, int32_t rank, const void* id) {
+    if (!ctx) return fail(ctx, HP_ERR_INVALID, "NULL ctx");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, HP_ERR_INVALID, "need 0 <= rank < nranks");
+    CK(cudaSetDevice(ctx->device));
+    comm_release(ctx);
+    if (nranks > 1) {
+        if (!id) return fail(ctx, HP_ERR_INVALID, "a multi-rank communicator needs the unique id of rank 0 (hp_comm_unique_id)");
+        NcclApi* N = nccl_api();
+        if (!N->err.empty()) return fail(ctx, HP_ERR_CUDA, N->err);
+        ncclUniqueId uid;
+        memcpy(&uid, id, sizeof(uid));
+        NCK(N->CommInitRank(&ctx->comm, nranks, uid, rank));
+    }
+    ctx->comm_nranks = nranks; ctx->comm_rank = rank;
+    return HP_OK;
+}
+
+extern "C" int hp_comm_destroy(hp_ctx* ctx) {
+    if (!ctx) return fail(ctx, HP_ERR_INVALID, "NULL ctx");
+    CK(cudaSetDevice(ctx->device));
+    comm_release(ctx);
+    return HP_OK;
+}
+
+__global__ void k_hist_accum(unsigned long long* __restrict__ acc, const unsigned int* __restrict__ h, size_t n,
+                             unsigned long long* __restrict__ acc_small, const unsigned long long* __restrict__ small) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const unsigned v = h[i]; if (v) acc[i] += v; }
+    if (i < 16) {                                       // [0, 16) E.max bits (max), [16, 32) valid counts (sum)
+        const unsigned long long e = small[i];
+        if (e > acc_small[i]) acc_small[i] = e;
+        acc_small[16 + i] += small[16 + i];
+    }
+}
+__global__ void k_hist_store(const unsigned long long* __restrict__ acc, unsigned int* __restrict__ h, size_t n,
+                             const unsigned long long* __restrict__ acc_small, unsigned long long* __restrict__ small,
+                             unsigned int* __restrict__ overflow) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const unsigned long long v = acc[i];
+        if (v > 0xffffffffull) *overflow = 1u;
+        h[i] = (unsigned)v;
+    }
+    if (i < 16) { small[i] = acc_small[i]; small[16 + i] = acc_small[16 + i]; }
+}
+
+extern "C" int hp_allreduce_hist(hp_ctx* ctx, hp_ctx* const* ctxs, int32_t nctx, float* ms_out) {
+    if (!ctx || (nctx > 0 && !ctxs) || nctx < 0) return fail(ctx, HP_ERR_INVALID, "bad argument");
+    if (ctx->comm_nranks < 1) return fail(ctx, HP_ERR_STATE, "hp_comm_init must come first");
+    CK(cudaSetDevice(ctx->device));
+    // geometry: every rank passes contexts scored with the same (pw, ww) list and chunk tables; a rank may hold none
+    int npw = 0;
+    for (int k = 0; k < nctx; ++k) {
+        hp_ctx* c = ctxs[k];
+        if (!c || !c->scored) return fail(ctx, HP_ERR_STATE, "every context must have been scored (hp_hiccups_score)");
+        if (c->device != ctx->device) return fail(ctx, HP_ERR_INVALID, "contexts of one call live on the communicator's GPU");
+        if (c->prm.flags & HP_PF_BHFDR) return fail(ctx, HP_ERR_INVALID, "the BH-FDR caller has no lambda-chunk histograms");
+        if (c->chunks.total_bins != ctx->chunks.total_bins) return fail(ctx, HP_ERR_INVALID, "contexts differ in max_chunks");
+        if (npw && c->prm.npw != npw) return fail(ctx, HP_ERR_INVALID, "contexts differ in the number of (pw, ww) pairs");
+        npw = c->prm.npw;
+    }
+    cudaStream_t st = ctx->stream;
+    const size_t tb = ctx->chunks.total_bins;
+    // ranks must agree on the message size: HP_MAX_PW pairs are always reduced (unused rows stay zero)
+    const size_t cnt = (size_t)HP_MAX_PW * 2 * tb;
+    CK(ensure(&ctx->d_acc, &ctx->cap_acc, cnt + 33));
+    CK(cudaMemsetAsync(ctx->d_acc, 0, (cnt + 33) * sizeof(unsigned long long), st));
+    if (!ctx->ev_t0) { CK(cudaEventCreate(&ctx->ev_t0)); CK(cudaEventCreate(&ctx->ev_t1)); }
+    CK(cudaEventRecord(ctx->ev[6], st));
+    for (int k = 0; k < nctx; ++k) {                    // contexts of one process: plain device-side sums, in stream order
+        hp_ctx* c = ctxs[k];
+        const size_t n = (size_t)c->prm.npw * 2 * tb;
+        k_hist_accum<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_acc, c->d_hist, n, ctx->d_acc + cnt, c->d_small);
+        CK(cudaGetLastError());
+    }
+    if (ctx->comm_nranks > 1) {
+        NcclApi* N = nccl_api();
+        NCK(N->GroupStart());
+        NCK(N->AllReduce(ctx->d_acc, ctx->d_acc, cnt, ncclUint64, ncclSum, ctx->comm, st));
+        NCK(N->AllReduce(ctx->d_acc + cnt, ctx->d_acc + cnt, 16, ncclUint64, ncclMax, ctx->comm, st));
+        NCK(N->AllReduce(ctx->d_acc + cnt + 16, ctx->d_acc + cnt + 16, 16, ncclUint64, ncclSum, ctx->comm, st));
+        NCK(N->GroupEnd());
+    }
+    unsigned int* d_over = (unsigned int*)(ctx->d_acc + cnt + 32);
+    for (int k = 0; k < nctx; ++k) {
+        hp_ctx* c = ctxs[k];
+        const size_t n = (size_t)c->prm.npw * 2 * tb;
+        k_hist_store<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_acc, c->d_hist, n, ctx->d_acc + cnt, c->d_small, d_over);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(ctx->ev[7], st));
+    unsigned long long small[33];
+    CK(cudaMemcpyAsync(ctx->h_res + 6400, ctx->d_acc + cnt, sizeof(small), cudaMemcpyDeviceToHost, st));
+    CK(stream_sync(ctx));
+    memcpy(small, ctx->h_res + 6400, sizeof(small));
+    if ((unsigned int)small[32]) return fail(ctx, HP_ERR_CAPACITY, "a merged histogram bin exceeds 2^32 - 1");
+    for (int k = 0; k < nctx; ++k) {
+        hp_ctx* c = ctxs[k];
+        for (int i = 0; i < c->prm.npw; ++i)
+            for (int fl = 0; fl < 2; ++fl) {
+                hp_lf_stat& L = c->sum.lf[i][fl];
+                L.n_valid = (int64_t)small[16 + i * 2 + fl];
+                double em;
+                memcpy(&em, &small[i * 2 + fl], 8);
+                L.e_max = em;
+                L.numbin = (L.n_valid > 0) ? (int)ceil(log(em) / log(2.0) * 3 + 1) : 0;
+            }
+        c->fdr_done = false;
+    }
+    if (ms_out) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); *ms_out = ms; }
+    return HP_OK;
+}
+
+// upload scratch (device landing zone, pinned staging, prep tables) is only needed during an upload: a caller that
+// keeps many scored contexts alive (genome-wide FDR: one per chromosome until the merged BH) gives it back
+extern "C" int hp_ctx_trim(hp_ctx* ctx) {
+    if (!ctx) return fail(ctx, HP_ERR_INVALID, "NULL ctx");
+    CK(cudaSetDevice(ctx->device));
+    CK(stream_sync(ctx));
+    if (ctx->d_tmp) { cudaFree(ctx->d_tmp); ctx->d_tmp = nullptr; ctx->cap_plane = 0; }
+    // cap_plane guards d_raw / d_bal / d_lvl as well: the next upload reallocates them (the band on the device is kept
+    // valid until then)
+    if (ctx->h_stage) { cudaFreeHost(ctx->h_stage); ctx->h_stage = nullptr; ctx->cap_stage = 0; }
+    if (ctx->d_prep) { cudaFree(ctx->d_prep); ctx->d_prep = nullptr; ctx->cap_prep = 0; }
+    if (ctx->d_dump) { cudaFree(ctx->d_dump); ctx->d_dump = nullptr; ctx->cap_dump = 0; }
     return HP_OK;
 }

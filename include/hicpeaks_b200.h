@@ -178,6 +178,8 @@ int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hiccups_summa
 /* Poisson + BH per lambda-chunk, survivor selection.  numbin_override: NULL, or [npw*2] chunk
  * counts to use instead of ceil(log(Emax)/log(2)*3+1) evaluated with the C library.        */
 int hp_hiccups_fdr(hp_ctx* ctx, const int32_t* numbin_override, hp_hiccups_summary* out);
+/* the summary of the last hp_hiccups_score as it stands now (after hp_allreduce_hist: genome-wide e_max / numbin / n_valid) */
+int hp_get_summary(hp_ctx* ctx, hp_hiccups_summary* out);
 /* both of the above */
 int hp_hiccups(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hiccups_summary* out);
 
@@ -205,6 +207,24 @@ int hp_get_survivors(hp_ctx* ctx, hp_survivor* buf, int64_t capacity, int64_t* c
 int hp_hist_bins(hp_ctx* ctx, int64_t* total_bins);
 int hp_hist_export(hp_ctx* ctx, int64_t* out, int64_t capacity);
 int hp_hist_import(hp_ctx* ctx, const int64_t* in, int64_t count);
+
+/* The same merge on the device and across GPUs: the one collective of the path (replaces nothing in the reference, whose
+ * dispatcher scripts/pyHICCUPS:192-198 gathers finished peak tables only).  hp_comm_init binds a context to rank `rank`
+ * of an `nranks`-GPU NCCL communicator (one context per GPU; id = the HP_COMM_ID_BYTES bytes hp_comm_unique_id produced
+ * on rank 0, passed to the other ranks by the caller; nranks == 1 needs no id and no NCCL).  hp_allreduce_hist, between
+ * hp_hiccups_score and hp_hiccups_fdr: sums the u32 histograms of the `nctx` scored contexts of this process (all on
+ * comm's GPU, same (pw, ww) list) into u64 on the device, ncclAllReduce(sum) over the ranks, max for E.max(), sum for
+ * the valid counts, and writes the merged tables back into every context, whose summary (e_max, numbin, n_valid)
+ * becomes the genome-wide one; hp_hiccups_fdr then runs BH on the merged counts.  Every rank must call it (nctx may
+ * be 0).  *ms (optional): device time from the first local sum to the last write-back. */
+#define HP_COMM_ID_BYTES 128
+int hp_comm_unique_id(void* id);
+int hp_comm_init(hp_ctx* ctx, int32_t nranks, int32_t rank, const void* id);
+int hp_comm_destroy(hp_ctx* ctx);
+int hp_allreduce_hist(hp_ctx* comm, hp_ctx* const* ctxs, int32_t nctx, float* ms);
+/* gives back the upload scratch of a context (device landing zone, pinned staging); the uploaded band and the results
+ * of the last score stay valid.  For callers that keep many scored contexts alive (one per chromosome until the merged BH). */
+int hp_ctx_trim(hp_ctx* ctx);
 
 /* rows of cM whose stored band is all zero ('gaps', callers.py:238): out[r] = 1 if row r is a gap
  * (available after hp_band_upload) */

@@ -44,6 +44,7 @@ class FakeCooler:
         """data: {chrom: (Diags list of int arrays for d = 0 .. num-1, weights)}"""
         self.binsize, self.data, self.weight_name = binsize, data, weight_name
         self.chromnames = list(data)
+        self.chromsizes = {k: len(v[0][0]) * binsize for k, v in data.items()}
 
     def matrix(self, balance=False, sparse=True):
         return _Matrix(self, balance)

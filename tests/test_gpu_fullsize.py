@@ -153,6 +153,6 @@ def test_cfg5_apa_50000_anchors_matches_oracle():
     assert len(got) == len(exp) > 10000
     assert np.array_equal(got.mean_arr, np.array([x.mean() for x in exp]))          # numpy's pairwise mean, bit for bit
     assert np.array_equal(res[0], ref[0])                                           # the 41 x 41 pile-up
-    assert tuple(float(x) for x in res[1:]) == tuple(float(x) for x in ref[1:])     # score, z, p, maxi
+    assert tuple(float(x) for x in res[1:5]) == tuple(float(x) for x in ref[1:5])   # score, z, p, maxi
     print("cfg5 APA: %d of %d windows kept, numpy port %.2f s, engine %.3f s (upload + kernels + download)" % (
         len(got), len(pos), t_cpu, t_gpu))
