@@ -36,6 +36,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the one JSON line and nothing else
 
 WORKLOAD = dict(n=20000, band=500, pw=[2], ww=[5], maxww=10, min_local_reads=16, sig=0.1)
 ALG_BYTES_PER_PIXEL = 12        # int32 raw count + fp64 balanced value, each read once
@@ -134,8 +135,8 @@ def engine_arrays(inp):
     return Diags, cDiags, ir
 
 
-def oracle_rate(n_sample, seed):
-    """One chromosome sample through the CPU restatement; returns (pixels, seconds)."""
+def oracle_rate(n_sample, seed, keep=False):
+    """One chromosome sample through the CPU restatement; returns (pixels, seconds) [+ (input, oracle result) with keep]."""
     from hicpeaks_b200.synth import band_pixels, synth_chromosome
     from oracle import glue_oracle, hiccups_oracle as ho
     W = WORKLOAD
@@ -144,7 +145,35 @@ def oracle_rate(n_sample, seed):
     sw, out = ho.score(inp, W["pw"], W["ww"], maxww=W["maxww"], sig=W["sig"], maxapart_bins=W["band"],
                        min_local_reads=W["min_local_reads"])
     glue_oracle.finish_hiccups(inp, sw, out, W["pw"], W["ww"], 10000, 0.01, 1.75, 2, False, 2, False)
-    return band_pixels(n_sample, min(W["ww"]), W["band"]), time.perf_counter() - t
+    dt = time.perf_counter() - t
+    if keep:
+        return band_pixels(n_sample, min(W["ww"]), W["band"]), dt, inp, out
+    return band_pixels(n_sample, min(W["ww"]), W["band"]), dt
+
+
+def parity_against_oracle(ctx, P, inp, res):
+    """Outside every timed region: the engine on the cpu_baseline sample against the oracle's result for it -- survivor
+    coordinates, observed counts and expected values bit for bit, q within 1e-6 (the parity gate of BASELINE.md)."""
+    from hicpeaks_b200 import _capi
+    W = WORKLOAD
+    Dg = [np.ascontiguousarray(d, dtype=np.int32) for d in inp["Diags"]]
+    ctx.upload_counts(inp["n"], inp["num"], inp["min_ww"], Dg, inp["weights"])
+    S = ctx.hiccups(P)
+    sv = ctx.survivors()
+    n_checked = 0
+    for fl, rbit in enumerate((_capi.SF_REJECT_K, _capi.SF_REJECT_Y)):
+        r = res[(W["pw"][0], fl)]
+        s = sv[(sv["flags"] & rbit) != 0]
+        s = s[np.lexsort((s["c"], s["r"]))]
+        rej = r["reject"]
+        ok = (np.array_equal(s["r"], r["x"][rej]) and np.array_equal(s["c"], r["y"][rej]) and
+              np.array_equal(s["e"][:, fl], r["E"][rej]) and np.array_equal(s["obs"], r["O"][rej]) and
+              (s.size == 0 or np.abs(s["q"][:, fl] - r["q"][rej]).max() <= 1e-6) and
+              S.lf[0][fl].n_valid == r["x"].size and S.lf[0][fl].numbin == r["numbin"])
+        if not ok:
+            return False, n_checked
+        n_checked += int(s.size)
+    return True, n_checked
 
 
 def _oracle_worker(a):
@@ -182,6 +211,173 @@ def run_reference(args, rank):
     }))
 
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The other BASELINE.json configs, reported in the same JSON line (cfg2 above stays the headline `value`)
+def _prefix_chromosome(base, n):
+    """A chromosome of n bins cut out of a longer generated one (same generator, no second Poisson draw)."""
+    num = base["num"]
+    return dict(n=n, num=num, Diags=[np.ascontiguousarray(base["Diags"][d][: n - d]) for d in range(num)],
+                weights=np.ascontiguousarray(base["weights"][:n]))
+
+
+def bench_cfg3(local, rank, world, dist, steps):
+    """configs[2]: 22 hg38 autosomes @10 kb, 5 Mb band, union (1,3)/(2,5)/(4,7), chromosomes LPT-sharded over the ranks
+    (strong scaling: the genome is fixed), host buffers in, peak-ready survivors out; per-chromosome FDR (the reference's
+    behaviour) and genome-wide FDR (one NCCL all-reduce of the lambda-chunk histograms inside the C ABI)."""
+    from hicpeaks_b200 import _capi, dispatch
+    from hicpeaks_b200.synth import band_pixels, hg38_autosome_bins, synth_chromosome
+    bins = hg38_autosome_bins(10000)
+    band, pw, ww = 500, [1, 2, 4], [3, 5, 7]
+    parts = dispatch.lpt_partition([dispatch.chrom_cost(n, band + 11) for n in bins], world)
+    mine = parts[rank]
+    base = synth_chromosome(max(bins), band, 3, maxww=10, seed=333)
+    inputs = [_prefix_chromosome(base, bins[i]) for i in mine]
+    ctxs = [_capi.Context(local) for _ in mine]
+    comm = _capi.Context(local)
+    uid = None
+    if world > 1:
+        box = [_capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+    comm.comm_init(world, rank, uid)
+    P = _capi.Context.make_params(pw, ww, 10, 0.1, band, 16)
+    px_mine = sum(band_pixels(bins[i], 3, band) for i in mine)
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max(1, min(4, len(ctxs))))
+
+    def up_score(job):
+        c, b = job
+        c.upload_counts(b["n"], b["num"], 3, b["Diags"], b["weights"])
+        return c.score(P)
+
+    def finish(c):
+        S = c.fdr()
+        return S, c.survivors().nbytes
+
+    def one_pass(scope):
+        t0 = time.perf_counter()
+        Ss = list(pool.map(up_score, zip(ctxs, inputs)))
+        merge_ms = comm.allreduce_hist(ctxs, len(pw)) if scope == "genome" else None
+        fin = list(pool.map(finish, ctxs))
+        return time.perf_counter() - t0, Ss, merge_ms, fin
+
+    out = {}
+    for scope in ("chrom", "genome"):
+        one_pass(scope)                                     # warm-up (allocations, first launches)
+        if dist is not None:
+            dist.barrier()
+        ts, merges, last = [], [], None
+        for _ in range(steps):
+            dt, Ss, mm, fin = one_pass(scope)
+            ts.append(dt); merges.append(mm); last = (Ss, fin)
+        t_rank = float(np.mean(ts))
+        if dist is not None:
+            import torch
+            v = torch.tensor([t_rank, float(px_mine)], dtype=torch.float64, device="cuda")
+            allv = [torch.zeros_like(v) for _ in range(world)]
+            dist.all_gather(allv, v)
+            per_rank = [float(a[0]) for a in allv]
+            px_all = sum(float(a[1]) for a in allv)
+        else:
+            per_rank, px_all = [t_rank], float(px_mine)
+        Ss, fin = last
+        out[scope] = {"value": px_all / max(per_rank), "unit": "pixels/s", "seconds": max(per_rank),
+                      "seconds_by_rank": [round(x, 5) for x in per_rank],
+                      "imbalance": max(per_rank) / (sum(per_rank) / len(per_rank)),
+                      "survivors_rank0": int(sum(S.n_survivors for S, _ in fin)),
+                      "ms_score_sum_rank0": float(sum(S.ms_score for S in Ss)), "ms_levels_sum_rank0": float(sum(S.ms_levels for S in Ss))}
+        if scope == "genome":
+            out[scope]["allreduce_ms_device"] = float(np.mean([m for m in merges if m is not None]))
+    ms_score = out["chrom"]["ms_score_sum_rank0"]
+    peak, _ = read_peaks()
+    out["roofline"] = {"kernel": "k_score_spec<(1,3),(2,5),(4,7)> (exact fp64 order; three pairs per pixel)",
+                       "achieved": ALG_BYTES_PER_PIXEL * px_mine / (ms_score * 1e-3) / 1e9 if ms_score else None,
+                       "peak": peak, "unit": "GB/s", "pixels": px_mine}
+    if out["roofline"]["achieved"]:
+        out["roofline"]["frac"] = out["roofline"]["achieved"] / peak
+    out["workload"] = ("cfg3: 22 hg38-autosome-sized synthetic chromosomes @10kb (prefixes of one generated %d-bin chromosome), 5 Mb band, "
+                       "union (1,3)/(2,5)/(4,7), LPT-sharded over %d rank(s); e2e: int32 count diagonals + weights from host memory in, "
+                       "survivors out; strong scaling" % (max(bins), world))
+    out["pixels"] = px_all
+    for c in ctxs + [comm]:
+        c.close()
+    return out
+
+
+def bench_cfg4(local, rank, steps):
+    """configs[3] shape, one shard per GPU: a chr1-sized chromosome @5 kb (49 792 bins), 10 Mb band (num = 2011), (4,7)."""
+    from hicpeaks_b200 import _capi
+    from hicpeaks_b200.synth import band_pixels, synth_chromosome
+    n, band = 49792, 2000
+    inp = synth_chromosome(n, band, 7, maxww=10, seed=4000 + rank)
+    Dg = [np.ascontiguousarray(d, dtype=np.int32) for d in inp["Diags"]]
+    P = _capi.Context.make_params([4], [7], 10, 0.1, band, 16)
+    px = band_pixels(n, 7, band)
+    with _capi.Context(local) as ctx:
+        ctx.upload_counts(n, inp["num"], 7, Dg, inp["weights"])
+        for _ in range(2):
+            S = ctx.hiccups(P)
+        ctx.timer_start()
+        for _ in range(steps):
+            S = ctx.hiccups(P)
+        ms = ctx.timer_stop() / steps
+        t0 = time.perf_counter()
+        for _ in range(max(1, steps // 2)):
+            ctx.upload_counts(n, inp["num"], 7, Dg, inp["weights"])
+            ctx.hiccups(P)
+            ctx.survivors()
+        e2e = (time.perf_counter() - t0) / max(1, steps // 2)
+        peak, _ = read_peaks()
+        ach = ALG_BYTES_PER_PIXEL * px / (S.ms_score * 1e-3) / 1e9
+        return {"workload": "cfg4 shard: one chr1-sized synthetic chromosome @5kb (%d bins), 10 Mb band (num=2011), p=4 w=7, per GPU" % n,
+                "pixels": px, "value": px / (ms * 1e-3), "unit": "pixels/s", "ms_per_pass": ms,
+                "e2e": {"value": px / e2e, "unit": "pixels/s", "seconds": e2e},
+                "kernel_ms": {"levels": S.ms_levels, "score": S.ms_score, "exact": S.ms_exact, "fdr": S.ms_fdr},
+                "fast_kernel": int(S.fast_kernel), "frozen_w": int(S.frozen_w), "survivors": int(S.n_survivors),
+                "roofline": {"achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}}
+
+
+def bench_cfg5(local):
+    """configs[4]: APA, 41 x 41 windows over 50 000 anchors @10 kb, through hicpeaks_b200.apa (upload + gather + pile-up)."""
+    from hicpeaks_b200 import apa as hapa
+    from hicpeaks_b200.synth import synth_chromosome
+    n, band, w, cw = 20000, 500, 20, 3
+    inp = synth_chromosome(n, band + 2 * w, 5, maxww=10, seed=41)
+    wt = inp["weights"]
+    diags = []
+    for d in range(inp["num"]):
+        raw = inp["Diags"][d]
+        with np.errstate(invalid="ignore"):
+            v = wt[: n - d] * wt[d:] * raw.astype(np.float64)
+        v[raw == 0] = 0.0
+        diags.append(v)
+
+    class Band:
+        shape = (n, n)
+
+        def diagonal(self, k):
+            return diags[k] if k < len(diags) else np.zeros(n - k)
+
+    rng = np.random.default_rng(7)
+    i = rng.integers(w, n - band - w - 1, 50000)
+    d = rng.integers(10 + w, band - w, 50000)
+    pos = [(int(a), int(a + b)) for a, b in zip(i, d)]
+    hapa.apa_analysis(hapa.apa_submatrix(Band(), pos[:2000], w=w), w=w, cw=cw)       # warm-up
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        wins = hapa.apa_submatrix(Band(), pos, w=w)
+        res = hapa.apa_analysis(wins, w=w, cw=cw)
+        ts.append(time.perf_counter() - t0)
+    sec = min(ts)
+    gathered = len(pos) * (2 * w + 1) ** 2 * 8
+    peak, _ = read_peaks()
+    return {"workload": "cfg5: APA 41x41 pile-up over 50000 synthetic anchors @10kb (20000-bin chromosome), apa.py path",
+            "anchors": len(pos), "windows_kept": len(wins), "seconds": sec, "value": len(pos) / sec, "unit": "anchors/s",
+            "gathered_bytes": gathered, "achieved_gbs_incl_upload": gathered / sec / 1e9, "peak_gbs": peak, "apa_score": float(res[1])}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -190,6 +386,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chroms", type=int, default=8, help="chromosomes per GPU per step (one host thread each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg3 / cfg4 / cfg5 legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -307,6 +504,25 @@ def main():
     h2d_counts = sum(c.upload_bytes() for c in ctxs)          # counted by the library from the copies it issued
     host_counts = sum(sum(a.nbytes for a in Dg) + inp["weights"].nbytes for inp, (Dg, cD, ir) in zip(batch, arrays))
 
+    # ---- the other BASELINE configs (every rank takes part in cfg3 / cfg4) -------------------------------------------
+    extra = {}
+    if not args.no_extra:
+        for c in ctxs:
+            c.trim()
+        esteps = max(2, min(args.steps, 5))
+        extra["cfg3"] = bench_cfg3(local, rank, world, dist, esteps)
+        c4 = bench_cfg4(local, rank, esteps)
+        if dist is not None:
+            import torch
+            v = torch.tensor([c4["ms_per_pass"], c4["e2e"]["seconds"]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            c4["value"] = world * c4["pixels"] / (float(v[0]) * 1e-3)
+            c4["e2e"]["value"] = world * c4["pixels"] / float(v[1])
+            c4["scaling"] = "weak (one shard per GPU, max over ranks)"
+        extra["cfg4"] = c4
+        if rank == 0:
+            extra["cfg5"] = bench_cfg5(local)
+
     px_step = acc["px"] // args.steps
     if dist is not None:
         import torch
@@ -374,13 +590,18 @@ def main():
         "clocks": clocks,
         "survivors_per_step": acc["surv"] // args.steps,
     }
+    out.update(extra)
     if rank_ms is not None:
         out["ms_per_step_by_rank"] = {"resident_e2e": rank_ms}          # the reported times are the max over ranks
     if world == 1 and not args.no_cpu_baseline:
         n_sample = 6000
-        px, sec = oracle_rate(n_sample, 4242)
+        px, sec, inp_o, res_o = oracle_rate(n_sample, 4242, keep=True)
         out["cpu_baseline"] = {"value": px / sec, "unit": "pixels/s", "cores": 1, "kind": "port",
                                "sample": "one %d-bin chromosome of the same generator/band/parameters (%.1f s)" % (n_sample, sec)}
+        ok, nchk = parity_against_oracle(ctxs[0], P, inp_o, res_o)
+        out["parity_checked"] = bool(ok)
+        out["parity"] = {"against": "oracle port on the cpu_baseline sample, outside the timed regions",
+                         "survivors_compared": nchk, "what": "survivor coordinates, O, E bit-exact; q within 1e-6; n_valid, numbin"}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

@@ -132,7 +132,7 @@ def load_library(path: str | None = None):
     lib.hp_comm_unique_id.argtypes = [vp]
     lib.hp_comm_init.argtypes = [vp, i32, i32, vp]
     lib.hp_comm_destroy.argtypes = [vp]
-    lib.hp_allreduce_hist.argtypes = [vp, vp, i32, C.POINTER(C.c_float)]
+    lib.hp_allreduce_hist.argtypes = [vp, vp, i32, i32, C.POINTER(C.c_float)]
     lib.hp_ctx_trim.argtypes = [vp]
     lib.hp_get_gaps.argtypes = [vp, vp, i64]
     lib.hp_dump_levels.argtypes = [vp, vp, i64]
@@ -395,12 +395,13 @@ class Context:
     def comm_destroy(self):
         self._check(self.lib.hp_comm_destroy(self._h))
 
-    def allreduce_hist(self, ctxs):
+    def allreduce_hist(self, ctxs, npw):
         """Merge the histograms / E.max / valid counts of the scored contexts ``ctxs`` (this process, this GPU) and of all
-        ranks; returns the device milliseconds of the merge.  Every rank calls it, ``ctxs`` may be empty."""
+        ranks; returns the device milliseconds of the merge.  Every rank calls it with the run's number of (pw, ww) pairs;
+        ``ctxs`` may be empty."""
         arr = (C.c_void_p * max(1, len(ctxs)))(*[c._h for c in ctxs])
         ms = C.c_float()
-        self._check(self.lib.hp_allreduce_hist(self._h, arr, len(ctxs), C.byref(ms)))
+        self._check(self.lib.hp_allreduce_hist(self._h, arr, len(ctxs), int(npw), C.byref(ms)))
         return float(ms.value)
 
     def summary(self):

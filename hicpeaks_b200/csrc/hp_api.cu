@@ -1675,25 +1675,23 @@ __global__ void k_hist_store(const unsigned long long* __restrict__ acc, unsigne
     if (i < 16) { small[i] = acc_small[i]; small[16 + i] = acc_small[16 + i]; }
 }
 
-extern "C" int hp_allreduce_hist(hp_ctx* ctx, hp_ctx* const* ctxs, int32_t nctx, float* ms_out) {
-    if (!ctx || (nctx > 0 && !ctxs) || nctx < 0) return fail(ctx, HP_ERR_INVALID, "bad argument");
+extern "C" int hp_allreduce_hist(hp_ctx* ctx, hp_ctx* const* ctxs, int32_t nctx, int32_t npw_all, float* ms_out) {
+    if (!ctx || (nctx > 0 && !ctxs) || nctx < 0 || npw_all < 1 || npw_all > HP_MAX_PW) return fail(ctx, HP_ERR_INVALID, "bad argument");
     if (ctx->comm_nranks < 1) return fail(ctx, HP_ERR_STATE, "hp_comm_init must come first");
     CK(cudaSetDevice(ctx->device));
     // geometry: every rank passes contexts scored with the same (pw, ww) list and chunk tables; a rank may hold none
-    int npw = 0;
     for (int k = 0; k < nctx; ++k) {
         hp_ctx* c = ctxs[k];
         if (!c || !c->scored) return fail(ctx, HP_ERR_STATE, "every context must have been scored (hp_hiccups_score)");
         if (c->device != ctx->device) return fail(ctx, HP_ERR_INVALID, "contexts of one call live on the communicator's GPU");
         if (c->prm.flags & HP_PF_BHFDR) return fail(ctx, HP_ERR_INVALID, "the BH-FDR caller has no lambda-chunk histograms");
         if (c->chunks.total_bins != ctx->chunks.total_bins) return fail(ctx, HP_ERR_INVALID, "contexts differ in max_chunks");
-        if (npw && c->prm.npw != npw) return fail(ctx, HP_ERR_INVALID, "contexts differ in the number of (pw, ww) pairs");
-        npw = c->prm.npw;
+        if (c->prm.npw != npw_all) return fail(ctx, HP_ERR_INVALID, "a context was scored with a different number of (pw, ww) pairs");
     }
     cudaStream_t st = ctx->stream;
     const size_t tb = ctx->chunks.total_bins;
-    // ranks must agree on the message size: HP_MAX_PW pairs are always reduced (unused rows stay zero)
-    const size_t cnt = (size_t)HP_MAX_PW * 2 * tb;
+    // every rank reduces the same npw_all * 2 tables (a rank without a chromosome contributes zeros)
+    const size_t cnt = (size_t)npw_all * 2 * tb;
     CK(ensure(&ctx->d_acc, &ctx->cap_acc, cnt + 33));
     CK(cudaMemsetAsync(ctx->d_acc, 0, (cnt + 33) * sizeof(unsigned long long), st));
     if (!ctx->ev_t0) { CK(cudaEventCreate(&ctx->ev_t0)); CK(cudaEventCreate(&ctx->ev_t1)); }

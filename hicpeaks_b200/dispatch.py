@@ -169,14 +169,14 @@ class CudaEngine:
     def hist(self, h):
         return h["ctx"].hist_export()
 
-    def merge(self, handles, nranks=1, rank=0, unique_id=None):
+    def merge(self, handles, npw, nranks=1, rank=0, unique_id=None):
         """Genome-wide merge on the device: sums over this GPU's contexts, one NCCL all-reduce over the ranks
         (``hp_allreduce_hist``).  Every rank calls it.  Returns the device milliseconds."""
         from . import _capi
         if self._comm_ctx is None:
             self._comm_ctx = _capi.Context(self.device, self.max_chunks if not handles else handles[0]["ctx"].max_chunks)
             self._comm_ctx.comm_init(nranks, rank, unique_id)
-        ms = self._comm_ctx.allreduce_hist([h["ctx"] for h in handles])
+        ms = self._comm_ctx.allreduce_hist([h["ctx"] for h in handles], npw)
         for h in handles:
             S = h["ctx"].summary()
             npw = len(h["emax"]) // 2
@@ -246,7 +246,7 @@ class GenomeRunner:
             if self.comm.world > 1:
                 from . import _capi
                 uid = self.comm.gather_objects(_capi.comm_unique_id() if self.comm.rank == 0 else None)[0]
-            self.merge_ms = engine.merge([handles[name] for name in mine], self.comm.world, self.comm.rank, uid)
+            self.merge_ms = engine.merge([handles[name] for name in mine], len(prm["pw"]), self.comm.world, self.comm.rank, uid)
             for name in mine:
                 tables[name] = engine.finish(handles[name], prm)
         else:

@@ -216,12 +216,13 @@ int hp_hist_import(hp_ctx* ctx, const int64_t* in, int64_t count);
  * comm's GPU, same (pw, ww) list) into u64 on the device, ncclAllReduce(sum) over the ranks, max for E.max(), sum for
  * the valid counts, and writes the merged tables back into every context, whose summary (e_max, numbin, n_valid)
  * becomes the genome-wide one; hp_hiccups_fdr then runs BH on the merged counts.  Every rank must call it (nctx may
- * be 0).  *ms (optional): device time from the first local sum to the last write-back. */
+ * be 0) with the same npw = number of (pw, ww) pairs of the run.  *ms (optional): device time from the first local sum
+ * to the last write-back. */
 #define HP_COMM_ID_BYTES 128
 int hp_comm_unique_id(void* id);
 int hp_comm_init(hp_ctx* ctx, int32_t nranks, int32_t rank, const void* id);
 int hp_comm_destroy(hp_ctx* ctx);
-int hp_allreduce_hist(hp_ctx* comm, hp_ctx* const* ctxs, int32_t nctx, float* ms);
+int hp_allreduce_hist(hp_ctx* comm, hp_ctx* const* ctxs, int32_t nctx, int32_t npw, float* ms);
 /* gives back the upload scratch of a context (device landing zone, pinned staging); the uploaded band and the results
  * of the last score stay valid.  For callers that keep many scored contexts alive (one per chromosome until the merged BH). */
 int hp_ctx_trim(hp_ctx* ctx);

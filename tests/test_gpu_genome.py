@@ -48,7 +48,7 @@ def test_device_merge_equals_host_merge():
         h["ctx"].close()
     # (b) device merge through the C ABI
     hb = [eng.score(k, v, prm) for k, v in chroms.items()]
-    ms = eng.merge(hb)
+    ms = eng.merge(hb, 3)
     assert ms >= 0
     for h, (sv_ref, tabs_ref) in zip(hb, ref):
         assert np.array_equal(h["emax"], emax) and np.array_equal(h["nvalid"], nval)
