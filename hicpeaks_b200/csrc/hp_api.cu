@@ -799,30 +799,23 @@ static const SpecKernel* find_spec(hp_ctx* ctx, int nexec) {
     return nullptr;
 }
 
-// ---- re-associated score kernels (hp_score_fast.cuh): single (p, w) programs, widths up to FM ----------------
+// ---- re-associated score kernels (hp_score_fast.cuh): any single (p, w) program, widths up to FM ----------------
 struct FastKernel {
-    int p, w0, fm;
+    int fm;
     int (*launch)(hp_ctx*, const CUtensorMap&, const FastArgs&, int, cudaStream_t);
 };
-template <int P, int W0, int FM>
+template <int FM>
 static int launch_fast(hp_ctx* ctx, const CUtensorMap& tm, const FastArgs& A, int grid, cudaStream_t st) {
     static std::atomic<size_t> granted[64];
-    const size_t smem = FastLayout<FM, FM - W0 + 1>::bytes;
-    CK(want_smem(k_score_fast<P, W0, FM>, ctx->device, smem, granted));
-    k_score_fast<P, W0, FM><<<grid, kFThreads, smem, st>>>(tm, A);
+    const size_t smem = FastLayout<FM, FM>::bytes;
+    CK(want_smem(k_score_fast<FM>, ctx->device, smem, granted));
+    k_score_fast<FM><<<grid, kFThreads, smem, st>>>(tm, A);
     return HP_OK;
 }
-static const FastKernel g_fast[] = {
-    {2, 5, 8, launch_fast<2, 5, 8>},
-#ifndef HP_FAST_BUILD
-    {2, 5, 10, launch_fast<2, 5, 10>},
-    {1, 3, 10, launch_fast<1, 3, 10>},
-    {4, 7, 10, launch_fast<4, 7, 10>},
-#endif
-};
-static const FastKernel* find_fast(int p, int w0, int frozen) {
+static const FastKernel g_fast[] = {{8, launch_fast<8>}, {10, launch_fast<10>}};
+static const FastKernel* find_fast(int frozen) {
     for (const FastKernel& k : g_fast)
-        if (k.p == p && k.w0 == w0 && frozen <= k.fm) return &k;
+        if (frozen <= k.fm) return &k;
     return nullptr;
 }
 
@@ -1033,7 +1026,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     static const bool no_fast_env = getenv("HP_NO_FAST") != nullptr;
     const FastKernel* fast = nullptr;
     if (spec_ok && !no_fast_env && !(P.flags & HP_PF_EXACT_SUMS) && !bhfdr && !P.dump && P.npw == 1 && P.pw[0] < P.ww[0] && ctx->domain_ok && ctx->edges_regular)
-        fast = find_fast(P.pw[0], P.ww[0], F);
+        fast = find_fast(F);
     size_t want_x = std::max<size_t>(65536, (size_t)total / 8);
     CUtensorMap tm_bal, tm_rawf;
     // the specialised kernel loads its tile as kTileParts boxes of consecutive planes
@@ -1086,6 +1079,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
             FA.maxchunk = ctx->chunks.maxchunk; FA.total_bins = ctx->chunks.total_bins;
             FA.nstrips = (dhi - dlo) / kFTD + 1; FA.ntr = (n + kFTR - 1) / kFTR;
             FA.nchunks = (FA.ntr + kFChunkTiles - 1) / kFChunkTiles;
+            FA.p = P.pw[0]; FA.w0 = P.ww[0];
             {   // mantissa bits of the in-octave edges, rounded down / up with margin (fast_classify)
                 auto mant = [](double x, bool up) {
                     float f = (float)(x * (up ? 1.0 + 1e-9 : 1.0 - 1e-9));

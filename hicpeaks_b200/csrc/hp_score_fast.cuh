@@ -78,6 +78,7 @@ struct FastArgs {
     unsigned int fcand_cap, xrec_cap;
     int n, num, pitch, dlo, dhi, F, nexec, maxchunk, total_bins;
     int nstrips, nchunks, ntr;
+    int p, w0;                      // the (pw, ww) pair of the run
     unsigned c1dn, c2dn, c1up, c2up;   // FastEdges (host: fast_edges())
 };
 
@@ -107,7 +108,7 @@ __host__ __device__ __forceinline__ unsigned fast_pack_err(float ek, float ey) {
 }
 
 // ---- the per-thread sums: one matrix row, kFNPX consecutive columns -------------------------------------------------
-template <int P, int W0, int FM>
+template <int FM>
 struct FastPass {
     static constexpr int SPAN = 2 * FM + kFNPX;
     static constexpr int PX = fast_px(FM);
@@ -183,9 +184,10 @@ struct FastPass {
     // lvpk: 8 nibbles, the level code (step index) of each pixel, 0xF = not a resolved pixel; lvmask: steps present in the
     // warp; ft: largest half-width any pixel of the warp needs.  For every resolved pixel i the sink receives, at the
     // pixel's own width w = W0 + code:  sink(i, code, K = Q_w - Q_p, Y = LL_w - LL_p, bounds on |K' - K| and |Y' - Y| as two bf16).
+    // P, W0: the (p, w) pair of the run (run-time values: one kernel covers every single-pair program up to maxww = FM)
     template <class Sink>
-    static __host__ __device__ __forceinline__ void run(const float* __restrict__ xrow, unsigned lvpk, unsigned lvmask, int ft,
-                                                        Sink&& sink) {
+    static __host__ __device__ __forceinline__ void run(const float* __restrict__ xrow, int P, int W0, unsigned lvpk, unsigned lvmask,
+                                                        int ft, Sink&& sink) {
         float dn[SPAN], W[SPAN];
         float Qp[kFNPX], Lp[kFNPX], fqp = 0.f, flp = 0.f;
         sfor<0, kFNPX>([&](auto I) { Qp[decltype(I)::value] = 0.f; Lp[decltype(I)::value] = 0.f; });
@@ -193,19 +195,18 @@ struct FastPass {
             constexpr int g = decltype(GG)::value;
             if (g <= ft) {
                 vert<g>(xrow, dn, W);
-                if constexpr (g == P) horiz<g>(dn, W, Qp, Lp, fqp, flp);
-                if constexpr (g >= W0) {
-                    if ((lvmask >> (g - W0)) & 1u) {
-                        float Q[kFNPX], L[kFNPX], fq, fl;
-                        horiz<g>(dn, W, Q, L, fq, fl);
-                        // the bounds of this width, kept as two bf16 rounded up (one word of the record)
-                        const unsigned epk = fast_pack_err(fast_cerr_k(g) * (fq + fqp), fast_cerr_y(g) * (fl + flp));
-                        sfor<0, kFNPX>([&](auto I) {
-                            constexpr int i = decltype(I)::value;
-                            if (((lvpk >> (4 * i)) & 0xFu) == (unsigned)(g - W0))
-                                sink(I, std::integral_constant<int, g - W0>{}, Q[i] - Qp[i], L[i] - Lp[i], epk);
-                        });
-                    }
+                if (g == P) {
+                    horiz<g>(dn, W, Qp, Lp, fqp, flp);
+                } else if (g >= W0 && ((lvmask >> (g - W0)) & 1u)) {
+                    float Q[kFNPX], L[kFNPX], fq, fl;
+                    horiz<g>(dn, W, Q, L, fq, fl);
+                    // the bounds of this width, kept as two bf16 rounded up (one word of the record)
+                    const unsigned epk = fast_pack_err(fast_cerr_k(g) * (fq + fqp), fast_cerr_y(g) * (fl + flp));
+                    const unsigned sc = (unsigned)(g - W0);
+                    sfor<0, kFNPX>([&](auto I) {
+                        constexpr int i = decltype(I)::value;
+                        if (((lvpk >> (4 * i)) & 0xFu) == sc) sink(I, sc, Q[i] - Qp[i], L[i] - Lp[i], epk);
+                    });
                 }
             }
         });
@@ -284,12 +285,13 @@ __device__ __forceinline__ void smem_red_max32(unsigned* p, unsigned v) {
     asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 
-template <int P, int W0, int FM>
+template <int FM>
 __global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_constant__ CUtensorMap tm_raw, const __grid_constant__ FastArgs A) {
-    using FP = FastPass<P, W0, FM>;
+    using FP = FastPass<FM>;
     constexpr int PX = FP::PX;
     constexpr int XC = kFTD + 4 * FM;                  // tile columns: diagonals d0 - 2 FM .. d0 + 63 + 2 FM
-    constexpr int NEX = FM - W0 + 1;
+    constexpr int NEX = FM;                            // executed steps: at most FM - w + 1
+    const int P = A.p, W0 = A.w0;
     using LY = FastLayout<FM, NEX>;
     extern __shared__ __align__(128) unsigned char smem[];
     float* const xs = reinterpret_cast<float*>(smem + LY::oXS);
@@ -464,10 +466,10 @@ __global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_consta
                 // element (r + a, c0 - FM + t) sits at tile column (d0 + 8 cb - FM + t - a) - (d0 - 2 FM) = 8 cb + FM + t - a
                 const float* xrow = xs + (size_t)(rl + kFRowHalo) * PX + kFNPX * cb;
                 const unsigned mbase = (unsigned)rl | ((unsigned)(kFNPX * cb) << 6);
-                FP::run(xrow, lvpk, lvmask, ft, [&](auto I, auto S, float kv, float yv, unsigned epk) {
-                    constexpr int i = decltype(I)::value, sc = decltype(S)::value;
+                FP::run(xrow, P, W0, lvpk, lvmask, ft, [&](auto I, unsigned sc, float kv, float yv, unsigned epk) {
+                    constexpr int i = decltype(I)::value;
                     const unsigned slot = ((i < 4 ? slotpk0 : slotpk1) >> (8 * (i & 3))) & 0xffu;
-                    q[slot] = make_uint4(__float_as_uint(kv), __float_as_uint(yv), epk, mbase + ((unsigned)i << 6) + ((unsigned)sc << 12));
+                    q[slot] = make_uint4(__float_as_uint(kv), __float_as_uint(yv), epk, mbase + ((unsigned)i << 6) + (sc << 12));
                 });
                 __syncwarp();
                 // ---- close the records: classify both backgrounds, account the certain ones ---------------------------

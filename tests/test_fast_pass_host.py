@@ -30,7 +30,7 @@ static double at(int r, int c) { return X[(size_t)(r + PAD) * NC + (c + PAD)]; }
 
 template <int P, int W0, int FM>
 static int run_case(unsigned seed, double sparsity, double spike, double* worst) {
-    using FP = FastPass<P, W0, FM>;
+    using FP = FastPass<FM>;
     constexpr int PX = FP::PX;
     const int r0 = 64, d0 = 40;                       // one tile: rows r0 .. r0 + 63, diagonals d0 .. d0 + 63
     NR = 64 + 2 * PAD + 64; NC = NR + 200;
@@ -68,10 +68,10 @@ static int run_case(unsigned seed, double sparsity, double spike, double* worst)
             int ft = W0; for (int s = 0; s <= FM - W0; ++s) if ((mask >> s) & 1u) ft = W0 + s;
             float K[kFNPX] = {0}, Y[kFNPX] = {0}, EK[kFNPX] = {0}, EY[kFNPX] = {0};
             int got[kFNPX] = {0};
-            FP::run(xs.data() + (size_t)(rl + kFRowHalo) * PX + kFNPX * cb, lvpk, mask, ft,
-                    [&](auto I, auto S, float kv, float yv, unsigned pk) {
+            FP::run(xs.data() + (size_t)(rl + kFRowHalo) * PX + kFNPX * cb, P, W0, lvpk, mask, ft,
+                    [&](auto I, unsigned sc, float kv, float yv, unsigned pk) {
                         constexpr int i = decltype(I)::value;
-                        if (decltype(S)::value != codes[i]) ++bad;
+                        if ((int)sc != codes[i]) ++bad;
                         K[i] = kv; Y[i] = yv; ++got[i];
                         // the bounds travel as two bf16 rounded up; the kernel unpacks them exactly like this
                         union { unsigned u; float f; } a, b; a.u = pk << 16; b.u = pk & 0xFFFF0000u;
@@ -161,6 +161,8 @@ int main() {
     bad += run_case<2, 5, 10>(3, 0.5, 0.001, worst);
     bad += run_case<1, 3, 10>(4, 0.2, 0.0, worst);
     bad += run_case<4, 7, 10>(5, 0.7, 0.005, worst);
+    bad += run_case<3, 6, 10>(6, 0.4, 0.001, worst);          // a pair no exact-order kernel is compiled for
+    bad += run_case<0, 2, 8>(7, 0.3, 0.0, worst);             // p = 0: no peak square beyond the pixel itself
     printf("sums bad %d worst_ratio_K %.4f worst_ratio_Y %.4f\n", bad, worst[0], worst[1]);
     bad += check_classify();
     printf("RESULT %s\n", bad ? "FAIL" : "OK");

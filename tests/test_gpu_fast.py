@@ -65,6 +65,8 @@ CASES = [
     (300, 40, 4, 7, 10, 60.0, 1.2, 30, 4),
     (2600, 300, 2, 5, 10, 300.0, 1.08, 16, 21),        # more than one work item per strip (row-tile carry-over)
     (90, 70, 2, 5, 10, 300.0, 1.08, 16, 2),            # chromosome shorter than band + windows: pixels next to both ends
+    (640, 90, 3, 6, 10, 40.0, 1.05, 20, 12),           # a pair with no compiled exact-order kernel: table-driven k_score vs fast
+    (520, 70, 0, 2, 9, 30.0, 1.1, 16, 13),             # p = 0
 ]
 
 
