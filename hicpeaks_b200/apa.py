@@ -32,6 +32,18 @@ class ApaWindows:
     def __len__(self):
         return int(self.index.size)
 
+    def close(self):
+        """Free the GPU memory of this chromosome (band copy, windows); the handle is unusable afterwards."""
+        if self.ctx is not None:
+            self.ctx.close()
+            self.ctx = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
     def __getitem__(self, k):
         if isinstance(k, slice):
             return list(self.ctx.apa_get_windows(self.index[k], self.w))

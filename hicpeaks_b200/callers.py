@@ -144,10 +144,16 @@ def hiccups(M, cM, B1, B2, IR, chromLen, Diags, cDiags, num, chrom, pw=[2], ww=[
     """HiCCUPS peak calling for one chromosome.  ``M`` and ``cM`` are accepted for signature parity;
     the engine reads the same data from ``Diags`` / ``cDiags``.  Returns
     ``{(x_bp, y_bp): (cx_bp, cy_bp, radius_bp, O, foldK, pK, qK, foldY, pY, qY)}``."""
-    ctx = get_context(device)
     pw, ww = list(pw), list(ww)
-    S, sv, gaps = score_chromosome(ctx, chromLen, Diags, cDiags, IR, B1, B2, num, pw, ww, maxww, sig,
-                                   maxapart // res, min_local_reads, chrom, weights=weights)
+    try:
+        S, sv, gaps = score_chromosome(get_context(device), chromLen, Diags, cDiags, IR, B1, B2, num, pw, ww, maxww, sig,
+                                       maxapart // res, min_local_reads, chrom, weights=weights)
+    except _capi.EngineError as e:
+        if e.code != _capi.HP_ERR_CHUNK_OVERFLOW:
+            raise
+        # an expected value beyond 2^17 (the default table): once more with every lambda-chunk the engine supports (2^21)
+        S, sv, gaps = score_chromosome(get_context(device, 64), chromLen, Diags, cDiags, IR, B1, B2, num, pw, ww, maxww, sig,
+                                       maxapart // res, min_local_reads, chrom, weights=weights)
     _log_sweep(chrom, S)
     logger.info('Chrom:{0}, Poisson Models and Benjamini-Hochberg Correcting for lambda chunks ...'.format(chrom))
     for pi, (p, w) in enumerate(zip(pw, ww)):
@@ -191,19 +197,23 @@ def bhfdr(M, cM, B1, B2, IR, chromLen, Diags, cDiags, num, chrom, pw=2, ww=5, si
     GPU: the donut sweep with the hard-coded ``Reads >= 16`` rule (:490), ``E`` (:526-535) and the per-pixel Poisson
     tail (:536-540) for every pixel that can still pass ``sig``.  Host (a few thousand records): the chromosome-wide
     Benjamini-Hochberg step (:545-547), gap filter (:557-577), clustering (:580-582) and ``fold > 2`` (:587)."""
-    ctx = get_context(device)
-    if weights is not None:
-        ctx.upload_counts(chromLen, num, ww, _as_counts(Diags, num, chromLen), weights)
-    else:
-        raw, bal, ir = _as_diags(Diags, cDiags, IR, chromLen, num, ww)
-        ctx.upload(chromLen, num, ww, raw, bal, ir, B1, B2)
-    P = ctx.make_params([pw], [ww], maxww, sig, maxapart // res, 16, bhfdr=True)
-    try:
-        S = ctx.score(P)
-    except _capi.EngineError as e:
-        if e.code == _capi.HP_ERR_EMPTY_REFIDX:
-            raise ValueError(str(e)) from None
-        raise
+    for max_chunks in (52, 64):
+        ctx = get_context(device, max_chunks)
+        if weights is not None:
+            ctx.upload_counts(chromLen, num, ww, _as_counts(Diags, num, chromLen), weights)
+        else:
+            raw, bal, ir = _as_diags(Diags, cDiags, IR, chromLen, num, ww)
+            ctx.upload(chromLen, num, ww, raw, bal, ir, B1, B2)
+        P = ctx.make_params([pw], [ww], maxww, sig, maxapart // res, 16, bhfdr=True)
+        try:
+            S = ctx.score(P)
+        except _capi.EngineError as e:
+            if e.code == _capi.HP_ERR_EMPTY_REFIDX:
+                raise ValueError(str(e)) from None
+            if e.code == _capi.HP_ERR_CHUNK_OVERFLOW and max_chunks < 64:
+                continue                  # the engine bins E for its candidate test: once more with its full table (E up to 2^21)
+            raise
+        break
     _log_sweep(chrom, S)
     S = ctx.fdr()
     n_tests = int(S.lf[0][0].n_valid)

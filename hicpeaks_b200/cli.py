@@ -450,6 +450,8 @@ def run_apa(argv=None, Lib=None):
     n_windows = sum(len(p) for p in parts)
     print(n_windows)
     avg, score, z, p, maxi = apa_mod.apa_analysis(parts, w=args.window, cw=args.corner_size)
+    for part in parts:                     # one engine context per chromosome: give the GPU memory back
+        part.close()
     vmax = maxi if args.vmax is None else args.vmax
     try:
         import matplotlib

@@ -13,6 +13,16 @@ with _capi.Context(0) as ctx:
     S = ctx.hiccups(P)
     sv = ctx.survivors(); g = ctx.gaps()
     print("ok", S.n_pixels, S.frozen_w, S.n_survivors, int(g.sum()), S.spec_kernel)
+    print("fast kernel", S.fast_kernel, "exact records", S.n_exact)
+    P = ctx.make_params([2], [5], 10, 0.1, 120, 16, exact_sums=True)
+    S = ctx.hiccups(P)
+    print("ok exact-order spec kernel", S.n_pixels, S.n_survivors, S.fast_kernel)
+    P = ctx.make_params([2], [5], 10, 0.1, 120, 16)
+    S = ctx.score(P)
+    ctx.comm_init(1, 0, None)
+    print("device merge ms", ctx.allreduce_hist([ctx], 1))
+    S = ctx.fdr()
+    print("ok genome-scope merge", S.n_survivors)
     P = ctx.make_params([2], [5], 10, 0.1, 120, 16, generic_kernel=True)
     S = ctx.hiccups(P)
     print("ok generic", S.n_pixels, S.n_survivors)
