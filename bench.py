@@ -574,7 +574,9 @@ def main():
                                            "ms_fdr": float(np.mean([t[2] for t in seq])),
                                            "ms_call_host_clock": float(np.mean([t[3] for t in seq]))},
         "roofline": {"bound": "hbm", "kernel": "k_score_fast (+ k_exact for the records it leaves open)" if seq[-1][5] else "k_score_spec", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": "ncu --set full capture of the same kernel on this workload (profiles/k_score_traffic.json); not measured in this run",
+                     "peak_source": peak_src,
                      "alg_bytes_per_pixel": ALG_BYTES_PER_PIXEL, "pixels_per_launch": px_launch,
                      "avg_launch_ms": ms_score},
         "e2e": {"value": e2e_value, "unit": "pixels/s", "h2d_bytes_per_step": h2d_counts * world,
