@@ -91,6 +91,10 @@ struct hp_ctx {
     FCand* d_fcand = nullptr; size_t cap_fcand = 0;
     XRec* d_xrec = nullptr; size_t cap_xrec = 0;
     float* d_ffac = nullptr; size_t cap_ffac = 0;
+    float* d_ffs = nullptr; size_t cap_ffs = 0;        // per-strip blocks of the interior factors (bulk-copied by the fast kernel)
+    float* d_xf = nullptr; size_t cap_xf = 0;          // fp32 row-major copy of the balanced band (k_f32plane), row pitch xf_ndp
+    float *d_b1f = nullptr, *d_b2s = nullptr; size_t cap_b1f = 0, cap_b2s = 0;
+    int xf_ndp = 0;
     unsigned int nfcand = 0;
     bool fast_used = false;
     bool edges_regular = false;           // every chunk edge is 2^e times rv[2] or rv[3]: the fast kernel's mantissa compares apply
@@ -99,7 +103,7 @@ struct hp_ctx {
     ncclComm_t comm = nullptr;
     int comm_nranks = 0, comm_rank = 0;
     unsigned long long* d_acc = nullptr; size_t cap_acc = 0;
-    int4* d_fscratch = nullptr;           // [2 * sm_count][kFScratch] E.max() contenders of the fast kernel's CTAs
+    int4* d_fscratch = nullptr;           // [sm_count][kFScratch] E.max() contenders of the fast kernel's CTAs
     hp_survivor* d_surv = nullptr; size_t cap_surv = 0;
     double* d_dump = nullptr; size_t cap_dump = 0;
     int numbin[HP_MAX_PW * 2] = {};
@@ -321,7 +325,7 @@ extern "C" void hp_ctx_destroy(hp_ctx* ctx) {
     comm_release(ctx);
     void* ptrs[] = {ctx->d_ptab, ctx->d_raw, ctx->d_bal, ctx->d_lvl, ctx->d_ir, ctx->d_b1, ctx->d_b2, ctx->d_rownz,
                     ctx->d_lhist, ctx->d_betab, ctx->d_hist, ctx->d_qtab, ctx->d_small, ctx->d_cnt, ctx->d_numbin,
-                    ctx->d_cand, ctx->d_fcand, ctx->d_xrec, ctx->d_ffac, ctx->d_fscratch, ctx->d_acc, ctx->d_surv, ctx->d_dump, ctx->d_tmp, ctx->d_tab, ctx->d_w, ctx->d_pk, ctx->d_prep, ctx->d_apa_bal, ctx->d_apa_plan, ctx->d_apa_pos,
+                    ctx->d_cand, ctx->d_fcand, ctx->d_xrec, ctx->d_ffac, ctx->d_ffs, ctx->d_xf, ctx->d_b1f, ctx->d_b2s, ctx->d_fscratch, ctx->d_acc, ctx->d_surv, ctx->d_dump, ctx->d_tmp, ctx->d_tab, ctx->d_w, ctx->d_pk, ctx->d_prep, ctx->d_apa_bal, ctx->d_apa_plan, ctx->d_apa_pos,
                     ctx->d_apa_wins, ctx->d_apa_valid, ctx->d_apa_mean, ctx->d_apa_sel, ctx->d_apa_avg};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -428,6 +432,26 @@ class PackPool {
     std::vector<std::thread> workers_;
 };
 
+// Row pitch of the band planes: a multiple of 64, so that a sub-plane of the u8 level plane (pitch / 4 bytes) starts on a
+// 16-byte boundary -- TMA strides and box origins must (hp_score_fast.cuh loads level tiles as 3-D boxes)
+static inline int band_pitch(int64_t n) { return (int)((n + 63) / 64 * 64); }
+
+// what the re-associated score kernel reads besides the planes: the fp32 row-major copy of the balanced band and the
+// fp32 bias vectors (hp_score_fast.cuh); queued on the context's stream right after the planes have been written
+static int fast_companions(hp_ctx* ctx, int64_t n, int num, int bf, int pitch) {
+    const int ndp = (num - bf + 3) & ~3;
+    const int n1 = (int)((n + kFTR - 1) / kFTR * kFTR) + kFTR, n2 = (int)n + num + 4 * kFTD;
+    CK(ensure(&ctx->d_xf, &ctx->cap_xf, (size_t)n * ndp));
+    CK(ensure(&ctx->d_b1f, &ctx->cap_b1f, (size_t)n1));
+    CK(ensure(&ctx->d_b2s, &ctx->cap_b2s, (size_t)n2));
+    k_f32plane<<<dim3((unsigned)((n + 63) / 64), (unsigned)((ndp + 31) / 32)), 256, 0, ctx->stream>>>(ctx->d_bal, ctx->d_xf, (int)n, num, bf, pitch, ndp);
+    CK(cudaGetLastError());
+    k_fast_bias<<<(unsigned)((std::max(n1, n2) + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_b1, ctx->d_b2, ctx->d_b1f, ctx->d_b2s, (int)n, bf, n1, n2);
+    CK(cudaGetLastError());
+    ctx->xf_ndp = ndp;
+    return HP_OK;
+}
+
 static int band_alloc(hp_ctx* ctx, int64_t n_, int num_, int bal_first_) {
     struct { int64_t n; int num; int bal_first; } bb{n_, num_, bal_first_};
     auto* b = &bb;
@@ -438,7 +462,7 @@ static int band_alloc(hp_ctx* ctx, int64_t n_, int num_, int bal_first_) {
     ctx->have_band = false; ctx->scored = false; ctx->fdr_done = false;
     const int64_t n = b->n;
     const int num = b->num;
-    const int pitch = (int)((n + 31) / 32 * 32);
+    const int pitch = band_pitch(n);
     const size_t plane = (size_t)num * pitch;
     if (plane > ctx->cap_plane) {
         for (void* p : {(void*)ctx->d_raw, (void*)ctx->d_bal, (void*)ctx->d_lvl, (void*)ctx->d_tmp}) if (p) cudaFree(p);
@@ -477,7 +501,7 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
     }
     const int64_t n = b->n;
     const int num = b->num;
-    const int pitch = (int)((n + 31) / 32 * 32);
+    const int pitch = band_pitch(n);
     const size_t plane = (size_t)num * pitch;
     double* hbal = (double*)ctx->h_stage;
     int* hraw = (int*)((char*)ctx->h_stage + plane * 8);
@@ -524,6 +548,7 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
     CK(cudaMemcpyAsync(ctx->d_ir, hir, (size_t)num * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_b1, b->b1, n * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_b2, b->b2, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    { const int rcf = fast_companions(ctx, n, num, bf, pitch); if (rcf) return rcf; }
     CK(cudaMemcpyAsync(ctx->h_res + 6144, ctx->d_cnt + 12, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(stream_sync(ctx));
     ctx->domain_ok = *(const unsigned int*)(ctx->h_res + 6144) == 0u;
@@ -579,7 +604,7 @@ extern "C" int hp_band_upload_counts(hp_ctx* ctx, const hp_counts_desc* b) {
     }
     const int64_t n = b->n;
     const int num = b->num, bf = b->bal_first;
-    const int pitch = (int)((n + 31) / 32 * 32);
+    const int pitch = band_pitch(n);
     const size_t plane = (size_t)num * pitch;
     cudaStream_t st = ctx->stream;
     int* hraw = (int*)((char*)ctx->h_stage + plane * 8);
@@ -648,6 +673,7 @@ extern "C" int hp_band_upload_counts(hp_ctx* ctx, const hp_counts_desc* b) {
     CK(cudaGetLastError());
     k_prep_bias<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_w, ctx->d_b1, ctx->d_b2, (int)n);
     CK(cudaGetLastError());
+    { const int rcf = fast_companions(ctx, n, num, bf, pitch); if (rcf) return rcf; }
     CK(cudaMemcpyAsync(ctx->h_res + 6144, ctx->d_cnt + 12, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     const auto t_launched = std::chrono::steady_clock::now();
     CK(stream_sync(ctx));
@@ -765,6 +791,19 @@ static int make_map_plane(hp_ctx* ctx, CUtensorMap* map, CUtensorMapDataType dt,
     return HP_OK;
 }
 
+// plain 2-D tensor: dims (inner, outer), outer stride in bytes (a multiple of 16)
+static int make_map_2d(hp_ctx* ctx, CUtensorMap* map, CUtensorMapDataType dt, void* base, uint64_t dim0, uint64_t dim1, uint64_t stride_bytes,
+                       int box0, int box1) {
+    cuuint64_t dims[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
+    cuuint64_t strides[1] = {(cuuint64_t)stride_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = ctx->encode(map, dt, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, HP_ERR_CUDA, "cuTensorMapEncodeTiled (2-D) failed: " + std::to_string((int)r));
+    return HP_OK;
+}
+
 // ---- specialised score kernels: sweep programs compiled in (hp_score_spec.cuh) --------------------
 struct SpecKernel {
     bool (*matches)(const Prog&, int, const signed char*, const signed char*, const unsigned char*, const unsigned char*);
@@ -807,11 +846,19 @@ struct FastKernel {
     int (*launch)(hp_ctx*, const CUtensorMap&, const FastArgs&, int, cudaStream_t);
 };
 template <int FM>
-static int launch_fast(hp_ctx* ctx, const CUtensorMap& tm, const FastArgs& A, int grid, cudaStream_t st) {
+static int launch_fast(hp_ctx* ctx, const CUtensorMap& tm_raw, const FastArgs& A, int grid, cudaStream_t st) {
     static std::atomic<size_t> granted[64];
     const size_t smem = FastLayout<FM, FM>::bytes;
     CK(want_smem(k_score_fast<FM>, ctx->device, smem, granted));
-    k_score_fast<FM><<<grid, kFThreads, smem, st>>>(tm, A);
+    // the fp32 tile: box of fast_px(FM) diagonals x 96 rows of xf[r][d - dlo]; the levels: the same 3-D box of the
+    // quad-interleaved u8 plane as the raw counts
+    CUtensorMap tm_x, tm_lvl;
+    int rc = make_map_2d(ctx, &tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, ctx->d_xf, (uint64_t)(ctx->num - ctx->bal_first), (uint64_t)ctx->n,
+                         (uint64_t)ctx->xf_ndp * 4, fast_px(FM), kFXR);
+    if (rc) return rc;
+    rc = make_map_plane(ctx, &tm_lvl, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ctx->d_lvl, kFTR / 4, kFTD);
+    if (rc) return rc;
+    k_score_fast<FM><<<grid, kFThreads, smem, st>>>(tm_raw, tm_x, tm_lvl, A);
     return HP_OK;
 }
 static const FastKernel g_fast[] = {{8, launch_fast<8>}, {10, launch_fast<10>}};
@@ -1039,10 +1086,13 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
         rc = make_map_plane(ctx, &tm_rawf, CU_TENSOR_MAP_DATA_TYPE_INT32, 4, ctx->d_raw, kFTR / 4, kFTD);
         if (rc) return rc;
         CK(ensure(&ctx->d_ffac, &ctx->cap_ffac, (size_t)(1 + 2 * F) * 2 * nexec * num));
-        if (!ctx->d_fscratch) CK(cudaMalloc(&ctx->d_fscratch, (size_t)2 * ctx->sm_count * kFScratch * sizeof(int4)));
+        if (!ctx->d_fscratch) CK(cudaMalloc(&ctx->d_fscratch, (size_t)ctx->sm_count * kFScratch * sizeof(int4)));
+        const size_t nffs = (size_t)((num - 1 - dlo) / kFTD + 1) * 2 * nexec * kFTD;      // k_betab writes every diagonal of the band
+        CK(ensure(&ctx->d_ffs, &ctx->cap_ffs, nffs));
+        CK(cudaMemsetAsync(ctx->d_ffs, 0, nffs * sizeof(float), st));       // diagonals beyond the band: factor 0
     }
     k_betab<<<dim3((num + 127) / 128, nexec, 1 + 2 * F), 128, 0, st>>>(ctx->d_tab, ctx->d_ir, ctx->d_betab, num, ctx->bal_first, nexec, F,
-                                                                     fast ? ctx->d_ffac : nullptr);
+                                                                     fast ? ctx->d_ffac : nullptr, fast ? ctx->d_ffs : nullptr);
     ++launches;
     unsigned int cnt[16] = {0};
     unsigned long long small[48];
@@ -1050,7 +1100,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     for (int attempt = 0;; ++attempt) {
         CK(ensure(&ctx->d_cand, &ctx->cap_cand, use_fast ? std::max<size_t>(65536, want_x) : want));
         if (use_fast) {
-            CK(ensure(&ctx->d_fcand, &ctx->cap_fcand, want + (size_t)kFCandChunk * (kFThreads / 32) * 2 * ctx->sm_count));   // + every warp's last piece
+            CK(ensure(&ctx->d_fcand, &ctx->cap_fcand, want + (size_t)kFCandChunk * kFWarps * ctx->sm_count));   // + every warp's last piece
             CK(ensure(&ctx->d_xrec, &ctx->cap_xrec, want_x));
         }
         CK(cudaMemsetAsync(ctx->d_hist, 0, (size_t)P.npw * 2 * tb * sizeof(unsigned int), st));
@@ -1071,8 +1121,8 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
         CK(cudaEventRecord(ctx->ev[2], st));      // ms_score = the score kernel alone (roofline leg of bench.py)
         if (use_fast) {
             FastArgs FA{};
-            FA.bal = ctx->d_bal; FA.lvl = ctx->d_lvl; FA.b1 = ctx->d_b1; FA.b2 = ctx->d_b2;
-            FA.ffac = ctx->d_ffac; FA.tab = ctx->d_tab; FA.scratch = ctx->d_fscratch;
+            FA.ffac = ctx->d_ffac; FA.ffs = ctx->d_ffs; FA.b1f = ctx->d_b1f; FA.b2s = ctx->d_b2s;
+            FA.tab = ctx->d_tab; FA.scratch = ctx->d_fscratch;
             FA.hist = ctx->d_hist; FA.nvalid = ctx->d_small + 16;
             FA.fcand = ctx->d_fcand; FA.xrec = ctx->d_xrec; FA.cnt = ctx->d_cnt;
             FA.fcand_cap = (unsigned)std::min<size_t>(ctx->cap_fcand, 0xffffffffu);
@@ -1080,7 +1130,6 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
             FA.n = n; FA.num = num; FA.pitch = pitch; FA.dlo = dlo; FA.dhi = dhi; FA.F = F; FA.nexec = nexec;
             FA.maxchunk = ctx->chunks.maxchunk; FA.total_bins = ctx->chunks.total_bins;
             FA.nstrips = (dhi - dlo) / kFTD + 1; FA.ntr = (n + kFTR - 1) / kFTR;
-            FA.nchunks = (FA.ntr + kFChunkTiles - 1) / kFChunkTiles;
             FA.p = P.pw[0]; FA.w0 = P.ww[0];
             {   // mantissa bits of the in-octave edges, rounded down / up with margin (fast_classify)
                 auto mant = [](double x, bool up) {
@@ -1092,8 +1141,8 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
                 FA.c1dn = mant(ctx->chunks.rv[2], false); FA.c2dn = mant(ctx->chunks.rv[3], false);
                 FA.c1up = mant(ctx->chunks.rv[2], true); FA.c2up = mant(ctx->chunks.rv[3], true);
             }
-            const int items = FA.nstrips * FA.nchunks;
-            rc = fast->launch(ctx, tm_rawf, FA, std::min(items, 2 * ctx->sm_count), st);
+            const int items = FA.nstrips * FA.ntr;
+            rc = fast->launch(ctx, tm_rawf, FA, std::min(items, ctx->sm_count), st);
             if (rc) return rc;
             ++launches;
             CK(cudaGetLastError());

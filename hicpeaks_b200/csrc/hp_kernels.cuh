@@ -84,9 +84,10 @@ __global__ void __launch_bounds__(kThreads) k_levels(const __grid_constant__ CUt
 // Layout betab[z][fl][s][d]: z = 0 interior pixels; z = 1 + r for the rows r < F next to the start of the
 // chromosome (cells with row < 0 or column < 0 drop out); z = 1 + F + e for the columns c = n - 1 - e, e < F,
 // next to its end (cells with row >= n or column >= n drop out).  Pixels near both ends take edge_be().
-// ffac (optional): the same table as fp32 factors IR[d] / bE for the re-associated kernel (hp_score_fast.cuh)
+// ffac (optional): the same table as fp32 factors IR[d] / bE for the re-associated kernel (hp_score_fast.cuh);
+// ffs: its interior part again as [strip][fl][s][64] blocks (one bulk copy per tile)
 __global__ void k_betab(const Tables* __restrict__ tab, const double* __restrict__ ir, double* __restrict__ betab, int num,
-                        int bal_first, int nsteps_exec, int F, float* __restrict__ ffac) {
+                        int bal_first, int nsteps_exec, int F, float* __restrict__ ffac, float* __restrict__ ffs) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     const int s = blockIdx.y, z = blockIdx.z;
     if (d >= num || s >= nsteps_exec) return;
@@ -110,6 +111,12 @@ __global__ void k_betab(const Tables* __restrict__ tab, const double* __restrict
         const double ird = ir[d];
         ffac[((size_t)(z * 2 + 0) * nsteps_exec + s) * num + d] = fast_factor(ird, ek);
         ffac[((size_t)(z * 2 + 1) * nsteps_exec + s) * num + d] = fast_factor(ird, ey);
+        if (ffs && z == 0 && d >= bal_first) {          // the interior factors once more, one block of 64 diagonals per strip
+            const int k = d - bal_first;
+            float* o = ffs + ((size_t)(k >> 6) * 2 * nsteps_exec + s) * 64 + (k & 63);
+            o[0] = fast_factor(ird, ek);
+            o[(size_t)nsteps_exec * 64] = fast_factor(ird, ey);
+        }
     }
 }
 

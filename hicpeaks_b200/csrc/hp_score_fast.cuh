@@ -24,10 +24,13 @@
 // over them at the levels some pixel of the warp resolves at.  ~110 fp32 adds per pixel instead of ~200 ordered fp64
 // adds, 128-bit conflict-free loads, no barrier inside a tile's compute phase.
 //
-// Data movement: the fp64 balanced plane is streamed from HBM with coalesced loads (32 consecutive matrix rows per
-// warp and plane), converted to fp32 and stored as the shared-memory tile; a CTA walks down a strip of row tiles and
-// keeps the 32 overlapping rows, so every plane element is read once per strip.  The raw counts of the tile (needed
-// only when a pixel's record is closed) arrive by TMA while the sums are computed.
+// Data movement: nothing is filled by threads.  The upload leaves an fp32 row-major copy of the balanced band in HBM
+// (xf[r][d - min(ww)], k_f32plane) next to the fp64 planes the exact kernels read; a tile of it -- 96 matrix rows x PX
+// diagonals, already in the order the sums want -- arrives by one TMA box, the raw counts and the levels of the tile and
+// the three small factor tables by further TMA / bulk copies on the same mbarrier.  A CTA owns two such stages and a
+// static list of tiles; its 16 warps claim the 16 (row half, column block) passes of tile after tile from one counter,
+// wait only for the mbarrier of the stage they need, and the warp that finishes the last pass of a tile re-arms the stage
+// with the tile after next: no CTA-wide barrier between the prologue and the epilogue, loads always one tile ahead.
 #pragma once
 #include "hp_kernels.cuh"
 
@@ -35,11 +38,13 @@ namespace hp {
 
 constexpr int kFTR = 64;            // tile rows
 constexpr int kFTD = 64;            // tile diagonals
-constexpr int kFThreads = 256;
+constexpr int kFThreads = 512;
+constexpr int kFWarps = kFThreads / 32;
 constexpr int kFNPX = 8;            // pixels (consecutive columns of one row) per thread and pass
-constexpr int kFRowHalo = 16;       // tile row 0 is matrix row r0 - 16 (>= FM, and a multiple of 16: whole 32-byte sectors)
+constexpr int kFRowHalo = 16;       // tile row 0 is matrix row r0 - 16 (>= FM)
 constexpr int kFXR = kFTR + 2 * kFRowHalo;
-constexpr int kFChunkTiles = 4;     // row tiles per work item (a CTA keeps the overlapping rows between them)
+constexpr int kFStages = 2;         // tiles in shared memory per CTA
+constexpr int kFPasses = 2 * (kFTD / kFNPX);    // (row half, column block) passes of a tile
 constexpr int kFQCap = 32 * kFNPX;  // per-warp record queue: every pixel of a pass
 constexpr unsigned kFScratch = 1024;            // E.max() contenders a CTA keeps until it knows its final lower bound
 constexpr unsigned kFCandChunk = 128;           // candidate slots a warp reserves at a time (unused ones are marked r = -1)
@@ -61,12 +66,11 @@ struct FCand {                      // 16 B: a classified pixel whose Poisson p 
 };
 
 struct FastArgs {
-    const double* bal;              // quad-interleaved balanced plane
-    const unsigned char* lvl;
-    const double* b1;
-    const double* b2;
     const float* ffac;              // [1 + 2F][2][nexec][num]: fp32 IR[d] / bE, laid out like betab
                                     // (0: the pixel is certainly invalid, NaN: fp32 cannot hold the factor)
+    const float* ffs;               // [nstrips][2][nexec][kFTD]: the interior (z = 0) part of ffac, one block per strip
+    const float* b1f;               // fp32 biases of the rows, zero padded (k_fast_bias)
+    const float* b2s;               // fp32 biases of the columns, shifted: b2s[i] = B2[i + dlo], zero padded
     const Tables* tab;
     unsigned int* hist;             // [2][total_bins]
     unsigned long long* nvalid;     // [2]
@@ -74,10 +78,10 @@ struct FastArgs {
     XRec* xrec;
     int4* scratch;                  // [gridDim.x][kFScratch] (r, d | step << 16, hi of K or 0, hi of Y or 0)
     unsigned int* cnt;              // d_cnt: [2] chunk overflow, [8] fcand, [9] fcand dropped, [10] xrec, [11] xrec dropped,
-                                    //        [13] work counter, [14..15] running max of lo
+                                    //        [14..15] running max of lo
     unsigned int fcand_cap, xrec_cap;
     int n, num, pitch, dlo, dhi, F, nexec, maxchunk, total_bins;
-    int nstrips, nchunks, ntr;
+    int nstrips, ntr;
     int p, w0;                      // the (pw, ww) pair of the run
     unsigned c1dn, c2dn, c1up, c2up;   // FastEdges (host: fast_edges())
 };
@@ -254,22 +258,25 @@ __host__ __device__ __forceinline__ int fast_classify(float S, float es, float f
     return 1;
 }
 
-// shared-memory layout of a k_score_fast CTA (offsets in bytes)
+// shared-memory layout of a k_score_fast CTA (offsets in bytes): kFStages tile stages, then the per-CTA state
 template <int FM, int NEX>
 struct FastLayout {
     static constexpr size_t al(size_t x) { return (x + 127) & ~(size_t)127; }
     static constexpr int PX = fast_px(FM);
-    static constexpr size_t oXS = 0;                                             // float [kFXR][PX]
-    static constexpr size_t oOBS = al(oXS + (size_t)kFXR * PX * 4);              // int   [kFTD][4][kFTR / 4] raw counts (TMA)
-    static constexpr size_t oHIST = al(oOBS + (size_t)kFTD * kFTR * 4);          // u32   [2][kShI][kShK]
+    // one stage (everything in it arrives by TMA / bulk copies on the stage's mbarrier)
+    static constexpr size_t sXS = 0;                                             // float [kFXR][PX] fp32 balanced tile
+    static constexpr size_t sOBS = al(sXS + (size_t)kFXR * PX * 4);              // int   [kFTD][4][kFTR / 4] raw counts
+    static constexpr size_t sLVL = al(sOBS + (size_t)kFTD * kFTR * 4);           // u8    [kFTD][4][kFTR / 4] levels
+    static constexpr size_t sFTAB = al(sLVL + (size_t)kFTD * kFTR);              // float [2][nexec][kFTD] (nexec <= NEX)
+    static constexpr size_t sB1 = al(sFTAB + (size_t)2 * NEX * kFTD * 4);        // float [kFTR]
+    static constexpr size_t sB2 = al(sB1 + kFTR * 4);                            // float [kFTR + kFTD]
+    static constexpr size_t stage = al(sB2 + (kFTR + kFTD) * 4);
+    static constexpr size_t oHIST = kFStages * stage;                            // u32   [2][kShI][kShK]
     static constexpr size_t oQ = al(oHIST + (size_t)2 * kShI * kShK * 4);        // uint4 [warps][kFQCap] K, Y, err pack, meta
-    static constexpr size_t oFTAB = al(oQ + (size_t)(kFThreads / 32) * kFQCap * 16);   // float [2][NEX][kFTD]
-    static constexpr size_t oB1 = al(oFTAB + (size_t)2 * NEX * kFTD * 4);        // float [kFTR]
-    static constexpr size_t oB2 = al(oB1 + kFTR * 4);                            // float [kFTR + kFTD]
-    static constexpr size_t oCINFO = al(oB2 + (kFTR + kFTD) * 4);                // int4  [kChunkTab]
-    static constexpr size_t oLVL = al(oCINFO + (size_t)kChunkTab * 16);          // u8    [kFTD][4][kFTR / 4] levels of the tile
-    static constexpr size_t oMISC = al(oLVL + (size_t)kFTD * kFTR);              // runmax[2], work, mbarrier
+    static constexpr size_t oCINFO = al(oQ + (size_t)kFWarps * kFQCap * 16);     // int4  [kChunkTab]
+    static constexpr size_t oMISC = al(oCINFO + (size_t)kChunkTab * 16);         // runmax[2], counters, mbarriers
     static constexpr size_t bytes = oMISC + 128;
+    static constexpr uint32_t tx_fixed = (uint32_t)(kFXR * PX * 4 + kFTD * kFTR * 4 + kFTD * kFTR + kFTR * 4 + (kFTR + kFTD) * 4);
 };
 
 #ifdef __CUDACC__
@@ -278,41 +285,71 @@ __device__ __forceinline__ unsigned smem_ld_volatile(const unsigned* p) {
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
     return v;
 }
+__device__ __forceinline__ void smem_st_volatile(unsigned* p, unsigned v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
 __device__ __forceinline__ void gmem_red_add(unsigned* p, unsigned v) {
     asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void gmem_red_max(unsigned* p, unsigned v) {
+    asm volatile("red.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void smem_red_max32(unsigned* p, unsigned v) {
     asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
+// plain (non-tensor) bulk copy global -> shared, completing on an mbarrier; 16-byte aligned addresses and size
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 template <int FM>
-__global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_constant__ CUtensorMap tm_raw, const __grid_constant__ FastArgs A) {
+__global__ void __launch_bounds__(kFThreads, 1) k_score_fast(const __grid_constant__ CUtensorMap tm_raw, const __grid_constant__ CUtensorMap tm_x,
+                                                             const __grid_constant__ CUtensorMap tm_lvl, const __grid_constant__ FastArgs A) {
     using FP = FastPass<FM>;
     constexpr int PX = FP::PX;
-    constexpr int XC = kFTD + 4 * FM;                  // tile columns: diagonals d0 - 2 FM .. d0 + 63 + 2 FM
     constexpr int NEX = FM;                            // executed steps: at most FM - w + 1
     const int P = A.p, W0 = A.w0;
     using LY = FastLayout<FM, NEX>;
     extern __shared__ __align__(128) unsigned char smem[];
-    float* const xs = reinterpret_cast<float*>(smem + LY::oXS);
-    int* const obs = reinterpret_cast<int*>(smem + LY::oOBS);
     unsigned int* const shist = reinterpret_cast<unsigned int*>(smem + LY::oHIST);
-    float* const ftab = reinterpret_cast<float*>(smem + LY::oFTAB);
-    float* const b1t = reinterpret_cast<float*>(smem + LY::oB1);
-    float* const b2t = reinterpret_cast<float*>(smem + LY::oB2);
     int4* const cinfo = reinterpret_cast<int4*>(smem + LY::oCINFO);
-    unsigned char* const lvt = smem + LY::oLVL;
-    unsigned int* const runmax = reinterpret_cast<unsigned int*>(smem + LY::oMISC);
-    int* const work = reinterpret_cast<int*>(smem + LY::oMISC + 8);
-    unsigned int* const nscr = reinterpret_cast<unsigned int*>(smem + LY::oMISC + 12);
-    unsigned int* const npass = reinterpret_cast<unsigned int*>(smem + LY::oMISC + 24);
-    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + LY::oMISC + 16);
+    unsigned int* const runmax = reinterpret_cast<unsigned int*>(smem + LY::oMISC);          // [2]
+    unsigned int* const nscr = reinterpret_cast<unsigned int*>(smem + LY::oMISC + 8);
+    unsigned int* const claim = reinterpret_cast<unsigned int*>(smem + LY::oMISC + 12);
+    unsigned int* const done = reinterpret_cast<unsigned int*>(smem + LY::oMISC + 16);       // [kFStages]
+    uint64_t* const full_bar = reinterpret_cast<uint64_t*>(smem + LY::oMISC + 32);           // [kFStages]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
-    const int nexec = A.nexec, n = A.n, num = A.num, pitch = A.pitch, mc = A.maxchunk;
-    const size_t sp = (size_t)(pitch >> 2);
+    const int nexec = A.nexec, n = A.n, num = A.num, mc = A.maxchunk;
     uint4* const q = reinterpret_cast<uint4*>(smem + LY::oQ) + warp * kFQCap;
     const FastEdges ed{A.c1dn, A.c2dn, A.c1up, A.c2up};
+    // this CTA's tiles: items blockIdx.x, blockIdx.x + gridDim.x, ...  Item order: the strip next to the diagonal first
+    // (E.max() lives there: once its lower bound is known, no pixel of the other strips is sent to the exact list as a
+    // contender), then the far strips (the deepest levels, the longest tiles) first.
+    const int items = A.nstrips * A.ntr;
+    const int ntiles = ((int)blockIdx.x < items) ? (items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    auto tile_of = [&](int j, int& strip, int& r0) {
+        const int item = (int)blockIdx.x + j * (int)gridDim.x;
+        const int sk = item / A.ntr;
+        strip = sk == 0 ? 0 : A.nstrips - sk;
+        r0 = (item - sk * A.ntr) * kFTR;
+    };
+    // one thread: every copy of tile j onto the mbarrier of stage j & 1
+    auto issue = [&](int j) {
+        int strip, r0;
+        tile_of(j, strip, r0);
+        unsigned char* const sb = smem + (size_t)(j & 1) * LY::stage;
+        uint64_t* const bar = full_bar + (j & 1);
+        const uint32_t ftb = (uint32_t)(2 * nexec * kFTD * 4);
+        mbar_expect_tx(bar, LY::tx_fixed + ftb);
+        tma_load_2d(sb + LY::sXS, &tm_x, strip * kFTD - 2 * FM, r0 - kFRowHalo, bar);
+        tma_load_3d(sb + LY::sOBS, &tm_raw, r0 / 4, 0, A.dlo + strip * kFTD, bar);
+        tma_load_3d(sb + LY::sLVL, &tm_lvl, r0 / 4, 0, A.dlo + strip * kFTD, bar);
+        bulk_load(sb + LY::sFTAB, A.ffs + (size_t)strip * 2 * nexec * kFTD, ftb, bar);
+        bulk_load(sb + LY::sB1, A.b1f + r0, kFTR * 4, bar);
+        bulk_load(sb + LY::sB2, A.b2s + r0 + strip * kFTD, (kFTR + kFTD) * 4, bar);
+    };
     {
         const Chunks& C = A.tab->chunks;
         for (int i = tid; i < kChunkTab; i += kFThreads) {
@@ -321,289 +358,213 @@ __global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_consta
         }
         for (int i = tid; i < 2 * kShI * kShK; i += kFThreads) shist[i] = 0u;
         if (tid == 0) {
-            runmax[0] = 0u; runmax[1] = 0u; *nscr = 0u;
-            mbar_init(bar, 1);
+            runmax[0] = 0u; runmax[1] = 0u; *nscr = 0u; *claim = 0u;
+            for (int s = 0; s < kFStages; ++s) { done[s] = 0u; mbar_init(full_bar + s, 1); }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (int j = 0; j < kFStages && j < ntiles; ++j) issue(j);
         }
     }
     __syncthreads();
-    unsigned obs_phase = 0;
     unsigned nvk = 0, nvy = 0;                          // valid pixels this thread classified (K / Y)
     unsigned cbase = 0, cused = kFCandChunk;            // this warp's piece of the candidate list (warp-uniform)
 
+#pragma unroll 1
     for (;;) {
-        if (tid == 0) {
-            *work = (int)atomicAdd(&A.cnt[13], 1u);
-            const unsigned g0 = A.cnt[14], g1 = A.cnt[15];          // other CTAs' running maxima (any value read is a valid bound)
-            if (g0 > runmax[0]) smem_red_max32(&runmax[0], g0);
-            if (g1 > runmax[1]) smem_red_max32(&runmax[1], g1);
-        }
-        __syncthreads();
-        const int item = *work;
-        if (item >= A.nstrips * A.nchunks) break;
-        // The strip next to the diagonal first: E.max() lives there, and once its lower bound is known no pixel of the other
-        // strips is sent to the exact list as a contender.  Then the far strips (the deepest levels, the longest tiles) first.
-        const int sk = item / A.nchunks;
-        const int strip = sk == 0 ? 0 : A.nstrips - sk;
-        const int chunk = item % A.nchunks;
+        unsigned g = 0;
+        if (lane == 0) g = smem_atom_add(claim, 1u);
+        g = __shfl_sync(full, g, 0);
+        const int j = (int)(g / kFPasses), ps = (int)(g % kFPasses);
+        if (j >= ntiles) break;
+        const int st = j & 1;
+        int strip, r0;
+        tile_of(j, strip, r0);
         const int d0 = A.dlo + strip * kFTD;
-        const int t0 = chunk * kFChunkTiles, t1 = min(A.ntr, t0 + kFChunkTiles);
-        for (int i = tid; i < 2 * nexec * kFTD; i += kFThreads) {
-            const int fs = i / kFTD, d = d0 + (i % kFTD);
-            ftab[i] = d < num ? A.ffac[(size_t)fs * num + d] : 0.f;            // z = 0: interior pixels
-        }
-        const unsigned nplanes = (unsigned)(num - A.dlo);                   // planes below min(ww) hold no balanced values
-        const unsigned long long pstep = (unsigned long long)pitch * 8ull;     // bytes from one plane to the next
-        auto fill_load = [&](int rg, int cg, int xlo, int r0, double (&v)[4], int& at, bool on) {
-            const int x = xlo + 32 * rg + lane;
-            const int rr = r0 - kFRowHalo + x;
-            const int db = d0 - 2 * FM + 4 * cg;
-            at = x * PX + 4 * cg;
-            const bool rok = on && (unsigned)rr < (unsigned)pitch;
-            // one 64-bit address per task, then a step of one plane per load
-            const char* p = reinterpret_cast<const char*>(A.bal) +
-                            ((long long)db * pitch + (long long)(rr & 3) * (long long)sp + (rr >> 2)) * 8ll;
-            const unsigned pl = (unsigned)(db - A.dlo);
-            v[0] = (rok && pl < nplanes) ? __ldg(reinterpret_cast<const double*>(p)) : 0.0;
-            p += pstep;
-            v[1] = (rok && pl + 1u < nplanes) ? __ldg(reinterpret_cast<const double*>(p)) : 0.0;
-            p += pstep;
-            v[2] = (rok && pl + 2u < nplanes) ? __ldg(reinterpret_cast<const double*>(p)) : 0.0;
-            p += pstep;
-            v[3] = (rok && pl + 3u < nplanes) ? __ldg(reinterpret_cast<const double*>(p)) : 0.0;
-        };
-        auto fill_store = [&](const double (&v)[4], int at) {
-            float4 o;
-            o.x = (float)v[0]; o.y = (float)v[1]; o.z = (float)v[2]; o.w = (float)v[3];
-            *reinterpret_cast<float4*>(xs + at) = o;
-        };
-        constexpr int NW = kFThreads / 32;
-        constexpr int NPF = 2 * ((XC / 4 + NW - 1) / NW);                  // tasks per warp for the 64 new rows of a tile:
-                                                                            // task k = row group k & 1, column group warp + 8 (k >> 1)
-        double nx[NPF][4];                                                  // the next tile's new rows, in flight across the tile barrier
-        int nat[NPF];
-        for (int tr = t0; tr < t1; ++tr) {
-            const int r0 = tr * kFTR;
-            if (tid == 0) {                             // raw counts of the tile: needed when the records are closed
-                *npass = 0u;
-                mbar_expect_tx(bar, (uint32_t)(kFTD * kFTR * 4));
-                tma_load_3d(obs, &tm_raw, r0 / 4, 0, d0, bar);
-            }
-            // levels of the tile: one 16-byte row piece (16 row quads of one (diagonal, row & 3)) per thread, as two 8-byte
-            // loads (issued now, stored after the tile has been filled)
-            uint2 lva = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu), lvb = lva;
-            {
-                const int dl = tid >> 2, qq = tid & 3, d = d0 + dl;
-                if (d <= A.dhi && d < num) {
-                    const unsigned char* src = A.lvl + (size_t)d * pitch + (size_t)qq * sp + (r0 >> 2);
-                    if (r0 + 32 <= pitch) lva = *reinterpret_cast<const uint2*>(src);
-                    if (r0 + 64 <= pitch) lvb = *reinterpret_cast<const uint2*>(src + 8);
-                }
-            }
-            // ---- fill the fp32 tile ----------------------------------------------------------------------------
-            // A warp task: 32 consecutive matrix rows (one per lane: coalesced in every plane) x 4 planes -> one 128-bit
-            // store per lane.  The first tile of a work item loads all 96 rows here; for the others, rows 0 .. 31 are the
-            // previous tile's rows 64 .. 95 and the 64 new rows were requested at the end of the previous tile (below).
-            if (tr > t0) {
-                for (int i = tid; i < 32 * (PX / 4); i += kFThreads) {
-                    const int x = i / (PX / 4), c4 = i % (PX / 4);
-                    reinterpret_cast<float4*>(xs + (size_t)x * PX)[c4] = reinterpret_cast<const float4*>(xs + (size_t)(x + 64) * PX)[c4];
-                }
-                __syncthreads();
-#pragma unroll
-                for (int k = 0; k < NPF; ++k)
-                    if (warp + (k >> 1) * NW < XC / 4) fill_store(nx[k], nat[k]);
-            } else {
-#pragma unroll 1
-                for (int cg = warp; cg < XC / 4; cg += NW) {                   // three tasks (12 loads) in flight per thread
-                    double va[3][4];
-                    int aa[3];
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) fill_load(k, cg, 0, r0, va[k], aa[k], true);
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) fill_store(va[k], aa[k]);
-                }
-            }
-            reinterpret_cast<uint4*>(lvt)[tid] = make_uint4(lva.x, lva.y, lvb.x, lvb.y);
-            for (int i = tid; i < kFTR; i += kFThreads) b1t[i] = r0 + i < n ? fast_bias(A.b1[r0 + i]) : 0.f;
-            for (int i = tid; i < kFTR + kFTD; i += kFThreads) {
-                const int c = r0 + d0 + i;
-                b2t[i] = c < n ? fast_bias(A.b2[c]) : 0.f;
-            }
-            __syncthreads();
-            mbar_wait(bar, obs_phase);
-            obs_phase ^= 1u;
+        unsigned char* const sb = smem + (size_t)st * LY::stage;
+        const float* const xs = reinterpret_cast<const float*>(sb + LY::sXS);
+        const int* const obs = reinterpret_cast<const int*>(sb + LY::sOBS);
+        const unsigned char* const lvt = sb + LY::sLVL;
+        const float* const ftab = reinterpret_cast<const float*>(sb + LY::sFTAB);
+        const float* const b1t = reinterpret_cast<const float*>(sb + LY::sB1);
+        const float* const b2t = reinterpret_cast<const float*>(sb + LY::sB2);
+        mbar_wait(full_bar + st, (unsigned)(j >> 1) & 1u);
 
-            // ---- the sums: two passes of 8 columns per thread ------------------------------------------------------
-            // the 16 (row half, column block) passes of the tile are claimed by the warps as they get free
-#pragma unroll 1
-            for (;;) {
-                int ps = 0;
-                if (lane == 0) ps = (int)smem_atom_add(npass, 1u);
-                ps = __shfl_sync(full, ps, 0);
-                if (ps >= 2 * (kFTD / kFNPX)) break;
-                const int cb = ps >> 1;
-                const int rl = 32 * (ps & 1) + lane;   // this thread's row of the tile
-                unsigned lvpk = 0, mine = 0, slotpk0 = 0, slotpk1 = 0;
-                int cnt = 0;                            // records of this warp and pass (warp-uniform)
+        // ---- the sums of one pass: 32 rows (one per lane) x 8 columns ---------------------------------------------
+        const int cb = ps >> 1;
+        const int rl = 32 * (ps & 1) + lane;           // this thread's row of the tile
+        unsigned lvpk = 0, mine = 0, slotpk0 = 0, slotpk1 = 0;
+        int cnt = 0;                                    // records of this warp and pass (warp-uniform)
+        {
+            const unsigned char* lp = lvt + (kFNPX * cb * 4 + (rl & 3)) * (kFTR / 4) + (rl >> 2);
+            const int r = r0 + rl;
 #pragma unroll
-                for (int i = 0; i < kFNPX; ++i) {
-                    // stale bytes beyond the chromosome or the band never reach here as levels: (r, d) is checked
-                    const int r = r0 + rl, d = d0 + kFNPX * cb + i;
-                    const unsigned lv = lvt[((kFNPX * cb + i) * 4 + (rl & 3)) * (kFTR / 4) + (rl >> 2)];
-                    const unsigned code = (lv < (unsigned)nexec && d <= A.dhi && r < n && r + d < n) ? lv : 0xFu;
-                    lvpk |= code << (4 * i);
-                    const bool e = code != 0xFu;
-                    if (e) mine |= 1u << code;
-                    const unsigned mb = __ballot_sync(full, e);
-                    const unsigned slot = (unsigned)cnt + __popc(mb & lt);       // < 256
-                    if (i < 4) slotpk0 |= slot << (8 * i); else slotpk1 |= slot << (8 * (i - 4));
-                    cnt += __popc(mb);
-                }
-                const unsigned lvmask = __reduce_or_sync(full, mine);
-                if (lvmask == 0u) continue;             // no resolved pixel in these 32 rows x 8 columns
-                const int ft = W0 + (31 - __clz((int)lvmask));
-                // element (r + a, c0 - FM + t) sits at tile column (d0 + 8 cb - FM + t - a) - (d0 - 2 FM) = 8 cb + FM + t - a
-                const float* xrow = xs + (size_t)(rl + kFRowHalo) * PX + kFNPX * cb;
-                const unsigned mbase = (unsigned)rl | ((unsigned)(kFNPX * cb) << 6);
-                FP::run(xrow, P, W0, lvpk, lvmask, ft, [&](auto I, unsigned sc, float kv, float yv, unsigned epk) {
-                    constexpr int i = decltype(I)::value;
-                    const unsigned slot = ((i < 4 ? slotpk0 : slotpk1) >> (8 * (i & 3))) & 0xffu;
-                    q[slot] = make_uint4(__float_as_uint(kv), __float_as_uint(yv), epk, mbase + ((unsigned)i << 6) + (sc << 12));
-                });
-                __syncwarp();
-                // ---- close the records: classify both backgrounds, account the certain ones ---------------------------
-#pragma unroll 1
-                for (int b0 = 0; b0 < cnt; b0 += 32) {
-                    const bool act = b0 + lane < cnt;
-                    const uint4 rec = act ? q[b0 + lane] : make_uint4(0u, 0u, 0u, 0u);
-                    const unsigned m = rec.w;
-                    const int rrl = m & 63, dl = (m >> 6) & 63, s = (m >> 12) & 15;
-                    const int r = r0 + rrl, d = d0 + dl;
-                    const int ob = obs[(dl * 4 + (rrl & 3)) * (kFTR / 4) + (rrl >> 2)];
-                    float fk = ftab[s * kFTD + dl], fy = ftab[(nexec + s) * kFTD + dl];
-                    const bool top = r < A.F, end = r + d >= n - A.F;
-                    if (act && (top || end)) {          // next to a chromosome end: the factor tables of that row / column
-                        const int z = top ? 1 + r : 1 + A.F + (n - 1 - r - d);
-                        const size_t at = ((size_t)(z * 2) * nexec + s) * num + d;
-                        fk = (top && end) ? NAN : A.ffac[at];                    // next to both: bE is a walk over the cell list
-                        fy = (top && end) ? NAN : A.ffac[at + (size_t)nexec * num];
-                    }
-                    const float bb = b1t[rrl] * b2t[rrl + dl];
-                    int ck, cy;
-                    float lo0, hi0, lo1, hi1;
-                    const int c0 = fast_classify(__uint_as_float(rec.x), __uint_as_float(rec.z << 16), fk, bb, ed, mc, ck, lo0, hi0);
-                    const int c1 = fast_classify(__uint_as_float(rec.y), __uint_as_float(rec.z & 0xFFFF0000u), fy, bb, ed, mc, cy, lo1, hi1);
-                    const bool ex = act && (c0 == 2 || c1 == 2 || !(bb == bb));
-                    const bool ok = act && !ex;
-                    unsigned flags = 0, emk = 0;
-                    bool cand = false;
-                    if (ok && c0 == 1) {
-                        flags |= HP_SF_VALID_K;
-                        ++nvk;
-                        if (ck > mc) {
-                            gmem_red_add(&A.cnt[2], 1u);
-                        } else {
-                            const int4 inf = cinfo[ck];
-                            const int kb = ob < inf.y - 1 ? ob : inf.y - 1;
-                            if (ck <= kShI && kb < kShK) smem_red_add(&shist[(ck - 1) * kShK + kb], 1u);
-                            else gmem_red_add(&A.hist[(size_t)inf.x + kb], 1u);
-                            cand |= ob >= inf.z;
-                        }
-                        // E.max(): a record whose interval reaches the largest lower bound seen so far is evaluated exactly
-                        const unsigned cur = smem_ld_volatile(&runmax[0]);
-                        if (__float_as_uint(hi0) >= cur) emk |= 1u;
-                        if (__float_as_uint(lo0) > cur) smem_red_max32(&runmax[0], __float_as_uint(lo0));
-                    }
-                    if (ok && c1 == 1) {
-                        flags |= HP_SF_VALID_Y | HP_SF_CEMY_NONZERO;
-                        ++nvy;
-                        if (cy > mc) {
-                            gmem_red_add(&A.cnt[2], 1u);
-                        } else {
-                            const int4 inf = cinfo[cy];
-                            const int kb = ob < inf.y - 1 ? ob : inf.y - 1;
-                            if (cy <= kShI && kb < kShK) smem_red_add(&shist[(kShI + cy - 1) * kShK + kb], 1u);
-                            else gmem_red_add(&A.hist[(size_t)A.total_bins + inf.x + kb], 1u);
-                            cand |= ob >= inf.z;
-                        }
-                        const unsigned cur = smem_ld_volatile(&runmax[1]);
-                        if (__float_as_uint(hi1) >= cur) emk |= 2u;
-                        if (__float_as_uint(lo1) > cur) smem_red_max32(&runmax[1], __float_as_uint(lo1));
-                    }
-                    // candidates (classified records whose Poisson tail can pass sig) go to the warp's own piece of the
-                    // list: one global atomic per kFCandChunk records instead of one (with its round trip) per batch
-                    const unsigned mcand = __ballot_sync(full, cand);
-                    if (mcand) {
-                        const unsigned nc = __popc(mcand);
-                        if (cused + nc > kFCandChunk) {
-                            if (cused < kFCandChunk && lane < kFCandChunk - cused && cbase + cused + lane < A.fcand_cap)
-                                A.fcand[cbase + cused + lane].r = -1;            // (a warp leaves at most 31 slots behind)
-                            if (cused < kFCandChunk && kFCandChunk - cused > 32 && lane + 32 < kFCandChunk - cused &&
-                                cbase + cused + lane + 32 < A.fcand_cap)
-                                A.fcand[cbase + cused + lane + 32].r = -1;
-                            unsigned nb = 0;
-                            if (lane == 0) nb = atomicAdd(&A.cnt[8], kFCandChunk);
-                            cbase = __shfl_sync(full, nb, 0);
-                            cused = 0;
-                        }
-                        if (cand) {
-                            const unsigned slot = cbase + cused + __popc(mcand & lt);
-                            if (slot < A.fcand_cap)
-                                *reinterpret_cast<int4*>(&A.fcand[slot]) =
-                                    make_int4(r, d | (s << 16), ob, (int)((unsigned)ck | ((unsigned)cy << 8) | (flags << 16)));
-                            else gmem_red_add(&A.cnt[9], 1u);
-                        }
-                        cused += nc;
-                    }
-                    // records the exact kernel must evaluate and account
-                    const unsigned mx = __ballot_sync(full, ex);
-                    if (mx) {
-                        unsigned base = 0;
-                        if (lane == 0) base = atomicAdd(&A.cnt[10], (unsigned)__popc(mx));
-                        base = __shfl_sync(full, base, 0);
-                        if (ex) {
-                            const unsigned slot = base + __popc(mx & lt);
-                            if (slot < A.xrec_cap) *reinterpret_cast<int4*>(&A.xrec[slot]) = make_int4(r, d | (s << 16), ob, 0);
-                            else gmem_red_add(&A.cnt[11], 1u);
-                        }
-                    }
-                    // E.max() contenders wait in the CTA's scratch list: most of them fall below the bound the CTA ends with
-                    const unsigned me = __ballot_sync(full, emk != 0u);
-                    if (me) {
-                        unsigned base = 0;
-                        if (lane == 0) base = smem_atom_add(nscr, (unsigned)__popc(me));
-                        base = __shfl_sync(full, base, 0);
-                        if (emk) {
-                            const unsigned slot = base + __popc(me & lt);
-                            const int hk = (emk & 1u) ? __float_as_int(hi0) : 0, hy = (emk & 2u) ? __float_as_int(hi1) : 0;
-                            if (slot < kFScratch) {
-                                A.scratch[(size_t)blockIdx.x * kFScratch + slot] = make_int4(r, d | (s << 16), hk, hy);
-                            } else {                       // scratch full: straight to the exact list
-                                const unsigned g = atomicAdd(&A.cnt[10], 1u);
-                                if (g < A.xrec_cap) *reinterpret_cast<int4*>(&A.xrec[g]) = make_int4(r, d | (s << 16), ob, (int)emk);
-                                else atomicAdd(&A.cnt[11], 1u);
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
+            for (int i = 0; i < kFNPX; ++i) {
+                // stale bytes beyond the chromosome or the band never reach here as levels: (r, d) is checked
+                const int d = d0 + kFNPX * cb + i;
+                const unsigned lv = lp[i * kFTR];
+                const unsigned code = (lv < (unsigned)nexec && d <= A.dhi && r < n && r + d < n) ? lv : 0xFu;
+                lvpk |= code << (4 * i);
+                const bool e = code != 0xFu;
+                if (e) mine |= 1u << code;
+                const unsigned mb = __ballot_sync(full, e);
+                const unsigned slot = (unsigned)cnt + __popc(mb & lt);       // < 256
+                if (i < 4) slotpk0 |= slot << (8 * i); else slotpk1 |= slot << (8 * (i - 4));
+                cnt += __popc(mb);
             }
-            // This warp is done with the tile: request its share of the next tile's new rows now, so that the loads fly while
-            // the other warps finish (no register is needed for anything else until the barrier)
-            // (unconditional definitions: the registers are dead during the sums)
-#pragma unroll
-            for (int k = 0; k < NPF; ++k)
-                fill_load(k & 1, warp + (k >> 1) * NW, 32, r0 + kFTR, nx[k], nat[k], tr + 1 < t1 && warp + (k >> 1) * NW < XC / 4);
-            __syncthreads();                            // tile, count tile and bias tables are free again
         }
-        if (tid == 0) {
-            if (runmax[0]) atomicMax(&A.cnt[14], runmax[0]);
-            if (runmax[1]) atomicMax(&A.cnt[15], runmax[1]);
+        const unsigned lvmask = __reduce_or_sync(full, mine);
+        if (lvmask != 0u) {                             // (else: no resolved pixel in these 32 rows x 8 columns)
+            const int ft = W0 + (31 - __clz((int)lvmask));
+            // element (r + a, c0 - FM + t) sits at tile column (d0 + 8 cb - FM + t - a) - (d0 - 2 FM) = 8 cb + FM + t - a
+            const float* xrow = xs + (size_t)(rl + kFRowHalo) * PX + kFNPX * cb;
+            const unsigned mbase = (unsigned)rl | ((unsigned)(kFNPX * cb) << 6);
+            FP::run(xrow, P, W0, lvpk, lvmask, ft, [&](auto I, unsigned sc, float kv, float yv, unsigned epk) {
+                constexpr int i = decltype(I)::value;
+                const unsigned slot = ((i < 4 ? slotpk0 : slotpk1) >> (8 * (i & 3))) & 0xffu;
+                q[slot] = make_uint4(__float_as_uint(kv), __float_as_uint(yv), epk, mbase + ((unsigned)i << 6) + (sc << 12));
+            });
+            __syncwarp();
+            // ---- close the records: classify both backgrounds, account the certain ones ---------------------------
+#pragma unroll 1
+            for (int b0 = 0; b0 < cnt; b0 += 32) {
+                const bool act = b0 + lane < cnt;
+                const uint4 rec = act ? q[b0 + lane] : make_uint4(0u, 0u, 0u, 0u);
+                const unsigned m = rec.w;
+                const int rrl = m & 63, dl = (m >> 6) & 63, s = (m >> 12) & 15;
+                const int r = r0 + rrl, d = d0 + dl;
+                const int ob = obs[(dl * 4 + (rrl & 3)) * (kFTR / 4) + (rrl >> 2)];
+                float fk = ftab[s * kFTD + dl], fy = ftab[(nexec + s) * kFTD + dl];
+                const bool top = r < A.F, end = r + d >= n - A.F;
+                if (act && (top || end)) {              // next to a chromosome end: the factor tables of that row / column
+                    const int z = top ? 1 + r : 1 + A.F + (n - 1 - r - d);
+                    const size_t at = ((size_t)(z * 2) * nexec + s) * num + d;
+                    fk = (top && end) ? NAN : A.ffac[at];                    // next to both: bE is a walk over the cell list
+                    fy = (top && end) ? NAN : A.ffac[at + (size_t)nexec * num];
+                }
+                const float bb = b1t[rrl] * b2t[rrl + dl];
+                int ck, cy;
+                float lo0, hi0, lo1, hi1;
+                const int c0 = fast_classify(__uint_as_float(rec.x), __uint_as_float(rec.z << 16), fk, bb, ed, mc, ck, lo0, hi0);
+                const int c1 = fast_classify(__uint_as_float(rec.y), __uint_as_float(rec.z & 0xFFFF0000u), fy, bb, ed, mc, cy, lo1, hi1);
+                const bool ex = act && (c0 == 2 || c1 == 2 || !(bb == bb));
+                const bool ok = act && !ex;
+                unsigned flags = 0, emk = 0;
+                bool cand = false;
+                if (ok && c0 == 1) {
+                    flags |= HP_SF_VALID_K;
+                    ++nvk;
+                    if (ck > mc) {
+                        gmem_red_add(&A.cnt[2], 1u);
+                    } else {
+                        const int4 inf = cinfo[ck];
+                        const int kb = ob < inf.y - 1 ? ob : inf.y - 1;
+                        if (ck <= kShI && kb < kShK) smem_red_add(&shist[(ck - 1) * kShK + kb], 1u);
+                        else gmem_red_add(&A.hist[(size_t)inf.x + kb], 1u);
+                        cand |= ob >= inf.z;
+                    }
+                    // E.max(): a record whose interval reaches the largest lower bound seen so far is evaluated exactly
+                    const unsigned cur = smem_ld_volatile(&runmax[0]);
+                    if (__float_as_uint(hi0) >= cur) emk |= 1u;
+                    if (__float_as_uint(lo0) > cur) smem_red_max32(&runmax[0], __float_as_uint(lo0));
+                }
+                if (ok && c1 == 1) {
+                    flags |= HP_SF_VALID_Y | HP_SF_CEMY_NONZERO;
+                    ++nvy;
+                    if (cy > mc) {
+                        gmem_red_add(&A.cnt[2], 1u);
+                    } else {
+                        const int4 inf = cinfo[cy];
+                        const int kb = ob < inf.y - 1 ? ob : inf.y - 1;
+                        if (cy <= kShI && kb < kShK) smem_red_add(&shist[(kShI + cy - 1) * kShK + kb], 1u);
+                        else gmem_red_add(&A.hist[(size_t)A.total_bins + inf.x + kb], 1u);
+                        cand |= ob >= inf.z;
+                    }
+                    const unsigned cur = smem_ld_volatile(&runmax[1]);
+                    if (__float_as_uint(hi1) >= cur) emk |= 2u;
+                    if (__float_as_uint(lo1) > cur) smem_red_max32(&runmax[1], __float_as_uint(lo1));
+                }
+                // candidates (classified records whose Poisson tail can pass sig) go to the warp's own piece of the
+                // list: one global atomic per kFCandChunk records instead of one (with its round trip) per batch
+                const unsigned mcand = __ballot_sync(full, cand);
+                if (mcand) {
+                    const unsigned nc = __popc(mcand);
+                    if (cused + nc > kFCandChunk) {
+                        if (cused < kFCandChunk && lane < kFCandChunk - cused && cbase + cused + lane < A.fcand_cap)
+                            A.fcand[cbase + cused + lane].r = -1;            // (a warp leaves at most 31 slots behind)
+                        if (cused < kFCandChunk && kFCandChunk - cused > 32 && lane + 32 < kFCandChunk - cused &&
+                            cbase + cused + lane + 32 < A.fcand_cap)
+                            A.fcand[cbase + cused + lane + 32].r = -1;
+                        unsigned nb = 0;
+                        if (lane == 0) nb = atomicAdd(&A.cnt[8], kFCandChunk);
+                        cbase = __shfl_sync(full, nb, 0);
+                        cused = 0;
+                    }
+                    if (cand) {
+                        const unsigned slot = cbase + cused + __popc(mcand & lt);
+                        if (slot < A.fcand_cap)
+                            *reinterpret_cast<int4*>(&A.fcand[slot]) =
+                                make_int4(r, d | (s << 16), ob, (int)((unsigned)ck | ((unsigned)cy << 8) | (flags << 16)));
+                        else gmem_red_add(&A.cnt[9], 1u);
+                    }
+                    cused += nc;
+                }
+                // records the exact kernel must evaluate and account
+                const unsigned mx = __ballot_sync(full, ex);
+                if (mx) {
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(&A.cnt[10], (unsigned)__popc(mx));
+                    base = __shfl_sync(full, base, 0);
+                    if (ex) {
+                        const unsigned slot = base + __popc(mx & lt);
+                        if (slot < A.xrec_cap) *reinterpret_cast<int4*>(&A.xrec[slot]) = make_int4(r, d | (s << 16), ob, 0);
+                        else gmem_red_add(&A.cnt[11], 1u);
+                    }
+                }
+                // E.max() contenders wait in the CTA's scratch list: most of them fall below the bound the CTA ends with
+                const unsigned me = __ballot_sync(full, emk != 0u);
+                if (me) {
+                    unsigned base = 0;
+                    if (lane == 0) base = smem_atom_add(nscr, (unsigned)__popc(me));
+                    base = __shfl_sync(full, base, 0);
+                    if (emk) {
+                        const unsigned slot = base + __popc(me & lt);
+                        const int hk = (emk & 1u) ? __float_as_int(hi0) : 0, hy = (emk & 2u) ? __float_as_int(hi1) : 0;
+                        if (slot < kFScratch) {
+                            A.scratch[(size_t)blockIdx.x * kFScratch + slot] = make_int4(r, d | (s << 16), hk, hy);
+                        } else {                       // scratch full: straight to the exact list
+                            const unsigned gx = atomicAdd(&A.cnt[10], 1u);
+                            if (gx < A.xrec_cap) *reinterpret_cast<int4*>(&A.xrec[gx]) = make_int4(r, d | (s << 16), ob, (int)emk);
+                            else atomicAdd(&A.cnt[11], 1u);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- this warp is done with its pass; the warp that finishes the last pass of the tile owns the stage: it
+        // exchanges the running E.max() bounds with the other CTAs and re-arms the stage with the tile after next --------
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            const unsigned old = smem_atom_add(done + st, 1u);
+            if (old == (unsigned)(kFPasses - 1)) {
+                __threadfence_block();
+                smem_st_volatile(done + st, 0u);
+                if (j + kFStages < ntiles) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(j + kFStages);
+                }
+                const unsigned g0 = A.cnt[14], g1 = A.cnt[15];          // (any value read is a valid bound)
+                const unsigned l0 = smem_ld_volatile(&runmax[0]), l1 = smem_ld_volatile(&runmax[1]);
+                if (g0 > l0) smem_red_max32(&runmax[0], g0); else if (l0 > g0) gmem_red_max(&A.cnt[14], l0);
+                if (g1 > l1) smem_red_max32(&runmax[1], g1); else if (l1 > g1) gmem_red_max(&A.cnt[15], l1);
+            }
         }
     }
     // ---- E.max() contenders that still reach the largest lower bound known now -> exact list ---------------------------
     __syncthreads();
+    if (tid == 0) {
+        if (runmax[0]) atomicMax(&A.cnt[14], runmax[0]);
+        if (runmax[1]) atomicMax(&A.cnt[15], runmax[1]);
+    }
     {
         const unsigned m0 = max(runmax[0], A.cnt[14]), m1 = max(runmax[1], A.cnt[15]);
         const unsigned ns = min(*nscr, kFScratch);
@@ -611,8 +572,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_consta
             const int4 c = A.scratch[(size_t)blockIdx.x * kFScratch + i];
             const int kind = ((c.z != 0 && (unsigned)c.z >= m0) ? 1 : 0) | ((c.w != 0 && (unsigned)c.w >= m1) ? 2 : 0);
             if (kind) {
-                const unsigned g = atomicAdd(&A.cnt[10], 1u);
-                if (g < A.xrec_cap) *reinterpret_cast<int4*>(&A.xrec[g]) = make_int4(c.x, c.y, 0, kind);
+                const unsigned gx = atomicAdd(&A.cnt[10], 1u);
+                if (gx < A.xrec_cap) *reinterpret_cast<int4*>(&A.xrec[gx]) = make_int4(c.x, c.y, 0, kind);
                 else atomicAdd(&A.cnt[11], 1u);
             }
         }
@@ -625,7 +586,6 @@ __global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_consta
         if (lane == 0 && a) atomicAdd(&A.nvalid[0], (unsigned long long)a);
         if (lane == 0 && b) atomicAdd(&A.nvalid[1], (unsigned long long)b);
     }
-    __syncthreads();
     for (int i = tid; i < 2 * kShI * kShK; i += kFThreads) {
         const unsigned v = shist[i];
         if (v) {
@@ -633,6 +593,35 @@ __global__ void __launch_bounds__(kFThreads, 2) k_score_fast(const __grid_consta
             atomicAdd(&A.hist[(size_t)fl * A.total_bins + cinfo[ci].x + kb], v);
         }
     }
+}
+
+// ---- upload-time companions: the fp32 row-major plane and the fp32 bias vectors the kernel's TMA / bulk copies read ----
+// xf[r][d - bf] = (float)balanced(r, r + d), row pitch ndp floats (a multiple of 4: 16-byte rows for the tensor map);
+// columns beyond the band and elements beyond the chromosome are zero (the fp64 plane has zero tails).
+__global__ void __launch_bounds__(256) k_f32plane(const double* __restrict__ bal, float* __restrict__ xf, int n, int num, int bf, int pitch,
+                                                  int ndp) {
+    __shared__ float t[32][65];                         // [diagonal][row]
+    const int r0 = blockIdx.x * 64, k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int dd = ty; dd < 32; dd += 8) {
+        const int d = bf + k0 + dd;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = r0 + 32 * h + tx;             // 32 consecutive rows of one plane: four 64-byte pieces
+            t[dd][32 * h + tx] = (d < num && r < pitch) ? (float)bal[qidx(d, r, pitch)] : 0.f;
+        }
+    }
+    __syncthreads();
+    for (int rr = ty; rr < 64; rr += 8) {
+        const int r = r0 + rr, k = k0 + tx;
+        if (r < n && k < ndp) xf[(size_t)r * ndp + k] = t[tx][rr];
+    }
+}
+__global__ void k_fast_bias(const double* __restrict__ b1, const double* __restrict__ b2, float* __restrict__ b1f, float* __restrict__ b2s,
+                            int n, int bf, int n1, int n2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n1) b1f[i] = i < n ? fast_bias(b1[i]) : 0.f;
+    if (i < n2) b2s[i] = i + bf < n ? fast_bias(b2[i + bf]) : 0.f;
 }
 #endif  // __CUDACC__
 
