@@ -84,8 +84,9 @@ struct hp_ctx {
     unsigned int* d_hist = nullptr; size_t cap_hist = 0;
     double* d_qtab = nullptr; size_t cap_qtab = 0;
     unsigned long long* d_small = nullptr;      // [0..15] emax bits, [16..31] nvalid, [32..47] nreject
-    unsigned int* d_cnt = nullptr;              // [0..3] cand counters, [4..7] survivor counters
+    unsigned int* d_cnt = nullptr;              // [0..3] cand counters, [4..7] survivor counters, [16..31] fast kernel: running E.max() bounds
     int* d_numbin = nullptr;                    // [16]
+    int* d_kq = nullptr;                        // [16][kMaxChunk + 2] per (pair, background, chunk): smallest count with q <= sig (k_bh)
     Cand* d_cand = nullptr; size_t cap_cand = 0;
     // re-associated score kernel (hp_score_fast.cuh): classified candidates without E, records for k_exact, fp32 factors
     FCand* d_fcand = nullptr; size_t cap_fcand = 0;
@@ -296,8 +297,9 @@ extern "C" int hp_ctx_create(int device, int max_chunks, const double* edges, hp
               cudaHostAlloc((void**)&ctx->h_res, 8192, cudaHostAllocDefault) == cudaSuccess &&
               cudaMalloc(&ctx->d_lhist, (HP_MAX_STEPS + 2) * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&ctx->d_small, 48 * sizeof(unsigned long long)) == cudaSuccess &&
-              cudaMalloc(&ctx->d_cnt, 16 * sizeof(unsigned int)) == cudaSuccess &&
-              cudaMalloc(&ctx->d_numbin, 16 * sizeof(int)) == cudaSuccess;
+              cudaMalloc(&ctx->d_cnt, 48 * sizeof(unsigned int)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_numbin, 16 * sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_kq, 16 * (kMaxChunk + 2) * sizeof(int)) == cudaSuccess;
     if (!ok) return bail(fail(nullptr, HP_ERR_CUDA, "device allocation failed"));
     // Poisson table (universal): p[i][k] = 1 - pdtr(k, rv_i)
     for (int i = 1; i <= max_chunks; ++i) ctx->chunks.kcand[i] = 0;
@@ -324,7 +326,7 @@ extern "C" void hp_ctx_destroy(hp_ctx* ctx) {
     if (ctx->stream) stream_sync(ctx);
     comm_release(ctx);
     void* ptrs[] = {ctx->d_ptab, ctx->d_raw, ctx->d_bal, ctx->d_lvl, ctx->d_ir, ctx->d_b1, ctx->d_b2, ctx->d_rownz,
-                    ctx->d_lhist, ctx->d_betab, ctx->d_hist, ctx->d_qtab, ctx->d_small, ctx->d_cnt, ctx->d_numbin,
+                    ctx->d_lhist, ctx->d_betab, ctx->d_hist, ctx->d_qtab, ctx->d_small, ctx->d_cnt, ctx->d_numbin, ctx->d_kq,
                     ctx->d_cand, ctx->d_fcand, ctx->d_xrec, ctx->d_ffac, ctx->d_ffs, ctx->d_xf, ctx->d_b1f, ctx->d_b2s, ctx->d_fscratch, ctx->d_acc, ctx->d_surv, ctx->d_dump, ctx->d_tmp, ctx->d_tab, ctx->d_w, ctx->d_pk, ctx->d_prep, ctx->d_apa_bal, ctx->d_apa_plan, ctx->d_apa_pos,
                     ctx->d_apa_wins, ctx->d_apa_valid, ctx->d_apa_mean, ctx->d_apa_sel, ctx->d_apa_avg};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -843,13 +845,14 @@ static const SpecKernel* find_spec(hp_ctx* ctx, int nexec) {
 // ---- re-associated score kernels (hp_score_fast.cuh): any single (p, w) program, widths up to FM ----------------
 struct FastKernel {
     int fm;
-    int (*launch)(hp_ctx*, const CUtensorMap&, const FastArgs&, int, cudaStream_t);
+    int (*launch)(hp_ctx*, const CUtensorMap&, const FastArgs&, int, cudaStream_t);        // one (pw, ww) pair
+    int (*launch_gen)(hp_ctx*, const CUtensorMap&, const FastArgs&, int, cudaStream_t);    // one pair of a union program
 };
-template <int FM>
+template <int FM, bool GEN>
 static int launch_fast(hp_ctx* ctx, const CUtensorMap& tm_raw, const FastArgs& A, int grid, cudaStream_t st) {
     static std::atomic<size_t> granted[64];
     const size_t smem = FastLayout<FM, FM>::bytes;
-    CK(want_smem(k_score_fast<FM>, ctx->device, smem, granted));
+    CK(want_smem(k_score_fast<FM, GEN>, ctx->device, smem, granted));
     // the fp32 tile: box of fast_px(FM) diagonals x 96 rows of xf[r][d - dlo]; the levels: the same 3-D box of the
     // quad-interleaved u8 plane as the raw counts
     CUtensorMap tm_x, tm_lvl;
@@ -858,10 +861,10 @@ static int launch_fast(hp_ctx* ctx, const CUtensorMap& tm_raw, const FastArgs& A
     if (rc) return rc;
     rc = make_map_plane(ctx, &tm_lvl, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ctx->d_lvl, kFTR / 4, kFTD);
     if (rc) return rc;
-    k_score_fast<FM><<<grid, kFThreads, smem, st>>>(tm_raw, tm_x, tm_lvl, A);
+    k_score_fast<FM, GEN><<<grid, kFThreads, smem, st>>>(tm_raw, tm_x, tm_lvl, A);
     return HP_OK;
 }
-static const FastKernel g_fast[] = {{8, launch_fast<8>}, {10, launch_fast<10>}};
+static const FastKernel g_fast[] = {{8, launch_fast<8, false>, launch_fast<8, true>}, {10, launch_fast<10, false>, launch_fast<10, true>}};
 static const FastKernel* find_fast(int frozen) {
     for (const FastKernel& k : g_fast)
         if (frozen <= k.fm) return &k;
@@ -1071,11 +1074,16 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     }
     size_t want = std::min<size_t>((size_t)total * P.npw, (size_t)((double)total * P.npw * std::max(0.15, 1.5 * P.sig)) + 65536);
     want = std::max<size_t>(want, 65536);
-    // the re-associated kernel: single pair, HiCCUPS mode, no per-pixel dump, widths the compiled kernels cover
+    // the re-associated kernel: HiCCUPS mode, no per-pixel dump, widths the compiled kernels cover; one launch per pair
     static const bool no_fast_env = getenv("HP_NO_FAST") != nullptr;
     const FastKernel* fast = nullptr;
-    if (spec_ok && !no_fast_env && !(P.flags & HP_PF_EXACT_SUMS) && !bhfdr && !P.dump && P.npw == 1 && P.pw[0] < P.ww[0] && ctx->domain_ok && ctx->edges_regular)
-        fast = find_fast(F);
+    bool fast_ok = spec_ok && !no_fast_env && !(P.flags & HP_PF_EXACT_SUMS) && !bhfdr && !P.dump && ctx->domain_ok && ctx->edges_regular;
+    for (int i = 0; i < P.npw; ++i) fast_ok = fast_ok && P.pw[i] < P.ww[i];
+    if (fast_ok) fast = find_fast(F);
+    // per pair: the widths (codes) it resolves at among the executed steps
+    int pair_nc[HP_MAX_PW] = {0};
+    for (int t = 0; t < nexec; ++t) ++pair_nc[G.step_pi[t]];
+    FfsLayout ffsl{};
     size_t want_x = std::max<size_t>(65536, (size_t)total / 8);
     CUtensorMap tm_bal, tm_rawf;
     // the specialised kernel loads its tile as kTileParts boxes of consecutive planes
@@ -1087,12 +1095,15 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
         if (rc) return rc;
         CK(ensure(&ctx->d_ffac, &ctx->cap_ffac, (size_t)(1 + 2 * F) * 2 * nexec * num));
         if (!ctx->d_fscratch) CK(cudaMalloc(&ctx->d_fscratch, (size_t)ctx->sm_count * kFScratch * sizeof(int4)));
-        const size_t nffs = (size_t)((num - 1 - dlo) / kFTD + 1) * 2 * nexec * kFTD;      // k_betab writes every diagonal of the band
+        const size_t per_code = (size_t)((num - 1 - dlo) / kFTD + 1) * 2 * kFTD;          // k_betab writes every diagonal of the band
+        size_t nffs = 0;
+        for (int i = 0; i < P.npw; ++i) { ffsl.off[i] = (int)nffs; ffsl.nc[i] = pair_nc[i]; nffs += per_code * pair_nc[i]; }
         CK(ensure(&ctx->d_ffs, &ctx->cap_ffs, nffs));
         CK(cudaMemsetAsync(ctx->d_ffs, 0, nffs * sizeof(float), st));       // diagonals beyond the band: factor 0
+        ffsl.base = ctx->d_ffs;
     }
     k_betab<<<dim3((num + 127) / 128, nexec, 1 + 2 * F), 128, 0, st>>>(ctx->d_tab, ctx->d_ir, ctx->d_betab, num, ctx->bal_first, nexec, F,
-                                                                     fast ? ctx->d_ffac : nullptr, fast ? ctx->d_ffs : nullptr);
+                                                                     fast ? ctx->d_ffac : nullptr, ffsl);
     ++launches;
     unsigned int cnt[16] = {0};
     unsigned long long small[48];
@@ -1105,7 +1116,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
         }
         CK(cudaMemsetAsync(ctx->d_hist, 0, (size_t)P.npw * 2 * tb * sizeof(unsigned int), st));
         CK(cudaMemsetAsync(ctx->d_small, 0, 48 * sizeof(unsigned long long), st));
-        CK(cudaMemsetAsync(ctx->d_cnt, 0, 16 * sizeof(unsigned int), st));
+        CK(cudaMemsetAsync(ctx->d_cnt, 0, 48 * sizeof(unsigned int), st));     // [16..31]: the fast kernel's running E.max() bounds per pair
         A.tab = ctx->d_tab; A.raw = ctx->d_raw; A.lvl = ctx->d_lvl; A.ir = ctx->d_ir; A.b1 = ctx->d_b1; A.b2 = ctx->d_b2;
         A.betab = ctx->d_betab; A.hist = ctx->d_hist; A.emax_bits = ctx->d_small; A.nvalid = ctx->d_small + 16;
         A.cand = ctx->d_cand; A.cand_count = ctx->d_cnt;
@@ -1123,14 +1134,12 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
             FastArgs FA{};
             FA.ffac = ctx->d_ffac; FA.ffs = ctx->d_ffs; FA.b1f = ctx->d_b1f; FA.b2s = ctx->d_b2s;
             FA.tab = ctx->d_tab; FA.scratch = ctx->d_fscratch;
-            FA.hist = ctx->d_hist; FA.nvalid = ctx->d_small + 16;
             FA.fcand = ctx->d_fcand; FA.xrec = ctx->d_xrec; FA.cnt = ctx->d_cnt;
             FA.fcand_cap = (unsigned)std::min<size_t>(ctx->cap_fcand, 0xffffffffu);
             FA.xrec_cap = (unsigned)std::min<size_t>(ctx->cap_xrec, 0xffffffffu);
             FA.n = n; FA.num = num; FA.pitch = pitch; FA.dlo = dlo; FA.dhi = dhi; FA.F = F; FA.nexec = nexec;
             FA.maxchunk = ctx->chunks.maxchunk; FA.total_bins = ctx->chunks.total_bins;
             FA.nstrips = (dhi - dlo) / kFTD + 1; FA.ntr = (n + kFTR - 1) / kFTR;
-            FA.p = P.pw[0]; FA.w0 = P.ww[0];
             {   // mantissa bits of the in-octave edges, rounded down / up with margin (fast_classify)
                 auto mant = [](double x, bool up) {
                     float f = (float)(x * (up ? 1.0 + 1e-9 : 1.0 - 1e-9));
@@ -1142,15 +1151,52 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
                 FA.c1up = mant(ctx->chunks.rv[2], true); FA.c2up = mant(ctx->chunks.rv[3], true);
             }
             const int items = FA.nstrips * FA.ntr;
-            rc = fast->launch(ctx, tm_rawf, FA, std::min(items, ctx->sm_count), st);
-            if (rc) return rc;
-            ++launches;
-            CK(cudaGetLastError());
+            for (int pi = 0; pi < P.npw; ++pi) {
+                if (pair_nc[pi] == 0) continue;                // no executed step of this pair: nothing resolves for it
+                FA.pair = pi; FA.p = P.pw[pi]; FA.w0 = P.ww[pi]; FA.wpair = P.ww[pi]; FA.ncode = pair_nc[pi];
+                FA.ffs = ctx->d_ffs + ffsl.off[pi];
+                FA.hist = ctx->d_hist + (size_t)pi * 2 * tb; FA.nvalid = ctx->d_small + 16 + 2 * pi; FA.gmax = ctx->d_cnt + 16 + 2 * pi;
+                FA.nlevels = G.nsteps;
+                memset(FA.tcode, 0xF, sizeof(FA.tcode)); memset(FA.tstep, 0, sizeof(FA.tstep));
+                memset(FA.hmask, 0, sizeof(FA.hmask)); memset(FA.cabs, 0, sizeof(FA.cabs)); memset(FA.ctab, 0, sizeof(FA.ctab));
+                if (pair_nc[pi] > kFMaxCode - 1) return fail(ctx, HP_ERR_INVALID, "internal: too many widths for the fast kernel");
+                for (int lv = 0; lv < G.nsteps; ++lv) {
+                    const int t = G.next_step[pi][lv];
+                    if (t != kNoStep) FA.tcode[lv] = (unsigned char)(G.step_w[t] - P.ww[pi]);
+                }
+                for (int t = 0; t < nexec; ++t) {
+                    if (G.step_pi[t] != pi) continue;
+                    const int code = G.step_w[t] - P.ww[pi];
+                    FA.tstep[code] = (unsigned char)t;
+                    // ring multiplicities of the accumulators at step t, from the cell list itself
+                    int cells[kFMaxG + 2] = {0};
+                    for (int k = 0; k < G.op_end[t]; ++k) {
+                        const int g = std::max(abs((int)ctx->opa[k]), abs((int)ctx->opb[k]));
+                        if (g > F) return fail(ctx, HP_ERR_INVALID, "internal: cell beyond the frozen width");
+                        ++cells[g];
+                    }
+                    int mult[kFMaxG + 2] = {0};
+                    for (int g = 1; g <= F; ++g) {
+                        if (cells[g] % (8 * g - 4)) return fail(ctx, HP_ERR_INVALID, "internal: partial ring in the sweep program");
+                        mult[g] = cells[g] / (8 * g - 4);
+                    }
+                    for (int g = 1; g <= F; ++g) {
+                        const int c = mult[g] - mult[g + 1];
+                        FA.ctab[code][g] = (float)c;
+                        if (c) FA.hmask[code] |= (unsigned short)(1u << g);
+                        FA.cabs[g] = std::max(FA.cabs[g], (float)abs(c));
+                    }
+                }
+                rc = (P.npw == 1 ? fast->launch : fast->launch_gen)(ctx, tm_rawf, FA, std::min(items, ctx->sm_count), st);
+                if (rc) return rc;
+                ++launches;
+                CK(cudaGetLastError());
+            }
             CK(cudaEventRecord(ctx->ev[3], st));
             // the records the fast kernel could not settle + the E.max() contenders, in the reference's fp64 order
             static std::atomic<size_t> granted_x[64];
             const size_t smem_x = ((score_smem_bytes(0, 0, sh_pairs, 0, 0, 0, 0) + 127) & ~(size_t)127) +
-                                  (size_t)(kExThreads / 32) * 2 * kExChunk * sizeof(double);
+                                  (size_t)(kExThreads / 32) * ex_warp_bytes(kExRecFew);
             CK(want_smem(k_exact, ctx->device, smem_x, granted_x));
             k_exact<<<2 * ctx->sm_count, kExThreads, smem_x, st>>>(A, ctx->d_bal, ctx->d_xrec, ctx->d_cnt + 10, FA.xrec_cap);
             ++launches;
@@ -1237,7 +1283,8 @@ extern "C" int hp_hiccups_fdr(hp_ctx* ctx, const int32_t* numbin_override, hp_hi
     CK(cudaMemsetAsync(ctx->d_small + 32, 0, 16 * sizeof(unsigned long long), st));
     int launches = 0;
     if (maxnb > 0) {
-        k_bh<<<dim3(maxnb, P.npw * 2), kThreads, 0, st>>>(ctx->d_tab, ctx->d_hist, ctx->d_ptab, ctx->d_qtab, ctx->d_numbin);
+        CK(cudaMemsetAsync(ctx->d_kq, 0x7f, 16 * (kMaxChunk + 2) * sizeof(int), st));
+        k_bh<<<dim3(maxnb, P.npw * 2), kThreads, 0, st>>>(ctx->d_tab, ctx->d_hist, ctx->d_ptab, ctx->d_qtab, ctx->d_numbin, ctx->d_kq, P.sig);
         ++launches;
         CK(cudaGetLastError());
     }
@@ -1262,14 +1309,18 @@ extern "C" int hp_hiccups_fdr(hp_ctx* ctx, const int32_t* numbin_override, hp_hi
         }
         if (ctx->nfcand) {
             // the re-associated kernel's candidates: same selection, then the survivors' E in the reference's fp64 order
-            k_filter_fast<<<(ctx->nfcand + 255) / 256, 256, 0, st>>>(A, ctx->d_fcand, ctx->nfcand);
+            const unsigned fblocks = std::min<unsigned>((ctx->nfcand + kFiltThreads - 1) / kFiltThreads, 8u * (unsigned)ctx->sm_count);
+            k_filter_fast<<<fblocks, kFiltThreads, 0, st>>>(A, ctx->d_fcand, ctx->nfcand, ctx->d_kq, P.npw);
             ++launches;
             CK(cudaGetLastError());
             FillArgs FA{};
             FA.tab = ctx->d_tab; FA.bal = ctx->d_bal; FA.ir = ctx->d_ir; FA.b1 = ctx->d_b1; FA.b2 = ctx->d_b2; FA.betab = ctx->d_betab;
             FA.surv = ctx->d_surv; FA.nsurv_ptr = ctx->d_cnt + 4; FA.cap = A.out_cap;
             FA.n = (int)ctx->n; FA.num = ctx->num; FA.pitch = ctx->pitch; FA.bal_first = ctx->bal_first; FA.F = S.frozen_w; FA.nexec = S.n_steps;
-            k_fill_exact<<<16 * ctx->sm_count, kFillThreads, 0, st>>>(FA);
+            static std::atomic<size_t> granted_f[64];
+            const size_t smem_f = (size_t)(kFillThreads / 32) * ex_warp_bytes(kExRec);
+            CK(want_smem(k_fill_exact, ctx->device, smem_f, granted_f));
+            k_fill_exact<<<3 * ctx->sm_count, kFillThreads, smem_f, st>>>(FA);
             ++launches;
             CK(cudaGetLastError());
         }

@@ -8,52 +8,77 @@
 
 namespace hp {
 
-constexpr int kExThreads = 256;
-constexpr int kExChunk = 256;       // cells gathered per round and warp
+constexpr int kExThreads = 128;
+constexpr int kExRec = 16;          // records a warp evaluates side by side (k_fill_exact: thousands of records)
+constexpr int kExRecFew = 4;        // ... in k_exact (a few hundred records: short critical path, every load of a round in flight)
+constexpr int kExChunk = 128;       // cells gathered per round
+constexpr int kExStride = kExChunk + 1;     // doubles between the cell buffers of two records: 16 records, 16 different bank pairs
+__host__ __device__ constexpr size_t ex_warp_bytes(int nr) {      // cells, Y flags, (r, d, cells) per record
+    return ((size_t)nr * kExStride * 8 + kExChunk + 3 * nr * 4 + 15) & ~(size_t)15;
+}
 
-// One warp, one record: the lanes gather the cells of steps 0..s (independent loads), lane 0 adds the donut sum and lane 1
-// the lower-left sum in list order.  A cell that is not part of the lower-left mask enters that chain as +0.0, which
-// leaves an fp64 sum of non-negative terms unchanged bit for bit.
-__device__ __forceinline__ void exact_sums_warp(const Tables* __restrict__ tab, const double* __restrict__ bal, int n, int num, int pitch,
-                                                int bal_first, int r, int d, int s, double* buf, double* bufy, int lane, double& SK,
-                                                double& SY) {
-    const int nops = tab->prog.op_end[s];
-    double sk = 0.0, sy = 0.0;
-    for (int base = 0; base < nops; base += kExChunk) {
-        const int m = min(kExChunk, nops - base);
-        for (int i0 = lane; i0 < m; i0 += 128) {          // four independent loads in flight per lane
-            double v[4];
-            bool y[4];
+// One warp, NR records (lane j < NR brings record j: row, diagonal, executed step; s < 0: no record).  Round by
+// round the lanes gather kExChunk cells of the sweep's cell list for all the records (lane = cell: the cell's offsets are
+// read once, the 16 loads of a lane are independent), then lane 2j walks the donut chain of record j and lane 2j + 1 its
+// lower-left chain in list order -- 32 chains per fp64 instruction instead of one.  A cell outside a record's step range,
+// the chromosome or the band, or outside the lower-left mask, enters the chain as +0.0, which leaves an fp64 sum of
+// non-negative terms unchanged bit for bit.  Returns the sums of record `lane` (lanes < NR).
+template <int NR>
+__device__ __forceinline__ void exact_sums_batch(const Tables* __restrict__ tab, const double* __restrict__ bal, int n, int num, int pitch,
+                                                 int bal_first, int myr, int myd, int mys, unsigned char* wbuf, int lane, double& SK,
+                                                 double& SY) {
+    const unsigned full = 0xffffffffu;
+    double* const buf = reinterpret_cast<double*>(wbuf);
+    unsigned char* const ys = wbuf + (size_t)NR * kExStride * 8;
+    int* const sr = reinterpret_cast<int*>(ys + kExChunk);
+    int* const sd = sr + NR;
+    int* const sn = sd + NR;
+    const int mynops = (lane < NR && mys >= 0) ? tab->prog.op_end[mys] : 0;
+    if (lane < NR) { sr[lane] = myr; sd[lane] = myd; sn[lane] = mynops; }
+    const int maxn = __reduce_max_sync(full, mynops);
+    __syncwarp();
+    const double* const chain = buf + (size_t)min(lane >> 1, NR - 1) * kExStride;
+    const bool isy = (lane & 1) != 0;
+    double acc = 0.0;
+    for (int base = 0; base < maxn; base += kExChunk) {
+        const int m = min(kExChunk, maxn - base);
+        constexpr int CI = NR <= 4 ? kExChunk / 32 : 1;       // cell rounds whose loads are in flight together
+        for (int i0 = 0; i0 < m; i0 += 32 * CI) {
+            double v[CI][NR];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + 32 * u;
-                v[u] = 0.0; y[u] = false;
-                if (i < m) {
-                    const int k = base + i;
-                    const int a = tab->opa[k], b = tab->opb[k];
+            for (int u = 0; u < CI; ++u) {
+                const int i = i0 + 32 * u + lane, k = base + i;
+                int a = 0, b = 0;
+                if (i < m) { a = tab->opa[k]; b = tab->opb[k]; ys[i] = tab->opy[k]; }
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    const int r = sr[j], d = sd[j];
                     const int rr = r + a, cc = r + d + b, dd = d + b - a;
-                    y[u] = tab->opy[k] != 0;
-                    if (rr >= 0 && rr < n && cc >= 0 && cc < n && dd >= bal_first && dd < num) v[u] = bal[qidx(dd, rr, pitch)];
+                    v[u][j] = 0.0;
+                    if (i < m && k < sn[j] && rr >= 0 && rr < n && cc >= 0 && cc < n && dd >= bal_first && dd < num)
+                        v[u][j] = bal[qidx(dd, rr, pitch)];
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + 32 * u;
-                if (i < m) { buf[i] = v[u]; bufy[i] = y[u] ? v[u] : 0.0; }
+            for (int u = 0; u < CI; ++u) {
+                const int i = i0 + 32 * u + lane;
+                if (i < m) {
+#pragma unroll
+                    for (int j = 0; j < NR; ++j) buf[(size_t)j * kExStride + i] = v[u][j];
+                }
             }
         }
         __syncwarp();
-        if (lane == 0) {
 #pragma unroll 4
-            for (int i = 0; i < m; ++i) sk = __dadd_rn(sk, buf[i]);
-        } else if (lane == 1) {
-#pragma unroll 4
-            for (int i = 0; i < m; ++i) sy = __dadd_rn(sy, bufy[i]);
+        for (int i = 0; i < m; ++i) {
+            double v = chain[i];
+            if (isy && !ys[i]) v = 0.0;
+            acc = __dadd_rn(acc, v);
         }
         __syncwarp();
     }
-    SK = __shfl_sync(0xffffffffu, sk, 0);
-    SY = __shfl_sync(0xffffffffu, sy, 1);
+    SK = __shfl_sync(full, acc, (2 * lane) & 31);
+    SY = __shfl_sync(full, acc, (2 * lane + 1) & 31);
 }
 
 // records of the fast kernel's exact list -> the same per-pixel tail as the score kernels (emit_record)
@@ -61,39 +86,28 @@ __global__ void __launch_bounds__(kExThreads) k_exact(const __grid_constant__ Sc
                                                       const XRec* __restrict__ rec, const unsigned int* __restrict__ nrec_ptr,
                                                       unsigned int cap) {
     extern __shared__ __align__(128) unsigned char smem[];
-    {
-        unsigned nr = *nrec_ptr;
-        if (nr > cap) nr = cap;
-        const unsigned nw = gridDim.x * (kExThreads / 32), pw = (nr + nw - 1) / nw;
-        if ((unsigned long long)blockIdx.x * (kExThreads / 32) * pw >= nr) return;      // no record for this CTA
-    }
+    unsigned nrec = *nrec_ptr;
+    if (nrec > cap) nrec = cap;
+    constexpr int NR = kExRecFew;
+    const unsigned nbatch = (nrec + NR - 1) / NR;
+    if (blockIdx.x >= nbatch) return;                   // batch b goes to warp b / gridDim.x of CTA b % gridDim.x
     const ScoreSmem sh = score_smem(smem, 0, 0, 0, 0, 0, 0);
     const int sh_bins = A.sh_pairs * 2 * kShI * kShK;
-    double* bufs = reinterpret_cast<double*>(smem + ((score_smem_bytes(0, 0, A.sh_pairs, 0, 0, 0, 0) + 127) & ~(size_t)127));
+    unsigned char* bufs = smem + ((score_smem_bytes(0, 0, A.sh_pairs, 0, 0, 0, 0) + 127) & ~(size_t)127);
     if (threadIdx.x == 0) { *sh.cnt = 0; *sh.next = 0; }
     score_prologue<false>(A, sh, nullptr, 0, 0, 0, sh_bins);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* buf = bufs + (size_t)warp * 2 * kExChunk;
-    double* bufy = buf + kExChunk;
-    unsigned nrec = *nrec_ptr;
-    if (nrec > cap) nrec = cap;
-    const unsigned nwarps = gridDim.x * (kExThreads / 32), gw = blockIdx.x * (kExThreads / 32) + warp;
-    const unsigned per = (nrec + nwarps - 1) / nwarps;
-    const unsigned begin = min(nrec, gw * per), endr = min(nrec, begin + per);
+    unsigned char* wbuf = bufs + (size_t)warp * ex_warp_bytes(NR);
     TailAcc tacc{};
-    for (unsigned b0 = begin; b0 < endr; b0 += 32) {
-        const int nb = (int)min(32u, endr - b0);
-        double mySK = 0.0, mySY = 0.0;
-        int myr = 0, myd = 0, mys = 0;
-        unsigned mykind = 0;
-        for (int j = 0; j < nb; ++j) {
-            const XRec x = rec[b0 + j];
-            const int d = x.ds & 0xffff, s = (x.ds >> 16) & 0xff;
-            double sk, sy;
-            exact_sums_warp(A.tab, bal, A.n, A.num, A.pitch, A.bal_first, x.r, d, s, buf, bufy, lane, sk, sy);
-            if (lane == j) { mySK = sk; mySY = sy; myr = x.r; myd = d; mys = s; mykind = (unsigned)x.kind; }
-        }
-        emit_record<0, false>(A, sh, tacc, lane < nb, mySK, mySY, myr, myd, mys, 0, lane, 0, mykind);
+    for (unsigned b = blockIdx.x + (unsigned)warp * gridDim.x; b < nbatch; b += gridDim.x * (kExThreads / 32)) {
+        const unsigned k = b * NR + lane;
+        const bool have = lane < NR && k < nrec;
+        XRec x{0, 0, 0, 0};
+        if (have) x = rec[k];
+        const int d = x.ds & 0xffff, s = (x.ds >> 16) & 0xff;
+        double sk, sy;
+        exact_sums_batch<NR>(A.tab, bal, A.n, A.num, A.pitch, A.bal_first, x.r, d, have ? s : -1, wbuf, lane, sk, sy);
+        emit_record<0, false>(A, sh, tacc, have, sk, sy, x.r, d, s, have ? A.step_pi[s] : 0, lane, 0, (unsigned)x.kind);
     }
     score_epilogue(A, sh, sh_bins);
 }
@@ -116,21 +130,24 @@ constexpr int kSurvNeedsE = 1 << 30;
 
 constexpr int kFillThreads = 128;
 __global__ void __launch_bounds__(kFillThreads) k_fill_exact(const FillArgs A) {
-    __shared__ double bufs[(kFillThreads / 32) * 2 * kExChunk];
+    extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* buf = bufs + (size_t)warp * 2 * kExChunk;
-    double* bufy = buf + kExChunk;
+    unsigned char* wbuf = smem + (size_t)warp * ex_warp_bytes(kExRec);
     unsigned ns = *A.nsurv_ptr;
     if (ns > A.cap) ns = A.cap;
-    const unsigned nwarps = gridDim.x * (kFillThreads / 32);
-    for (unsigned k = blockIdx.x * (kFillThreads / 32) + warp; k < ns; k += nwarps) {
+    const unsigned nbatch = (ns + kExRec - 1) / kExRec;
+    for (unsigned b = blockIdx.x + (unsigned)warp * gridDim.x; b < nbatch; b += gridDim.x * (kFillThreads / 32)) {
+        const unsigned k = b * kExRec + lane;
         hp_survivor* sv = A.surv + k;
-        const int pr = sv->pair;
-        if (!(pr & kSurvNeedsE)) continue;               // warp-uniform: every lane reads the same record
-        const int r = sv->r, d = sv->c - sv->r, s = (pr >> 8) & 0xff;
+        int pr = 0, r = 0, d = 0, s = -1;
+        if (lane < kExRec && k < ns) {
+            pr = sv->pair;
+            if (pr & kSurvNeedsE) { r = sv->r; d = sv->c - sv->r; s = (pr >> 8) & 0xff; }
+        }
+        if (__ballot_sync(0xffffffffu, s >= 0) == 0u) continue;      // no survivor of the fast list in this batch
         double SK, SY;
-        exact_sums_warp(A.tab, A.bal, A.n, A.num, A.pitch, A.bal_first, r, d, s, buf, bufy, lane, SK, SY);
-        if (lane == 0) {
+        exact_sums_batch<kExRec>(A.tab, A.bal, A.n, A.num, A.pitch, A.bal_first, r, d, s, wbuf, lane, SK, SY);
+        if (s >= 0) {
             double be[2];
             record_be(BeArgs{A.tab, A.ir, A.betab, A.n, A.num, A.F, A.nexec, A.bal_first}, r, d, s, be);
             const RecVal V = record_values(SK, SY, be, A.ir[d], A.b1[r], A.b2[r + d], true);
@@ -147,57 +164,68 @@ __global__ void __launch_bounds__(kFillThreads) k_fill_exact(const FillArgs A) {
     }
 }
 
-// survivor selection over the fast kernel's candidate list: q <= sig for K or Y (callers.py:279-287)
-__global__ void k_filter_fast(FilterArgs A, const FCand* __restrict__ fc, unsigned int nfc) {
-    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = idx < nfc;
-    const unsigned lane = threadIdx.x & 31u;
+// survivor selection over the fast kernel's candidate list: q <= sig for K or Y (callers.py:279-287).  q never rises with
+// the observed count inside a lambda-chunk, so the test is "count >= the chunk's threshold" (kq, written by k_bh): the
+// list (16 B per candidate, ~80 candidates per survivor) is streamed against a table in shared memory, and only the
+// survivors touch the p / q tables.
+constexpr int kFiltThreads = 256;
+__global__ void __launch_bounds__(kFiltThreads) k_filter_fast(FilterArgs A, const FCand* __restrict__ fc, unsigned int nfc,
+                                                              const int* __restrict__ kq, int npw) {
+    __shared__ int s_kq[2 * HP_MAX_PW][kMaxChunk + 2], s_hw[kMaxChunk + 2], s_hoff[kMaxChunk + 2];
+    __shared__ unsigned int s_nrej[2 * HP_MAX_PW];
     const Chunks& c_chunks = A.tab->chunks;
-    FCand c{};
-    if (live) *reinterpret_cast<int4*>(&c) = *reinterpret_cast<const int4*>(&fc[idx]);
-    if (c.r < 0) { live = false; c = FCand{}; }           // an unused slot of a warp's piece of the list
-    const int d = c.ds & 0xffff, s = (c.ds >> 16) & 0xff;
-    const unsigned cflags = (c.info >> 16) & 0xffu;
-    const int pair = (int)(c.info >> 24);
-    hp_survivor sv;
-    sv.r = c.r; sv.c = c.r + d; sv.pair = pair | (s << 8) | kSurvNeedsE; sv.flags = cflags;
-    sv.obs = (double)c.obs;
-    sv.e[0] = 0.0; sv.e[1] = 0.0;
-    bool rej[2] = {false, false};
-#pragma unroll
-    for (int fl = 0; fl < 2; ++fl) {
-        const int lf = pair * 2 + fl;
-        const int ci = (int)((c.info >> (8 * fl)) & 0xffu);
-        double p = 1.0, q = 1.0;
-        if (live && ci >= 1 && ci <= A.numbin[lf]) {
-            const int w = c_chunks.hw[ci];
-            const int kb = c.obs < w - 1 ? c.obs : w - 1;
-            p = A.ptab[c_chunks.hoff[ci] + kb];
-            q = A.qtab[(size_t)lf * c_chunks.total_bins + c_chunks.hoff[ci] + kb];
+    for (int i = threadIdx.x; i < 2 * npw * (kMaxChunk + 2); i += kFiltThreads) {
+        const int lf = i / (kMaxChunk + 2), ci = i % (kMaxChunk + 2);
+        s_kq[lf][ci] = (ci >= 1 && ci <= A.numbin[lf]) ? kq[i] : 0x7fffffff;
+        if (lf == 0) { s_hw[ci] = ci <= c_chunks.maxchunk ? c_chunks.hw[ci] : 1; s_hoff[ci] = ci <= c_chunks.maxchunk ? c_chunks.hoff[ci] : 0; }
+    }
+    if (threadIdx.x < 2 * HP_MAX_PW) s_nrej[threadIdx.x] = 0u;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u;
+    for (unsigned base = blockIdx.x * kFiltThreads; base < nfc; base += gridDim.x * kFiltThreads) {      // warp-uniform trip count
+        const unsigned idx = base + threadIdx.x;
+        bool live = idx < nfc;
+        FCand c{};
+        if (live) *reinterpret_cast<int4*>(&c) = __ldcs(reinterpret_cast<const int4*>(&fc[idx]));
+        if (c.r < 0) { live = false; c = FCand{}; }      // an unused slot of a warp's piece of the list
+        const unsigned cflags = (c.info >> 16) & 0xffu;
+        const int pair = (int)(c.info >> 24);
+        const int ck = (int)(c.info & 0xffu), cy = (int)((c.info >> 8) & 0xffu);
+        const int kbk = min(c.obs, s_hw[ck] - 1), kby = min(c.obs, s_hw[cy] - 1);
+        const bool rk = live && (cflags & HP_SF_VALID_K) && kbk >= s_kq[pair * 2][ck];
+        const bool ry = live && (cflags & HP_SF_VALID_Y) && kby >= s_kq[pair * 2 + 1][cy];
+        if (rk) atomicAdd(&s_nrej[pair * 2], 1u);
+        if (ry) atomicAdd(&s_nrej[pair * 2 + 1], 1u);
+        const bool any = rk || ry;
+        const unsigned many = __ballot_sync(0xffffffffu, any);
+        if (many) {
+            unsigned ob = 0;
+            if (lane == (unsigned)__ffs(many) - 1u) ob = atomicAdd(&A.out_count[0], (unsigned)__popc(many));
+            ob = __shfl_sync(0xffffffffu, ob, __ffs(many) - 1);
+            if (any) {
+                const int d = c.ds & 0xffff, s = (c.ds >> 16) & 0xff;
+                hp_survivor sv;
+                sv.r = c.r; sv.c = c.r + d; sv.pair = pair | (s << 8) | kSurvNeedsE;
+                sv.flags = cflags | (rk ? HP_SF_REJECT_K : 0u) | (ry ? HP_SF_REJECT_Y : 0u);
+                sv.obs = (double)c.obs;
+                sv.e[0] = 0.0; sv.e[1] = 0.0;
+                sv.p[0] = 1.0; sv.q[0] = 1.0; sv.p[1] = 1.0; sv.q[1] = 1.0;
+                if (ck >= 1 && ck <= A.numbin[pair * 2]) {
+                    sv.p[0] = A.ptab[s_hoff[ck] + kbk];
+                    sv.q[0] = A.qtab[(size_t)(pair * 2) * c_chunks.total_bins + s_hoff[ck] + kbk];
+                }
+                if (cy >= 1 && cy <= A.numbin[pair * 2 + 1]) {
+                    sv.p[1] = A.ptab[s_hoff[cy] + kby];
+                    sv.q[1] = A.qtab[(size_t)(pair * 2 + 1) * c_chunks.total_bins + s_hoff[cy] + kby];
+                }
+                sv.ice = A.bal[qidx(d, c.r, A.pitch)];
+                const unsigned g = ob + __popc(many & ((1u << lane) - 1u));
+                if (g < A.out_cap) A.out[g] = sv; else atomicAdd(&A.out_count[1], 1u);
+            }
         }
-        sv.p[fl] = p; sv.q[fl] = q;
-        const bool valid = (cflags & (fl ? HP_SF_VALID_Y : HP_SF_VALID_K)) != 0;
-        rej[fl] = live && valid && q <= A.sig;
     }
-    if (rej[0]) sv.flags |= HP_SF_REJECT_K;
-    if (rej[1]) sv.flags |= HP_SF_REJECT_Y;
-#pragma unroll
-    for (int fl = 0; fl < 2; ++fl) {
-        const unsigned peers = __match_any_sync(0xffffffffu, rej[fl] ? pair : -1);
-        if (rej[fl] && lane == (unsigned)__ffs(peers) - 1u) atomicAdd(&A.nreject[pair * 2 + fl], (unsigned long long)__popc(peers));
-    }
-    const bool any = rej[0] || rej[1];
-    const unsigned many = __ballot_sync(0xffffffffu, any);
-    if (many) {
-        unsigned base = 0;
-        if (lane == (unsigned)__ffs(many) - 1u) base = atomicAdd(&A.out_count[0], (unsigned)__popc(many));
-        base = __shfl_sync(0xffffffffu, base, __ffs(many) - 1);
-        if (any) {
-            sv.ice = A.bal[qidx(d, c.r, A.pitch)];
-            const unsigned g = base + __popc(many & ((1u << lane) - 1u));
-            if (g < A.out_cap) A.out[g] = sv; else atomicAdd(&A.out_count[1], 1u);
-        }
-    }
+    __syncthreads();
+    if (threadIdx.x < 2 * npw && s_nrej[threadIdx.x]) atomicAdd(&A.nreject[threadIdx.x], (unsigned long long)s_nrej[threadIdx.x]);
 }
 
 }  // namespace hp

@@ -85,9 +85,15 @@ __global__ void __launch_bounds__(kThreads) k_levels(const __grid_constant__ CUt
 // chromosome (cells with row < 0 or column < 0 drop out); z = 1 + F + e for the columns c = n - 1 - e, e < F,
 // next to its end (cells with row >= n or column >= n drop out).  Pixels near both ends take edge_be().
 // ffac (optional): the same table as fp32 factors IR[d] / bE for the re-associated kernel (hp_score_fast.cuh);
-// ffs: its interior part again as [strip][fl][s][64] blocks (one bulk copy per tile)
+// ffs: its interior part again, per pair, as [strip][fl][code][64] blocks (one bulk copy per tile; code = width of the
+// step - ww of its pair, nc codes per pair)
+struct FfsLayout {
+    float* base;                       // nullptr: none
+    int off[HP_MAX_PW];                // first float of the pair's blocks
+    int nc[HP_MAX_PW];                 // codes of the pair among the executed steps
+};
 __global__ void k_betab(const Tables* __restrict__ tab, const double* __restrict__ ir, double* __restrict__ betab, int num,
-                        int bal_first, int nsteps_exec, int F, float* __restrict__ ffac, float* __restrict__ ffs) {
+                        int bal_first, int nsteps_exec, int F, float* __restrict__ ffac, const FfsLayout ffs) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     const int s = blockIdx.y, z = blockIdx.z;
     if (d >= num || s >= nsteps_exec) return;
@@ -111,11 +117,12 @@ __global__ void k_betab(const Tables* __restrict__ tab, const double* __restrict
         const double ird = ir[d];
         ffac[((size_t)(z * 2 + 0) * nsteps_exec + s) * num + d] = fast_factor(ird, ek);
         ffac[((size_t)(z * 2 + 1) * nsteps_exec + s) * num + d] = fast_factor(ird, ey);
-        if (ffs && z == 0 && d >= bal_first) {          // the interior factors once more, one block of 64 diagonals per strip
-            const int k = d - bal_first;
-            float* o = ffs + ((size_t)(k >> 6) * 2 * nsteps_exec + s) * 64 + (k & 63);
+        if (ffs.base && z == 0 && d >= bal_first) {     // the interior factors once more, one block of 64 diagonals per strip
+            const int k = d - bal_first, pi = tab->prog.step_pi[s], nc = ffs.nc[pi];
+            const int code = tab->prog.step_w[s] - tab->prog.ww[pi];
+            float* o = ffs.base + ffs.off[pi] + ((size_t)(k >> 6) * 2 * nc + code) * 64 + (k & 63);
             o[0] = fast_factor(ird, ek);
-            o[(size_t)nsteps_exec * 64] = fast_factor(ird, ey);
+            o[(size_t)nc * 64] = fast_factor(ird, ey);
         }
     }
 }
@@ -635,7 +642,7 @@ __device__ __forceinline__ double block_scan_min(double v, double* sh, double& t
 
 __global__ void __launch_bounds__(kThreads) k_bh(const Tables* __restrict__ tab, const unsigned int* __restrict__ hist,
                                                   const double* __restrict__ ptab, double* __restrict__ qtab,
-                                                  const int* __restrict__ numbin) {
+                                                  const int* __restrict__ numbin, int* __restrict__ kq, double sig) {
     const Chunks& c_chunks = tab->chunks;
     __shared__ unsigned long long sh_u[kThreads / 32];
     __shared__ double sh_d[kThreads / 32];
@@ -652,6 +659,7 @@ __global__ void __launch_bounds__(kThreads) k_bh(const Tables* __restrict__ tab,
     __syncthreads();
     if (n == 0) {
         for (int k = threadIdx.x; k < w; k += kThreads) q[k] = 1.0;
+        if (kq && threadIdx.x == 0 && 1.0 <= sig) kq[lf * (kMaxChunk + 2) + ci] = 0;
         return;
     }
     const double fn = (double)n;
@@ -674,7 +682,12 @@ __global__ void __launch_bounds__(kThreads) k_bh(const Tables* __restrict__ tab,
         const double rv = (k < w) ? q[k] : INFINITY;
         double tot;
         const double m = fmin(block_scan_min(rv, sh_d, tot), cmin);
-        if (k < w) q[k] = m > 1.0 ? 1.0 : m;
+        if (k < w) {
+            const double qk = m > 1.0 ? 1.0 : m;
+            q[k] = qk;
+            // q never rises with k: the first count with q <= sig is the chunk's survivor threshold (k_filter_fast)
+            if (kq && qk <= sig) atomicMin(&kq[lf * (kMaxChunk + 2) + ci], k);
+        }
         cmin = fmin(cmin, tot);
         __syncthreads();
     }

@@ -56,6 +56,13 @@ constexpr float kFCRel = 16.f * kFU;           // relative error of the fp32 fac
 // two roundings per slide, one per difference); 5 % on top for the second-order terms.
 __host__ __device__ constexpr float fast_cerr_k(int w) { return (10.f * w + 17.f) * 1.05f * kFU; }
 __host__ __device__ constexpr float fast_cerr_y(int w) { return (4.f * w + 16.f) * 1.05f * kFU; }
+// General (multi-pair) form: K = sum_g c(g) Q_g with small integer coefficients (below); every Q'_g carries the bound
+// above, every fused multiply-add of the chain (at most FM of them) rounds once more on a partial sum that is itself
+// bounded by sum_g |c(g)| Fmax_g:  |K' - K| <= sum_g |c(g)| fast_cerr_gen_k(g) Fmax_g, likewise for Y.
+__host__ __device__ constexpr float fast_cerr_gen_k(int w) { return (10.f * w + 40.f) * 1.05f * kFU; }
+__host__ __device__ constexpr float fast_cerr_gen_y(int w) { return (4.f * w + 40.f) * 1.05f * kFU; }
+constexpr int kFMaxCode = 16;       // widths a pair can resolve at (codes 0 .. maxww - ww), 0xF = none
+constexpr int kFMaxG = 16;          // ring index bound of the coefficient tables (> FM)
 
 struct XRec {                       // a record for k_exact: kind 0 = evaluate and account the whole record,
     int r, ds, obs, kind;           // kind bit 0 / 1 = only E.max() of K / Y needs the exact value.  ds = d | step << 16
@@ -77,13 +84,25 @@ struct FastArgs {
     FCand* fcand;
     XRec* xrec;
     int4* scratch;                  // [gridDim.x][kFScratch] (r, d | step << 16, hi of K or 0, hi of Y or 0)
-    unsigned int* cnt;              // d_cnt: [2] chunk overflow, [8] fcand, [9] fcand dropped, [10] xrec, [11] xrec dropped,
-                                    //        [14..15] running max of lo
+    unsigned int* cnt;              // d_cnt: [2] chunk overflow, [8] fcand, [9] fcand dropped, [10] xrec, [11] xrec dropped
     unsigned int fcand_cap, xrec_cap;
     int n, num, pitch, dlo, dhi, F, nexec, maxchunk, total_bins;
     int nstrips, ntr;
     int p, w0;                      // the (pw, ww) pair of the run
     unsigned c1dn, c2dn, c1up, c2up;   // FastEdges (host: fast_edges())
+    unsigned int* gmax;             // [2] running max of lo over the CTAs (K, Y) for this pair
+    // ---- general form (union programs: one launch per pair, GEN kernels) ------------------------------------------------
+    // The reference keeps ONE set of accumulators for all pairs and re-adds rings whenever p drops back (callers.py:150-152),
+    // so at executed step t the donut sum is sum_g m_t(g) Ring_g with multiplicities m_t(g) >= 0, i.e. sum_g c_t(g) Q_g with
+    // c_t(g) = m_t(g) - m_t(g + 1).  A pixel resolves this pair at step t = next_step[pair][level]; code = width(t) - w0.
+    int pair, ncode;                // pair index; codes of this pair among the executed steps
+    int nlevels;                    // level codes below this are real steps (tcode has that many entries)
+    int wpair;                      // ww of this pair: pixels on diagonals below it are not tested for the pair
+    unsigned char tcode[HP_MAX_STEPS + 2];      // level -> code (0xF: the pair never resolves for that level)
+    unsigned char tstep[kFMaxCode];             // code -> executed step index (the record's step)
+    unsigned short hmask[kFMaxCode];            // code -> rings g with c(g) != 0
+    float cabs[kFMaxG];                         // ring -> max over the codes of |c(g)|
+    float ctab[kFMaxCode][kFMaxG];              // [code][g] = c(g)
 };
 
 __host__ __device__ constexpr int fast_px(int FM) {        // tile pitch in floats: >= 64 + 4 FM and == 4 (mod 8), so that
@@ -217,6 +236,46 @@ struct FastPass {
     }
 };
 
+// The general form of FastPass::run: K = sum_g c[code][g] Q_g, Y = sum_g c[code][g] LL_g (coefficients in shared memory,
+// looked up per pixel), window sums only at the rings some code present in the warp needs (hm).
+template <int FM>
+struct FastPassGen {
+    using FP = FastPass<FM>;
+    static constexpr int SPAN = FP::SPAN;
+    template <class Sink>
+    static __host__ __device__ __forceinline__ void run(const float* __restrict__ xrow, int W0, unsigned lvpk, unsigned lvmask, int ft,
+                                                        unsigned hm, const float* __restrict__ ctab, const float* __restrict__ cabs,
+                                                        Sink&& sink) {
+        float dn[SPAN], W[SPAN];
+        float Ka[kFNPX], Ya[kFNPX], ek = 0.f, ey = 0.f;
+        sfor<0, kFNPX>([&](auto I) { Ka[decltype(I)::value] = 0.f; Ya[decltype(I)::value] = 0.f; });
+        sfor<1, FM + 1>([&](auto GG) {
+            constexpr int g = decltype(GG)::value;
+            if (g <= ft) {
+                FP::template vert<g>(xrow, dn, W);
+                if ((hm >> g) & 1u) {
+                    float Q[kFNPX], L[kFNPX], fq, fl;
+                    FP::template horiz<g>(dn, W, Q, L, fq, fl);
+                    ek += cabs[g] * fast_cerr_gen_k(g) * fq;
+                    ey += cabs[g] * fast_cerr_gen_y(g) * fl;
+                    const bool res = g >= W0 && ((lvmask >> (g - W0)) & 1u);
+                    const unsigned epk = fast_pack_err(ek, ey);
+                    sfor<0, kFNPX>([&](auto I) {
+                        constexpr int i = decltype(I)::value;
+                        const unsigned code = (lvpk >> (4 * i)) & 0xFu;
+                        if (code != 0xFu) {
+                            const float c = ctab[code * kFMaxG + g];
+                            Ka[i] = fmaf(c, Q[i], Ka[i]);
+                            Ya[i] = fmaf(c, L[i], Ya[i]);
+                            if (res && code == (unsigned)(g - W0)) sink(I, code, Ka[i], Ya[i], epk);
+                        }
+                    });
+                }
+            }
+        });
+    }
+};
+
 // lambda-chunk edges inside one octave: chunk i has the upper edge 2^((i-1)/3), so for x in [2^e, 2^(e+1)) the chunk is
 // 3e + 2 + (mantissa >= 2^(1/3)) + (mantissa >= 2^(2/3)) -- an exponent and two mantissa compares, no table.  c?dn / c?up:
 // mantissa bits of the two edges rounded down / up (with a 1e-9 margin for the edges the caller's pow() produced;
@@ -275,7 +334,8 @@ struct FastLayout {
     static constexpr size_t oQ = al(oHIST + (size_t)2 * kShI * kShK * 4);        // uint4 [warps][kFQCap] K, Y, err pack, meta
     static constexpr size_t oCINFO = al(oQ + (size_t)kFWarps * kFQCap * 16);     // int4  [kChunkTab]
     static constexpr size_t oMISC = al(oCINFO + (size_t)kChunkTab * 16);         // runmax[2], counters, mbarriers
-    static constexpr size_t bytes = oMISC + 128;
+    static constexpr size_t oGEN = oMISC + 128;                                  // general form: float ctab[16][16], cabs[16]; u8 tcode, tstep
+    static constexpr size_t bytes = oGEN + (size_t)kFMaxCode * kFMaxG * 4 + kFMaxG * 4 + ((HP_MAX_STEPS + 2 + 127) & ~127) + kFMaxCode;
     static constexpr uint32_t tx_fixed = (uint32_t)(kFXR * PX * 4 + kFTD * kFTR * 4 + kFTD * kFTR + kFTR * 4 + (kFTR + kFTD) * 4);
 };
 
@@ -303,13 +363,13 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int FM>
+template <int FM, bool GEN>
 __global__ void __launch_bounds__(kFThreads, 1) k_score_fast(const __grid_constant__ CUtensorMap tm_raw, const __grid_constant__ CUtensorMap tm_x,
                                                              const __grid_constant__ CUtensorMap tm_lvl, const __grid_constant__ FastArgs A) {
     using FP = FastPass<FM>;
     constexpr int PX = FP::PX;
-    constexpr int NEX = FM;                            // executed steps: at most FM - w + 1
-    const int P = A.p, W0 = A.w0;
+    constexpr int NEX = FM;                            // widths a pair resolves at: at most FM - w + 1
+    const int P = A.p, W0 = A.w0, ncode = A.ncode;
     using LY = FastLayout<FM, NEX>;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned int* const shist = reinterpret_cast<unsigned int*>(smem + LY::oHIST);
@@ -319,6 +379,10 @@ __global__ void __launch_bounds__(kFThreads, 1) k_score_fast(const __grid_consta
     unsigned int* const claim = reinterpret_cast<unsigned int*>(smem + LY::oMISC + 12);
     unsigned int* const done = reinterpret_cast<unsigned int*>(smem + LY::oMISC + 16);       // [kFStages]
     uint64_t* const full_bar = reinterpret_cast<uint64_t*>(smem + LY::oMISC + 32);           // [kFStages]
+    float* const s_ctab = reinterpret_cast<float*>(smem + LY::oGEN);
+    float* const s_cabs = s_ctab + kFMaxCode * kFMaxG;
+    unsigned char* const s_tcode = reinterpret_cast<unsigned char*>(s_cabs + kFMaxG);
+    unsigned char* const s_tstep = s_tcode + ((HP_MAX_STEPS + 2 + 127) & ~127);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
     const int nexec = A.nexec, n = A.n, num = A.num, mc = A.maxchunk;
@@ -341,12 +405,12 @@ __global__ void __launch_bounds__(kFThreads, 1) k_score_fast(const __grid_consta
         tile_of(j, strip, r0);
         unsigned char* const sb = smem + (size_t)(j & 1) * LY::stage;
         uint64_t* const bar = full_bar + (j & 1);
-        const uint32_t ftb = (uint32_t)(2 * nexec * kFTD * 4);
+        const uint32_t ftb = (uint32_t)(2 * ncode * kFTD * 4);
         mbar_expect_tx(bar, LY::tx_fixed + ftb);
         tma_load_2d(sb + LY::sXS, &tm_x, strip * kFTD - 2 * FM, r0 - kFRowHalo, bar);
         tma_load_3d(sb + LY::sOBS, &tm_raw, r0 / 4, 0, A.dlo + strip * kFTD, bar);
         tma_load_3d(sb + LY::sLVL, &tm_lvl, r0 / 4, 0, A.dlo + strip * kFTD, bar);
-        bulk_load(sb + LY::sFTAB, A.ffs + (size_t)strip * 2 * nexec * kFTD, ftb, bar);
+        bulk_load(sb + LY::sFTAB, A.ffs + (size_t)strip * 2 * ncode * kFTD, ftb, bar);
         bulk_load(sb + LY::sB1, A.b1f + r0, kFTR * 4, bar);
         bulk_load(sb + LY::sB2, A.b2s + r0 + strip * kFTD, (kFTR + kFTD) * 4, bar);
     };
@@ -357,6 +421,12 @@ __global__ void __launch_bounds__(kFThreads, 1) k_score_fast(const __grid_consta
             cinfo[i] = in ? make_int4(C.hoff[i], C.hw[i], C.kcand[i], 0) : make_int4(0, 1, 0x7fffffff, 0);
         }
         for (int i = tid; i < 2 * kShI * kShK; i += kFThreads) shist[i] = 0u;
+        if constexpr (GEN) {
+            for (int i = tid; i < kFMaxCode * kFMaxG; i += kFThreads) s_ctab[i] = A.ctab[i / kFMaxG][i % kFMaxG];
+            for (int i = tid; i < kFMaxG; i += kFThreads) s_cabs[i] = A.cabs[i];
+            for (int i = tid; i < HP_MAX_STEPS + 2; i += kFThreads) s_tcode[i] = A.tcode[i];
+        }
+        for (int i = tid; i < kFMaxCode; i += kFThreads) s_tstep[i] = A.tstep[i];
         if (tid == 0) {
             runmax[0] = 0u; runmax[1] = 0u; *nscr = 0u; *claim = 0u;
             for (int s = 0; s < kFStages; ++s) { done[s] = 0u; mbar_init(full_bar + s, 1); }
@@ -400,8 +470,9 @@ __global__ void __launch_bounds__(kFThreads, 1) k_score_fast(const __grid_consta
             for (int i = 0; i < kFNPX; ++i) {
                 // stale bytes beyond the chromosome or the band never reach here as levels: (r, d) is checked
                 const int d = d0 + kFNPX * cb + i;
-                const unsigned lv = lp[i * kFTR];
-                const unsigned code = (lv < (unsigned)nexec && d <= A.dhi && r < n && r + d < n) ? lv : 0xFu;
+                unsigned lv = lp[i * kFTR];
+                if constexpr (GEN) lv = (lv < (unsigned)A.nlevels && d >= A.wpair) ? (unsigned)s_tcode[lv] : 0xFu;
+                const unsigned code = (lv < (unsigned)ncode && d <= A.dhi && r < n && r + d < n) ? lv : 0xFu;
                 lvpk |= code << (4 * i);
                 const bool e = code != 0xFu;
                 if (e) mine |= 1u << code;
@@ -417,11 +488,18 @@ __global__ void __launch_bounds__(kFThreads, 1) k_score_fast(const __grid_consta
             // element (r + a, c0 - FM + t) sits at tile column (d0 + 8 cb - FM + t - a) - (d0 - 2 FM) = 8 cb + FM + t - a
             const float* xrow = xs + (size_t)(rl + kFRowHalo) * PX + kFNPX * cb;
             const unsigned mbase = (unsigned)rl | ((unsigned)(kFNPX * cb) << 6);
-            FP::run(xrow, P, W0, lvpk, lvmask, ft, [&](auto I, unsigned sc, float kv, float yv, unsigned epk) {
+            auto push = [&](auto I, unsigned sc, float kv, float yv, unsigned epk) {
                 constexpr int i = decltype(I)::value;
                 const unsigned slot = ((i < 4 ? slotpk0 : slotpk1) >> (8 * (i & 3))) & 0xffu;
                 q[slot] = make_uint4(__float_as_uint(kv), __float_as_uint(yv), epk, mbase + ((unsigned)i << 6) + (sc << 12));
-            });
+            };
+            if constexpr (GEN) {
+                unsigned hm = 0;                        // rings at which some code present in the warp has a coefficient
+                for (unsigned mm = lvmask; mm; mm &= mm - 1u) hm |= A.hmask[__ffs((int)mm) - 1];
+                FastPassGen<FM>::run(xrow, W0, lvpk, lvmask, ft, hm, s_ctab, s_cabs, push);
+            } else {
+                FP::run(xrow, P, W0, lvpk, lvmask, ft, push);
+            }
             __syncwarp();
             // ---- close the records: classify both backgrounds, account the certain ones ---------------------------
 #pragma unroll 1
@@ -429,10 +507,11 @@ __global__ void __launch_bounds__(kFThreads, 1) k_score_fast(const __grid_consta
                 const bool act = b0 + lane < cnt;
                 const uint4 rec = act ? q[b0 + lane] : make_uint4(0u, 0u, 0u, 0u);
                 const unsigned m = rec.w;
-                const int rrl = m & 63, dl = (m >> 6) & 63, s = (m >> 12) & 15;
+                const int rrl = m & 63, dl = (m >> 6) & 63, sc = (m >> 12) & 15;
+                const int s = s_tstep[sc];              // the executed step the record resolves at
                 const int r = r0 + rrl, d = d0 + dl;
                 const int ob = obs[(dl * 4 + (rrl & 3)) * (kFTR / 4) + (rrl >> 2)];
-                float fk = ftab[s * kFTD + dl], fy = ftab[(nexec + s) * kFTD + dl];
+                float fk = ftab[sc * kFTD + dl], fy = ftab[(ncode + sc) * kFTD + dl];
                 const bool top = r < A.F, end = r + d >= n - A.F;
                 if (act && (top || end)) {              // next to a chromosome end: the factor tables of that row / column
                     const int z = top ? 1 + r : 1 + A.F + (n - 1 - r - d);
@@ -502,7 +581,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_score_fast(const __grid_consta
                         const unsigned slot = cbase + cused + __popc(mcand & lt);
                         if (slot < A.fcand_cap)
                             *reinterpret_cast<int4*>(&A.fcand[slot]) =
-                                make_int4(r, d | (s << 16), ob, (int)((unsigned)ck | ((unsigned)cy << 8) | (flags << 16)));
+                                make_int4(r, d | (s << 16), ob, (int)((unsigned)ck | ((unsigned)cy << 8) | (flags << 16) | ((unsigned)A.pair << 24)));
                         else gmem_red_add(&A.cnt[9], 1u);
                     }
                     cused += nc;
@@ -552,21 +631,21 @@ __global__ void __launch_bounds__(kFThreads, 1) k_score_fast(const __grid_consta
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     issue(j + kFStages);
                 }
-                const unsigned g0 = A.cnt[14], g1 = A.cnt[15];          // (any value read is a valid bound)
+                const unsigned g0 = A.gmax[0], g1 = A.gmax[1];          // (any value read is a valid bound)
                 const unsigned l0 = smem_ld_volatile(&runmax[0]), l1 = smem_ld_volatile(&runmax[1]);
-                if (g0 > l0) smem_red_max32(&runmax[0], g0); else if (l0 > g0) gmem_red_max(&A.cnt[14], l0);
-                if (g1 > l1) smem_red_max32(&runmax[1], g1); else if (l1 > g1) gmem_red_max(&A.cnt[15], l1);
+                if (g0 > l0) smem_red_max32(&runmax[0], g0); else if (l0 > g0) gmem_red_max(&A.gmax[0], l0);
+                if (g1 > l1) smem_red_max32(&runmax[1], g1); else if (l1 > g1) gmem_red_max(&A.gmax[1], l1);
             }
         }
     }
     // ---- E.max() contenders that still reach the largest lower bound known now -> exact list ---------------------------
     __syncthreads();
     if (tid == 0) {
-        if (runmax[0]) atomicMax(&A.cnt[14], runmax[0]);
-        if (runmax[1]) atomicMax(&A.cnt[15], runmax[1]);
+        if (runmax[0]) atomicMax(&A.gmax[0], runmax[0]);
+        if (runmax[1]) atomicMax(&A.gmax[1], runmax[1]);
     }
     {
-        const unsigned m0 = max(runmax[0], A.cnt[14]), m1 = max(runmax[1], A.cnt[15]);
+        const unsigned m0 = max(runmax[0], A.gmax[0]), m1 = max(runmax[1], A.gmax[1]);
         const unsigned ns = min(*nscr, kFScratch);
         for (unsigned i = tid; i < ns; i += kFThreads) {
             const int4 c = A.scratch[(size_t)blockIdx.x * kFScratch + i];

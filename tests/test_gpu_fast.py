@@ -29,13 +29,15 @@ def _upload(ctx, inp, counts=False):
 
 
 def _run(ctx, inp, p, w, maxww, sig, band, thr, exact, counts=False):
+    """p, w: one pair or the lists of a union program."""
     _upload(ctx, inp, counts)
-    P = ctx.make_params([p], [w], maxww, sig, band, thr, exact_sums=exact)
+    pw, ww = (list(p), list(w)) if isinstance(p, (list, tuple)) else ([p], [w])
+    P = ctx.make_params(pw, ww, maxww, sig, band, thr, exact_sums=exact)
     S1 = ctx.score(P)
     S = ctx.fdr()
     sv = ctx.survivors()
-    sv = sv[np.lexsort((sv["c"], sv["r"]))]
-    tabs = [ctx.chunk_table(0, fl) for fl in (0, 1)]
+    sv = sv[np.lexsort((sv["pair"], sv["c"], sv["r"]))]
+    tabs = [ctx.chunk_table(pi, fl) for pi in range(len(pw)) for fl in (0, 1)]
     return S1, S, sv, tabs
 
 
@@ -43,9 +45,10 @@ def _assert_same(a, b):
     S1a, Sa, sva, ta = a
     S1b, Sb, svb, tb = b
     assert (Sa.n_pixels, Sa.frozen_w, Sa.n_steps) == (Sb.n_pixels, Sb.frozen_w, Sb.n_steps)
-    for fl in (0, 1):
-        La, Lb = Sa.lf[0][fl], Sb.lf[0][fl]
-        assert (La.n_valid, La.e_max, La.numbin, La.n_reject) == (Lb.n_valid, Lb.e_max, Lb.numbin, Lb.n_reject), fl
+    assert len(ta) == len(tb)
+    for lf in range(len(ta)):
+        La, Lb = Sa.lf[lf // 2][lf % 2], Sb.lf[lf // 2][lf % 2]
+        assert (La.n_valid, La.e_max, La.numbin, La.n_reject) == (Lb.n_valid, Lb.e_max, Lb.numbin, Lb.n_reject), lf
     for x, y in zip(ta, tb):
         assert x[0] == y[0]
         assert np.array_equal(x[3], y[3]), "histograms differ"
@@ -82,6 +85,38 @@ def test_fast_equals_exact_order(ctx, case):
     _assert_same(fast, exact)
     # worker-level input (band built on the GPU) through the fast path too
     _assert_same(_run(ctx, inp, p, w, maxww, 0.1, band, thr, exact=False, counts=True), exact)
+
+
+UNION_CASES = [
+    # n, band, pw, ww, maxww, scale, decay, thr, seed
+    (900, 120, (1, 2, 4), (3, 5, 7), 10, 300.0, 1.08, 16, 31),     # the BASELINE cfg3 program (compiled exact-order kernel)
+    (700, 100, (1, 2, 4), (3, 5, 7), 10, 15.0, 1.0, 16, 32),       # sparse: deep levels, re-added rings at every width
+    (640, 90, (1, 2), (3, 5), 10, 40.0, 1.05, 16, 33),             # two pairs: table-driven k_score on the exact side
+    (500, 80, (2, 4), (5, 7), 9, 60.0, 1.1, 20, 34),
+    (129, 40, (1, 3), (4, 6), 8, 80.0, 1.1, 16, 35),               # ragged, FM = 8 kernel
+    (90, 70, (1, 2, 4), (3, 5, 7), 10, 300.0, 1.08, 16, 36),       # pixels next to both chromosome ends
+    (2300, 260, (4, 2, 1), (7, 5, 3), 10, 200.0, 1.08, 16, 37),    # pairs given in another order, several tiles per strip
+]
+
+
+@pytest.mark.parametrize("case", UNION_CASES, ids=lambda c: "n%d_b%d_p%s_w%s" % (c[0], c[1], "".join(map(str, c[2])), "".join(map(str, c[3]))))
+def test_union_fast_equals_exact_order(ctx, case):
+    """Union programs: one launch of the general-form fast kernel per pair (ring multiplicities as coefficients of the
+    quadrant boxes) against the exact-order kernels -- every pair's counts, E.max(), histograms, q tables and survivors."""
+    n, band, pw, ww, maxww, scale, decay, thr, seed = case
+    inp = synth_chromosome(n, band, min(ww), maxww=maxww, seed=seed, scale=scale, decay=decay)
+    try:
+        exact = _run(ctx, inp, pw, ww, maxww, 0.1, band, thr, exact=True)
+    except _capi.EngineError as e:                       # the reference's crash (empty unresolved set): same on both routes
+        assert e.code == _capi.HP_ERR_EMPTY_REFIDX
+        with pytest.raises(_capi.EngineError):
+            _run(ctx, inp, pw, ww, maxww, 0.1, band, thr, exact=False)
+        return
+    fast = _run(ctx, inp, pw, ww, maxww, 0.1, band, thr, exact=False)
+    assert exact[0].fast_kernel == 0
+    assert fast[0].fast_kernel == 1, "the re-associated kernel did not run"
+    _assert_same(fast, exact)
+    _assert_same(_run(ctx, inp, pw, ww, maxww, 0.1, band, thr, exact=False, counts=True), exact)
 
 
 @pytest.mark.parametrize("case", CASES[:5], ids=lambda c: "n%d_b%d_p%dw%d" % (c[0], c[1], c[2], c[3]))
