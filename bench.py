@@ -291,7 +291,9 @@ def bench_cfg3(local, rank, world, dist, steps):
             out[scope]["allreduce_ms_device"] = float(np.mean([m for m in merges if m is not None]))
     ms_score = out["chrom"]["ms_score_sum_rank0"]
     peak, _ = read_peaks()
-    out["roofline"] = {"kernel": "k_score_spec<(1,3),(2,5),(4,7)> (exact fp64 order; three pairs per pixel)",
+    fastk = bool(Ss and Ss[0].fast_kernel)
+    out["roofline"] = {"kernel": ("k_score_fast, general form: one launch per pair, three pairs per pixel" if fastk else
+                                  "k_score_spec<(1,3),(2,5),(4,7)> (exact fp64 order; three pairs per pixel)"),
                        "achieved": ALG_BYTES_PER_PIXEL * px_mine / (ms_score * 1e-3) / 1e9 if ms_score else None,
                        "peak": peak, "unit": "GB/s", "pixels": px_mine}
     if out["roofline"]["achieved"]:

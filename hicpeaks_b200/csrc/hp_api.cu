@@ -1102,7 +1102,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
         CK(cudaMemsetAsync(ctx->d_ffs, 0, nffs * sizeof(float), st));       // diagonals beyond the band: factor 0
         ffsl.base = ctx->d_ffs;
     }
-    k_betab<<<dim3((num + 127) / 128, nexec, 1 + 2 * F), 128, 0, st>>>(ctx->d_tab, ctx->d_ir, ctx->d_betab, num, ctx->bal_first, nexec, F,
+    k_betab<<<dim3((num + kBetabThreads - 1) / kBetabThreads, 1 + 2 * F), kBetabThreads, 0, st>>>(ctx->d_tab, ctx->d_ir, ctx->d_betab, num, ctx->bal_first, nexec, F,
                                                                      fast ? ctx->d_ffac : nullptr, ffsl);
     ++launches;
     unsigned int cnt[16] = {0};
@@ -1149,6 +1149,11 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
                 };
                 FA.c1dn = mant(ctx->chunks.rv[2], false); FA.c2dn = mant(ctx->chunks.rv[3], false);
                 FA.c1up = mant(ctx->chunks.rv[2], true); FA.c2up = mant(ctx->chunks.rv[3], true);
+                // lower edge of every chunk (rv[i - 1]), rounded up with the same margin; chunk maxchunk + 1 = beyond the last edge
+                for (int i = 0; i < kMaxChunk + 4; ++i) FA.elo[i] = INFINITY;
+                FA.elo[0] = 0.f; FA.elo[1] = 0.f;
+                for (int i = 2; i <= ctx->chunks.maxchunk + 1; ++i)
+                    FA.elo[i] = nextafterf((float)(ctx->chunks.rv[i - 1] * (1.0 + 1e-9)), INFINITY);
             }
             const int items = FA.nstrips * FA.ntr;
             for (int pi = 0; pi < P.npw; ++pi) {

@@ -92,37 +92,64 @@ struct FfsLayout {
     int off[HP_MAX_PW];                // first float of the pair's blocks
     int nc[HP_MAX_PW];                 // codes of the pair among the executed steps
 };
-__global__ void k_betab(const Tables* __restrict__ tab, const double* __restrict__ ir, double* __restrict__ betab, int num,
-                        int bal_first, int nsteps_exec, int F, float* __restrict__ ffac, const FfsLayout ffs) {
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
-    const int s = blockIdx.y, z = blockIdx.z;
-    if (d >= num || s >= nsteps_exec) return;
+constexpr int kBetabThreads = 64;
+__global__ void __launch_bounds__(kBetabThreads) k_betab(const Tables* __restrict__ tab, const double* __restrict__ ir, double* __restrict__ betab,
+                                                         int num, int bal_first, int nsteps_exec, int F, float* __restrict__ ffac,
+                                                         const FfsLayout ffs) {
+    // One thread per (diagonal, edge variant) walks the cell list ONCE and leaves its running sums at every step boundary
+    // (the accumulators are never reset between steps, callers.py:132-198).  The cells are staged in shared memory,
+    // decoded; the two fp64 chains stay sequential, everything around them is independent and four cells wide.
+    __shared__ int pk[kMaxOps];                         // (b - a) + 64 | a + 64 << 8 | b + 64 << 16 | y << 24
+    const int nops = tab->prog.op_end[nsteps_exec - 1];
+    for (int i = threadIdx.x; i < nops; i += kBetabThreads) {
+        const int a = tab->opa[i], b = tab->opb[i];
+        pk[i] = (b - a + 64) | ((a + 64) << 8) | ((b + 64) << 16) | ((tab->opy[i] ? 1 : 0) << 24);
+    }
+    __syncthreads();
+    const int d = blockIdx.x * kBetabThreads + threadIdx.x;
+    const int z = blockIdx.y;
+    if (d >= num) return;
     int amin = -128, bmin = -128, amax = 127, bmax = 127;
     if (z >= 1 && z <= F) { const int r = z - 1; amin = -r; bmin = -(r + d); }
     if (z > F) { const int e = z - F - 1; amax = e + d; bmax = e; }
+    const double ird = ir[d];
     double ek = 0.0, ey = 0.0;
-    const int e = tab->prog.op_end[s];
-    for (int i = 0; i < e; ++i) {
-        const int a = tab->opa[i], b = tab->opb[i];
-        const int dd = d + b - a;
-        if (dd >= bal_first && dd < num && a >= amin && a <= amax && b >= bmin && b <= bmax) {
-            const double v = ir[dd];
-            ek = __dadd_rn(ek, v);
-            if (tab->opy[i]) ey = __dadd_rn(ey, v);
+    int i = 0;
+    for (int s = 0; s < nsteps_exec; ++s) {
+        const int e = tab->prog.op_end[s];
+        for (; i < e; i += 4) {
+            double v[4];
+            bool on[4], y[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int w = (i + u < e) ? pk[i + u] : 0;
+                const int dd = d + (w & 0xff) - 64, a = ((w >> 8) & 0xff) - 64, b = ((w >> 16) & 0xff) - 64;
+                on[u] = (i + u < e) && dd >= bal_first && dd < num && a >= amin && a <= amax && b >= bmin && b <= bmax;
+                y[u] = (w >> 24) != 0;
+                v[u] = on[u] ? ir[dd] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (on[u]) {
+                    ek = __dadd_rn(ek, v[u]);
+                    if (y[u]) ey = __dadd_rn(ey, v[u]);
+                }
+            }
         }
-    }
-    betab[((size_t)(z * 2 + 0) * nsteps_exec + s) * num + d] = ek;
-    betab[((size_t)(z * 2 + 1) * nsteps_exec + s) * num + d] = ey;
-    if (ffac) {
-        const double ird = ir[d];
-        ffac[((size_t)(z * 2 + 0) * nsteps_exec + s) * num + d] = fast_factor(ird, ek);
-        ffac[((size_t)(z * 2 + 1) * nsteps_exec + s) * num + d] = fast_factor(ird, ey);
-        if (ffs.base && z == 0 && d >= bal_first) {     // the interior factors once more, one block of 64 diagonals per strip
-            const int k = d - bal_first, pi = tab->prog.step_pi[s], nc = ffs.nc[pi];
-            const int code = tab->prog.step_w[s] - tab->prog.ww[pi];
-            float* o = ffs.base + ffs.off[pi] + ((size_t)(k >> 6) * 2 * nc + code) * 64 + (k & 63);
-            o[0] = fast_factor(ird, ek);
-            o[(size_t)nc * 64] = fast_factor(ird, ey);
+        i = e;
+        betab[((size_t)(z * 2 + 0) * nsteps_exec + s) * num + d] = ek;
+        betab[((size_t)(z * 2 + 1) * nsteps_exec + s) * num + d] = ey;
+        if (ffac) {
+            const float fk = fast_factor(ird, ek), fy = fast_factor(ird, ey);
+            ffac[((size_t)(z * 2 + 0) * nsteps_exec + s) * num + d] = fk;
+            ffac[((size_t)(z * 2 + 1) * nsteps_exec + s) * num + d] = fy;
+            if (ffs.base && z == 0 && d >= bal_first) {     // the interior factors once more, one block of 64 diagonals per strip
+                const int k = d - bal_first, pi = tab->prog.step_pi[s], nc = ffs.nc[pi];
+                const int code = tab->prog.step_w[s] - tab->prog.ww[pi];
+                float* o = ffs.base + ffs.off[pi] + ((size_t)(k >> 6) * 2 * nc + code) * 64 + (k & 63);
+                o[0] = fk;
+                o[(size_t)nc * 64] = fy;
+            }
         }
     }
 }

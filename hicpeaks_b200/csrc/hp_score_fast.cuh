@@ -90,6 +90,7 @@ struct FastArgs {
     int nstrips, ntr;
     int p, w0;                      // the (pw, ww) pair of the run
     unsigned c1dn, c2dn, c1up, c2up;   // FastEdges (host: fast_edges())
+    float elo[kMaxChunk + 4];       // [i] = lower edge of lambda-chunk i rounded up (with margin); [1] = 0
     unsigned int* gmax;             // [2] running max of lo over the CTAs (K, Y) for this pair
     // ---- general form (union programs: one launch per pair, GEN kernels) ------------------------------------------------
     // The reference keeps ONE set of accumulators for all pairs and re-adds rings whenever p drops back (callers.py:150-152),
@@ -134,12 +135,13 @@ __host__ __device__ __forceinline__ unsigned fast_pack_err(float ek, float ey) {
 template <int FM>
 struct FastPass {
     static constexpr int SPAN = 2 * FM + kFNPX;
+    static constexpr int SPAN_DN = FM + kFNPX - 1;     // the lower-left boxes only reach the columns left of the last pixel
     static constexpr int PX = fast_px(FM);
 
     // xrow = &tile[row of r][8 * column block]: element (r + a, c0 - FM + t) is xrow[a * PX + FM - a + t] (the tile is
     // indexed by diagonal along a row: one matrix row down is one diagonal back)
     template <int G>
-    static __host__ __device__ __forceinline__ void vert(const float* __restrict__ xrow, float (&dn)[SPAN], float (&W)[SPAN]) {
+    static __host__ __device__ __forceinline__ void vert(const float* __restrict__ xrow, float (&dn)[SPAN_DN], float (&W)[SPAN]) {
         {
             constexpr int c0 = FM - G, sh = c0 & 3, nv = (sh + SPAN + 3) / 4;
             float f[4 * nv];
@@ -155,8 +157,13 @@ struct FastPass {
 #endif
             sfor<0, SPAN>([&](auto T) {
                 constexpr int t = decltype(T)::value;
-                if constexpr (G == 1) { dn[t] = f[sh + t]; W[t] = f[sh + t]; }
-                else { dn[t] += f[sh + t]; W[t] += f[sh + t]; }
+                if constexpr (G == 1) {
+                    W[t] = f[sh + t];
+                    if constexpr (t < SPAN_DN) dn[t] = f[sh + t];
+                } else {
+                    W[t] += f[sh + t];
+                    if constexpr (t < SPAN_DN) dn[t] += f[sh + t];
+                }
             });
         }
         {
@@ -182,7 +189,7 @@ struct FastPass {
     // quadrant boxes of half-width w for the 8 pixels: Q[i] = Q_w(r, c0 + i), L[i] = LL_w(r, c0 + i); fq / fl = the largest
     // full window sum / lower-left sum among them (bounds every intermediate of the slides)
     template <int w>
-    static __host__ __device__ __forceinline__ void horiz(const float (&dn)[SPAN], const float (&W)[SPAN], float (&Q)[kFNPX],
+    static __host__ __device__ __forceinline__ void horiz(const float (&dn)[SPAN_DN], const float (&W)[SPAN], float (&Q)[kFNPX],
                                                           float (&L)[kFNPX], float& fq, float& fl) {
         float full = W[FM - w];
         sfor<FM - w + 1, FM + w + 1>([&](auto T) { full += W[decltype(T)::value]; });
@@ -211,7 +218,7 @@ struct FastPass {
     template <class Sink>
     static __host__ __device__ __forceinline__ void run(const float* __restrict__ xrow, int P, int W0, unsigned lvpk, unsigned lvmask,
                                                         int ft, Sink&& sink) {
-        float dn[SPAN], W[SPAN];
+        float dn[SPAN_DN], W[SPAN];
         float Qp[kFNPX], Lp[kFNPX], fqp = 0.f, flp = 0.f;
         sfor<0, kFNPX>([&](auto I) { Qp[decltype(I)::value] = 0.f; Lp[decltype(I)::value] = 0.f; });
         sfor<1, FM + 1>([&](auto GG) {
@@ -246,7 +253,7 @@ struct FastPassGen {
     static __host__ __device__ __forceinline__ void run(const float* __restrict__ xrow, int W0, unsigned lvpk, unsigned lvmask, int ft,
                                                         unsigned hm, const float* __restrict__ ctab, const float* __restrict__ cabs,
                                                         Sink&& sink) {
-        float dn[SPAN], W[SPAN];
+        float dn[FP::SPAN_DN], W[SPAN];
         float Ka[kFNPX], Ya[kFNPX], ek = 0.f, ey = 0.f;
         sfor<0, kFNPX>([&](auto I) { Ka[decltype(I)::value] = 0.f; Ya[decltype(I)::value] = 0.f; });
         sfor<1, FM + 1>([&](auto GG) {
@@ -298,22 +305,29 @@ __host__ __device__ __forceinline__ int fast_chunk_index(unsigned bits, unsigned
 // Classification of one background of one pixel from its fp32 sum S (|S - exact| <= es), the fp32 factor f = IR / bE
 // and bb = B1 * B2.  0: certainly not a valid pixel (E == 0), 1: certainly valid and strictly inside lambda-chunk
 // `chunk` (chunk == maxchunk + 1: beyond the last edge), 2: cannot tell -- evaluate exactly.
-// Certain means: the chunk of the float just below lo (edges rounded up) equals the chunk of hi (edges rounded down);
-// then edge(chunk - 1) < lo <= E <= hi < edge(chunk) for every E the bound allows.
-__host__ __device__ __forceinline__ int fast_classify(float S, float es, float f, float bb, const FastEdges& ed, int mc, int& chunk,
-                                                      float& lo, float& hi) {
+// Certain means: with i = the chunk of hi (edges rounded DOWN, so hi < edge(i) for sure), lo lies above the lower edge
+// of chunk i rounded UP (cinfo[i].w, float bits; 0 for chunk 1): edge(i - 1) < lo <= E <= hi < edge(i) for every E the
+// bound allows.  inf = cinfo[chunk] = {first histogram bin, bins, candidate threshold, lower edge}.
+__host__ __device__ __forceinline__ int fast_classify(float S, float es, float f, float bb, const FastEdges& ed, int mc,
+                                                      const int4* __restrict__ cinfo, int& chunk, float& lo, float& hi, int4& inf) {
     chunk = 0; lo = 0.f; hi = 0.f;
+    inf = make_int4(0, 1, 0x7fffffff, 0);
     if (f == 0.f || bb == 0.f || es == 0.f) return 0;    // bE == 0 / IR == 0 / a zero bias, or every cell in reach is zero
     const float fm = f * bb;
     const float ea = S * fm;
     const float err = es * fabsf(fm) + fabsf(ea) * kFCRel;
     lo = ea - err;
     hi = ea + err;
-    if (!(lo > 0.f) || !(hi < 1e37f)) return 2;
-    const int il = fast_chunk_index(fast_bits(lo) - 1u, ed.c1up, ed.c2up);
+    if (!(hi < 1e37f)) return 2;
     const int ih = fast_chunk_index(fast_bits(hi), ed.c1dn, ed.c2dn);
-    if (il != ih) return 2;
     chunk = ih > mc ? mc + 1 : ih;
+    inf = cinfo[chunk];
+#ifdef __CUDA_ARCH__
+    const float elo = __int_as_float(inf.w);
+#else
+    float elo; { union { int i; float f; } v; v.i = inf.w; elo = v.f; }
+#endif
+    if (!(lo > elo)) return 2;                           // (also lo <= 0 and NaN)
     return 1;
 }
 
@@ -418,7 +432,8 @@ __global__ void __launch_bounds__(kFThreads, 1) k_score_fast(const __grid_consta
         const Chunks& C = A.tab->chunks;
         for (int i = tid; i < kChunkTab; i += kFThreads) {
             const bool in = i <= C.maxchunk;
-            cinfo[i] = in ? make_int4(C.hoff[i], C.hw[i], C.kcand[i], 0) : make_int4(0, 1, 0x7fffffff, 0);
+            const int eb = i <= C.maxchunk + 1 ? __float_as_int(A.elo[i]) : 0x7f800000;     // lower edge of chunk i, rounded up
+            cinfo[i] = in ? make_int4(C.hoff[i], C.hw[i], C.kcand[i], eb) : make_int4(0, 1, 0x7fffffff, eb);
         }
         for (int i = tid; i < 2 * kShI * kShK; i += kFThreads) shist[i] = 0u;
         if constexpr (GEN) {
@@ -449,6 +464,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_score_fast(const __grid_consta
         int strip, r0;
         tile_of(j, strip, r0);
         const int d0 = A.dlo + strip * kFTD;
+        const bool edge_tile = r0 < A.F || r0 + d0 + kFTR + kFTD - 2 >= n - A.F;      // some pixel of the tile is next to a chromosome end
         unsigned char* const sb = smem + (size_t)st * LY::stage;
         const float* const xs = reinterpret_cast<const float*>(sb + LY::sXS);
         const int* const obs = reinterpret_cast<const int*>(sb + LY::sOBS);
@@ -512,7 +528,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_score_fast(const __grid_consta
                 const int r = r0 + rrl, d = d0 + dl;
                 const int ob = obs[(dl * 4 + (rrl & 3)) * (kFTR / 4) + (rrl >> 2)];
                 float fk = ftab[sc * kFTD + dl], fy = ftab[(ncode + sc) * kFTD + dl];
-                const bool top = r < A.F, end = r + d >= n - A.F;
+                const bool top = edge_tile && r < A.F, end = edge_tile && r + d >= n - A.F;
                 if (act && (top || end)) {              // next to a chromosome end: the factor tables of that row / column
                     const int z = top ? 1 + r : 1 + A.F + (n - 1 - r - d);
                     const size_t at = ((size_t)(z * 2) * nexec + s) * num + d;
@@ -522,8 +538,9 @@ __global__ void __launch_bounds__(kFThreads, 1) k_score_fast(const __grid_consta
                 const float bb = b1t[rrl] * b2t[rrl + dl];
                 int ck, cy;
                 float lo0, hi0, lo1, hi1;
-                const int c0 = fast_classify(__uint_as_float(rec.x), __uint_as_float(rec.z << 16), fk, bb, ed, mc, ck, lo0, hi0);
-                const int c1 = fast_classify(__uint_as_float(rec.y), __uint_as_float(rec.z & 0xFFFF0000u), fy, bb, ed, mc, cy, lo1, hi1);
+                int4 infk, infy;
+                const int c0 = fast_classify(__uint_as_float(rec.x), __uint_as_float(rec.z << 16), fk, bb, ed, mc, cinfo, ck, lo0, hi0, infk);
+                const int c1 = fast_classify(__uint_as_float(rec.y), __uint_as_float(rec.z & 0xFFFF0000u), fy, bb, ed, mc, cinfo, cy, lo1, hi1, infy);
                 const bool ex = act && (c0 == 2 || c1 == 2 || !(bb == bb));
                 const bool ok = act && !ex;
                 unsigned flags = 0, emk = 0;
@@ -534,7 +551,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_score_fast(const __grid_consta
                     if (ck > mc) {
                         gmem_red_add(&A.cnt[2], 1u);
                     } else {
-                        const int4 inf = cinfo[ck];
+                        const int4 inf = infk;
                         const int kb = ob < inf.y - 1 ? ob : inf.y - 1;
                         if (ck <= kShI && kb < kShK) smem_red_add(&shist[(ck - 1) * kShK + kb], 1u);
                         else gmem_red_add(&A.hist[(size_t)inf.x + kb], 1u);
@@ -551,7 +568,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_score_fast(const __grid_consta
                     if (cy > mc) {
                         gmem_red_add(&A.cnt[2], 1u);
                     } else {
-                        const int4 inf = cinfo[cy];
+                        const int4 inf = infy;
                         const int kb = ob < inf.y - 1 ? ob : inf.y - 1;
                         if (cy <= kShI && kb < kShK) smem_red_add(&shist[(kShI + cy - 1) * kShK + kb], 1u);
                         else gmem_red_add(&A.hist[(size_t)A.total_bins + inf.x + kb], 1u);

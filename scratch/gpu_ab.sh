@@ -1,0 +1,6 @@
+cd $GRAFT_REPO_ROOT
+for rep in 1 2; do
+for v in A B; do
+echo "variant $v"; HICPEAKS_B200_LIB=$GRAFT_REPO_ROOT/scratch/ab/lib_$v.so timeout 120 python scratch/prof_fast.py 20000 4 2>&1 | tail -2
+done
+done

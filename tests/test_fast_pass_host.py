@@ -113,6 +113,12 @@ static int check_classify() {
         return v.u & 0x7fffffu;
     };
     const FastEdges ed{mant(rv[2], false), mant(rv[3], false), mant(rv[2], true), mant(rv[3], true)};
+    std::vector<int4> cinfo(mc + 4);                   // .w = lower edge of the chunk rounded up, as hp_hiccups_score builds it
+    for (int i = 0; i < mc + 4; ++i) {
+        float e = i <= 1 ? 0.f : (i <= mc + 1 ? nextafterf((float)(rv[i - 1] * (1.0 + 1e-9)), INFINITY) : INFINITY);
+        union { float f; int i; } v; v.f = e;
+        cinfo[i] = make_int4(0, 1, 0, v.i);
+    }
     std::mt19937_64 rng(7);
     std::uniform_real_distribution<double> U(0.0, 1.0);
     int bad = 0, certain = 0, total = 0;
@@ -125,7 +131,8 @@ static int check_classify() {
         const float S = (float)(E / ((double)f * bb));
         const float es = S * 1e-5f * (float)U(rng) + 1e-30f;
         int chunk; float l, h;
-        const int code = fast_classify(S, es, f, bb, ed, mc, chunk, l, h);
+        int4 inf;
+        const int code = fast_classify(S, es, f, bb, ed, mc, cinfo.data(), chunk, l, h, inf);
         ++total;
         if (code != 1) continue;
         ++certain;
