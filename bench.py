@@ -289,7 +289,12 @@ def bench_cfg3(local, rank, world, dist, steps):
                       "ms_score_sum_rank0": float(sum(S.ms_score for S in Ss)), "ms_levels_sum_rank0": float(sum(S.ms_levels for S in Ss))}
         if scope == "genome":
             out[scope]["allreduce_ms_device"] = float(np.mean([m for m in merges if m is not None]))
-    ms_score = out["chrom"]["ms_score_sum_rank0"]
+    # roofline leg: this rank's chromosomes once more, one at a time on an otherwise idle GPU, so that the CUDA-event time
+    # of the score kernels (three launches per chromosome) is not stretched by kernels of other streams
+    ms_score = 0.0
+    for c in ctxs:
+        ms_score += float(c.hiccups(P).ms_score)
+    out["ms_score_alone_sum_rank0"] = ms_score
     peak, _ = read_peaks()
     fastk = bool(Ss and Ss[0].fast_kernel)
     out["roofline"] = {"kernel": ("k_score_fast, general form: one launch per pair, three pairs per pixel" if fastk else
