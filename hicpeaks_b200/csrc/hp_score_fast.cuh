@@ -61,6 +61,7 @@ __host__ __device__ constexpr float fast_cerr_y(int w) { return (4.f * w + 16.f)
 // bounded by sum_g |c(g)| Fmax_g:  |K' - K| <= sum_g |c(g)| fast_cerr_gen_k(g) Fmax_g, likewise for Y.
 __host__ __device__ constexpr float fast_cerr_gen_k(int w) { return (10.f * w + 40.f) * 1.05f * kFU; }
 __host__ __device__ constexpr float fast_cerr_gen_y(int w) { return (4.f * w + 40.f) * 1.05f * kFU; }
+constexpr int kFMaxPeak = 4;        // largest pw the single-pair kernel has window code for
 constexpr int kFMaxCode = 16;       // widths a pair can resolve at (codes 0 .. maxww - ww), 0xF = none
 constexpr int kFMaxG = 16;          // ring index bound of the coefficient tables (> FM)
 
@@ -225,8 +226,8 @@ struct FastPass {
             constexpr int g = decltype(GG)::value;
             if (g <= ft) {
                 vert<g>(xrow, dn, W);
-                if (g == P) {
-                    horiz<g>(dn, W, Qp, Lp, fqp, flp);
+                if (g <= kFMaxPeak && g == P) {         // (peak widths beyond kFMaxPeak take the general-form kernel)
+                    if constexpr (g <= kFMaxPeak) horiz<g>(dn, W, Qp, Lp, fqp, flp);
                 } else if (g >= W0 && ((lvmask >> (g - W0)) & 1u)) {
                     float Q[kFNPX], L[kFNPX], fq, fl;
                     horiz<g>(dn, W, Q, L, fq, fl);

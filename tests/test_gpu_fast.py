@@ -70,6 +70,7 @@ CASES = [
     (90, 70, 2, 5, 10, 300.0, 1.08, 16, 2),            # chromosome shorter than band + windows: pixels next to both ends
     (640, 90, 3, 6, 10, 40.0, 1.05, 20, 12),           # a pair with no compiled exact-order kernel: table-driven k_score vs fast
     (520, 70, 0, 2, 9, 30.0, 1.1, 16, 13),             # p = 0
+    (600, 80, 5, 7, 10, 50.0, 1.08, 16, 14),           # p > 4: one pair through the general-form kernel
 ]
 
 
