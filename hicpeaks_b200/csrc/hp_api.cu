@@ -1192,7 +1192,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
                         FA.cabs[g] = std::max(FA.cabs[g], (float)abs(c));
                     }
                 }
-                rc = (P.npw == 1 && P.pw[0] <= kFMaxPeak ? fast->launch : fast->launch_gen)(ctx, tm_rawf, FA, std::min(items, ctx->sm_count), st);
+                rc = (P.npw == 1 && P.pw[0] <= kFMaxPeak && P.ww[0] >= kFMinWidth ? fast->launch : fast->launch_gen)(ctx, tm_rawf, FA, std::min(items, ctx->sm_count), st);
                 if (rc) return rc;
                 ++launches;
                 CK(cudaGetLastError());

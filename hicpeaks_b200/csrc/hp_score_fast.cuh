@@ -62,6 +62,7 @@ __host__ __device__ constexpr float fast_cerr_y(int w) { return (4.f * w + 16.f)
 __host__ __device__ constexpr float fast_cerr_gen_k(int w) { return (10.f * w + 40.f) * 1.05f * kFU; }
 __host__ __device__ constexpr float fast_cerr_gen_y(int w) { return (4.f * w + 40.f) * 1.05f * kFU; }
 constexpr int kFMaxPeak = 4;        // largest pw the single-pair kernel has window code for
+constexpr int kFMinWidth = 3;       // smallest ww ...                                           (others: the general-form kernel)
 constexpr int kFMaxCode = 16;       // widths a pair can resolve at (codes 0 .. maxww - ww), 0xF = none
 constexpr int kFMaxG = 16;          // ring index bound of the coefficient tables (> FM)
 
@@ -228,9 +229,9 @@ struct FastPass {
                 vert<g>(xrow, dn, W);
                 if (g <= kFMaxPeak && g == P) {         // (peak widths beyond kFMaxPeak take the general-form kernel)
                     if constexpr (g <= kFMaxPeak) horiz<g>(dn, W, Qp, Lp, fqp, flp);
-                } else if (g >= W0 && ((lvmask >> (g - W0)) & 1u)) {
+                } else if (g >= kFMinWidth && g >= W0 && ((lvmask >> (g - W0)) & 1u)) {
                     float Q[kFNPX], L[kFNPX], fq, fl;
-                    horiz<g>(dn, W, Q, L, fq, fl);
+                    if constexpr (g >= kFMinWidth) horiz<g>(dn, W, Q, L, fq, fl);
                     // the bounds of this width, kept as two bf16 rounded up (one word of the record)
                     const unsigned epk = fast_pack_err(fast_cerr_k(g) * (fq + fqp), fast_cerr_y(g) * (fl + flp));
                     const unsigned sc = (unsigned)(g - W0);
