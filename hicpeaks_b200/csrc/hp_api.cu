@@ -843,16 +843,18 @@ static const SpecKernel* find_spec(hp_ctx* ctx, int nexec) {
 }
 
 // ---- re-associated score kernels (hp_score_fast.cuh): any single (p, w) program, widths up to FM ----------------
+typedef int (*FastLaunch)(hp_ctx*, const CUtensorMap&, const FastArgs&, int, cudaStream_t);
 struct FastKernel {
     int fm;
-    int (*launch)(hp_ctx*, const CUtensorMap&, const FastArgs&, int, cudaStream_t);        // one (pw, ww) pair
-    int (*launch_gen)(hp_ctx*, const CUtensorMap&, const FastArgs&, int, cudaStream_t);    // one pair of a union program
+    FastLaunch launch;              // one (pw, ww) pair, run-time values (pw <= kFMaxPeak, ww >= kFMinWidth)
+    FastLaunch launch_gen;          // the general form: one pair of a union program, or any other single pair
+    FastLaunch launch_p1w3, launch_p2w5, launch_p4w7;      // the usual pairs, known at compile time
 };
-template <int FM, bool GEN>
+template <int FM, bool GEN, int CP = -1, int CW = -1>
 static int launch_fast(hp_ctx* ctx, const CUtensorMap& tm_raw, const FastArgs& A, int grid, cudaStream_t st) {
     static std::atomic<size_t> granted[64];
     const size_t smem = FastLayout<FM, FM>::bytes;
-    CK(want_smem(k_score_fast<FM, GEN>, ctx->device, smem, granted));
+    CK(want_smem(k_score_fast<FM, GEN, CP, CW>, ctx->device, smem, granted));
     // the fp32 tile: box of fast_px(FM) diagonals x 96 rows of xf[r][d - dlo]; the levels: the same 3-D box of the
     // quad-interleaved u8 plane as the raw counts
     CUtensorMap tm_x, tm_lvl;
@@ -861,10 +863,22 @@ static int launch_fast(hp_ctx* ctx, const CUtensorMap& tm_raw, const FastArgs& A
     if (rc) return rc;
     rc = make_map_plane(ctx, &tm_lvl, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ctx->d_lvl, kFTR / 4, kFTD);
     if (rc) return rc;
-    k_score_fast<FM, GEN><<<grid, kFThreads, smem, st>>>(tm_raw, tm_x, tm_lvl, A);
+    k_score_fast<FM, GEN, CP, CW><<<grid, kFThreads, smem, st>>>(tm_raw, tm_x, tm_lvl, A);
     return HP_OK;
 }
-static const FastKernel g_fast[] = {{8, launch_fast<8, false>, launch_fast<8, true>}, {10, launch_fast<10, false>, launch_fast<10, true>}};
+#ifdef HP_FAST_BUILD
+#define HP_FASTK(FM) {FM, launch_fast<FM, false>, launch_fast<FM, true>, nullptr, launch_fast<FM, false, 2, 5>, nullptr}
+#else
+#define HP_FASTK(FM) {FM, launch_fast<FM, false>, launch_fast<FM, true>, launch_fast<FM, false, 1, 3>, launch_fast<FM, false, 2, 5>, launch_fast<FM, false, 4, 7>}
+#endif
+static const FastKernel g_fast[] = {HP_FASTK(8), HP_FASTK(10)};
+static FastLaunch pick_fast(const FastKernel* k, int npw, int p, int w) {
+    if (npw != 1) return k->launch_gen;
+    if (p == 1 && w == 3 && k->launch_p1w3) return k->launch_p1w3;
+    if (p == 2 && w == 5 && k->launch_p2w5) return k->launch_p2w5;
+    if (p == 4 && w == 7 && k->launch_p4w7) return k->launch_p4w7;
+    return (p <= kFMaxPeak && w >= kFMinWidth) ? k->launch : k->launch_gen;
+}
 static const FastKernel* find_fast(int frozen) {
     for (const FastKernel& k : g_fast)
         if (frozen <= k.fm) return &k;
@@ -1192,7 +1206,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
                         FA.cabs[g] = std::max(FA.cabs[g], (float)abs(c));
                     }
                 }
-                rc = (P.npw == 1 && P.pw[0] <= kFMaxPeak && P.ww[0] >= kFMinWidth ? fast->launch : fast->launch_gen)(ctx, tm_rawf, FA, std::min(items, ctx->sm_count), st);
+                rc = pick_fast(fast, P.npw, P.pw[pi], P.ww[pi])(ctx, tm_rawf, FA, std::min(items, ctx->sm_count), st);
                 if (rc) return rc;
                 ++launches;
                 CK(cudaGetLastError());

@@ -216,8 +216,10 @@ struct FastPass {
     // lvpk: 8 nibbles, the level code (step index) of each pixel, 0xF = not a resolved pixel; lvmask: steps present in the
     // warp; ft: largest half-width any pixel of the warp needs.  For every resolved pixel i the sink receives, at the
     // pixel's own width w = W0 + code:  sink(i, code, K = Q_w - Q_p, Y = LL_w - LL_p, bounds on |K' - K| and |Y' - Y| as two bf16).
-    // P, W0: the (p, w) pair of the run (run-time values: one kernel covers every single-pair program up to maxww = FM)
-    template <class Sink>
+    // P, W0: the (p, w) pair of the run (run-time values: one kernel covers every single-pair program up to maxww = FM);
+    // CP, CW >= 0: the pair is known at compile time (the usual pairs get their own kernels: only the window code they can
+    // reach is generated -- the unrolled sums are ~60 KB of code and instruction-cache misses are a measurable stall)
+    template <int CP, int CW, class Sink>
     static __host__ __device__ __forceinline__ void run(const float* __restrict__ xrow, int P, int W0, unsigned lvpk, unsigned lvmask,
                                                         int ft, Sink&& sink) {
         float dn[SPAN_DN], W[SPAN];
@@ -227,11 +229,9 @@ struct FastPass {
             constexpr int g = decltype(GG)::value;
             if (g <= ft) {
                 vert<g>(xrow, dn, W);
-                if (g <= kFMaxPeak && g == P) {         // (peak widths beyond kFMaxPeak take the general-form kernel)
-                    if constexpr (g <= kFMaxPeak) horiz<g>(dn, W, Qp, Lp, fqp, flp);
-                } else if (g >= kFMinWidth && g >= W0 && ((lvmask >> (g - W0)) & 1u)) {
+                auto level = [&]() {
                     float Q[kFNPX], L[kFNPX], fq, fl;
-                    if constexpr (g >= kFMinWidth) horiz<g>(dn, W, Q, L, fq, fl);
+                    horiz<g>(dn, W, Q, L, fq, fl);
                     // the bounds of this width, kept as two bf16 rounded up (one word of the record)
                     const unsigned epk = fast_pack_err(fast_cerr_k(g) * (fq + fqp), fast_cerr_y(g) * (fl + flp));
                     const unsigned sc = (unsigned)(g - W0);
@@ -239,6 +239,16 @@ struct FastPass {
                         constexpr int i = decltype(I)::value;
                         if (((lvpk >> (4 * i)) & 0xFu) == sc) sink(I, sc, Q[i] - Qp[i], L[i] - Lp[i], epk);
                     });
+                };
+                if constexpr (CP >= 0) {
+                    if constexpr (g == CP) horiz<g>(dn, W, Qp, Lp, fqp, flp);
+                    else if constexpr (g >= CW) { if ((lvmask >> (g - CW)) & 1u) level(); }
+                } else {
+                    if (g <= kFMaxPeak && g == P) {     // (peak widths beyond kFMaxPeak take the general-form kernel)
+                        if constexpr (g <= kFMaxPeak) horiz<g>(dn, W, Qp, Lp, fqp, flp);
+                    } else if (g >= kFMinWidth && g >= W0 && ((lvmask >> (g - W0)) & 1u)) {
+                        if constexpr (g >= kFMinWidth) level();
+                    }
                 }
             }
         });
@@ -379,13 +389,13 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int FM, bool GEN>
+template <int FM, bool GEN, int CP = -1, int CW = -1>
 __global__ void __launch_bounds__(kFThreads, 1) k_score_fast(const __grid_constant__ CUtensorMap tm_raw, const __grid_constant__ CUtensorMap tm_x,
                                                              const __grid_constant__ CUtensorMap tm_lvl, const __grid_constant__ FastArgs A) {
     using FP = FastPass<FM>;
     constexpr int PX = FP::PX;
     constexpr int NEX = FM;                            // widths a pair resolves at: at most FM - w + 1
-    const int P = A.p, W0 = A.w0, ncode = A.ncode;
+    const int P = CP >= 0 ? CP : A.p, W0 = CW >= 0 ? CW : A.w0, ncode = A.ncode;
     using LY = FastLayout<FM, NEX>;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned int* const shist = reinterpret_cast<unsigned int*>(smem + LY::oHIST);
@@ -516,7 +526,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_score_fast(const __grid_consta
                 for (unsigned mm = lvmask; mm; mm &= mm - 1u) hm |= A.hmask[__ffs((int)mm) - 1];
                 FastPassGen<FM>::run(xrow, W0, lvpk, lvmask, ft, hm, s_ctab, s_cabs, push);
             } else {
-                FP::run(xrow, P, W0, lvpk, lvmask, ft, push);
+                FP::template run<CP, CW>(xrow, P, W0, lvpk, lvmask, ft, push);
             }
             __syncwarp();
             // ---- close the records: classify both backgrounds, account the certain ones ---------------------------

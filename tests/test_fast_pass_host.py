@@ -21,6 +21,7 @@ SRC = r'''
 #include <cmath>
 #include <vector>
 #include <random>
+#include <algorithm>
 #include "hp_score_fast.cuh"
 using namespace hp;
 
@@ -28,7 +29,7 @@ static std::vector<double> X;          // X[(r + PAD) * NC + (c + PAD)] dense sy
 static int NR, NC, PAD = 32;
 static double at(int r, int c) { return X[(size_t)(r + PAD) * NC + (c + PAD)]; }
 
-template <int P, int W0, int FM>
+template <int P, int W0, int FM, bool CT = false>      // CT: the kernel form with (p, w) known at compile time
 static int run_case(unsigned seed, double sparsity, double spike, double* worst) {
     using FP = FastPass<FM>;
     constexpr int PX = FP::PX;
@@ -68,7 +69,7 @@ static int run_case(unsigned seed, double sparsity, double spike, double* worst)
             int ft = W0; for (int s = 0; s <= FM - W0; ++s) if ((mask >> s) & 1u) ft = W0 + s;
             float K[kFNPX] = {0}, Y[kFNPX] = {0}, EK[kFNPX] = {0}, EY[kFNPX] = {0};
             int got[kFNPX] = {0};
-            FP::run(xs.data() + (size_t)(rl + kFRowHalo) * PX + kFNPX * cb, P, W0, lvpk, mask, ft,
+            FP::template run<CT ? P : -1, CT ? W0 : -1>(xs.data() + (size_t)(rl + kFRowHalo) * PX + kFNPX * cb, P, W0, lvpk, mask, ft,
                     [&](auto I, unsigned sc, float kv, float yv, unsigned pk) {
                         constexpr int i = decltype(I)::value;
                         if ((int)sc != codes[i]) ++bad;
@@ -87,6 +88,119 @@ static int run_case(unsigned seed, double sparsity, double spike, double* worst)
                         if (a == 0 || b == 0 || (abs(a) <= P && abs(b) <= P)) continue;
                         const int dd = (c + b) - (r + a);
                         const double v = dd >= 0 ? at(r + a, c + b) : 0.0;
+                        ek += v;
+                        if (a > 0 && b < 0) ey += v;
+                    }
+                const double bk = EK[i], by = EY[i];
+                const double rk = bk > 0 ? fabs((double)K[i] - ek) / bk : (K[i] == 0.f && ek == 0.0 ? 0.0 : 1e9);
+                const double ry = by > 0 ? fabs((double)Y[i] - ey) / by : (Y[i] == 0.f && ey == 0.0 ? 0.0 : 1e9);
+                if (rk > worst[0]) worst[0] = rk;
+                if (ry > worst[1]) worst[1] = ry;
+                if (rk > 1.0 || ry > 1.0) ++bad;
+            }
+        }
+    return bad;
+}
+
+// ---- the general form (union programs, and single pairs outside the single-pair kernel's compiled range) ----------------
+// ring multiplicities of the reference's one set of accumulators after every step (callers.py:15-23 step order, :150-152 skip
+// rule), as hp_hiccups_score derives them from the cell list
+struct UStep { int w, p, pi; };
+static void union_program(const std::vector<int>& pw, const std::vector<int>& ww, int maxww, std::vector<UStep>& steps,
+                          std::vector<std::vector<int>>& mult) {
+    steps.clear(); mult.clear();
+    for (size_t i = 0; i < pw.size(); ++i)
+        for (int w = ww[i]; w <= maxww; ++w) steps.push_back({w, pw[i], (int)i});
+    std::stable_sort(steps.begin(), steps.end(), [](const UStep& a, const UStep& b) { return a.w != b.w ? a.w < b.w : a.p < b.p; });
+    std::vector<int> m(maxww + 2, 0);
+    bool limit = false; int lp = 0, lw = 0;
+    for (const UStep& st : steps) {
+        for (int g = 1; g <= st.w; ++g) {
+            if (limit && ((g <= lw && g > std::max(st.p, lp)) || g <= std::min(st.p, lp))) continue;
+            if (g <= st.p) continue;
+            ++m[g];
+        }
+        limit = true; lp = st.p; lw = st.w;
+        mult.push_back(m);
+    }
+}
+
+template <int FM>
+static int run_case_gen(unsigned seed, const std::vector<int>& pw, const std::vector<int>& ww, int pair, double sparsity, double spike,
+                        double* worst) {
+    using FP = FastPass<FM>;
+    constexpr int PX = FP::PX;
+    const int r0 = 64, d0 = 40, W0 = ww[pair];
+    NR = 64 + 2 * PAD + 64; NC = NR + 200;
+    X.assign((size_t)(NR + 2 * PAD) * (NC + 2 * PAD), 0.0);
+    std::mt19937_64 rng(seed);
+    std::uniform_real_distribution<double> U(0.0, 1.0);
+    for (int r = 0; r < NR; ++r)
+        for (int c = r + 1; c < NC; ++c) {
+            const int d = c - r;
+            if (d < 3) continue;
+            double v = 0.0;
+            if (U(rng) > sparsity) v = (1 + (int)(U(rng) * 60.0 / (1 + 0.1 * d))) * 0.0025 * std::exp(0.4 * (U(rng) - 0.5));
+            if (U(rng) < spike) v *= 1e4;
+            X[(size_t)(r + PAD) * NC + (c + PAD)] = v;
+        }
+    std::vector<float> xs((size_t)kFXR * PX, 0.f);
+    for (int x = 0; x < kFXR; ++x)
+        for (int col = 0; col < kFTD + 4 * FM; ++col) {
+            const int rr = r0 - kFRowHalo + x, dd = d0 - 2 * FM + col;
+            xs[(size_t)x * PX + col] = (float)((dd >= 0) ? at(rr, rr + dd) : 0.0);
+        }
+    std::vector<UStep> steps; std::vector<std::vector<int>> mult;
+    union_program(pw, ww, FM, steps, mult);
+    // coefficient tables of this pair, as hp_hiccups_score fills FastArgs
+    std::vector<float> ctab(kFMaxCode * kFMaxG, 0.f), cabs(kFMaxG, 0.f);
+    unsigned short hmask[kFMaxCode] = {0};
+    int tstep[kFMaxCode]; int ncode = 0;
+    for (size_t t = 0; t < steps.size(); ++t) {
+        if (steps[t].pi != pair) continue;
+        const int code = steps[t].w - W0;
+        tstep[code] = (int)t; ncode = std::max(ncode, code + 1);
+        for (int g = 1; g <= FM; ++g) {
+            const int c = mult[t][g] - (g + 1 <= FM ? mult[t][g + 1] : 0);
+            ctab[code * kFMaxG + g] = (float)c;
+            if (c) hmask[code] |= (unsigned short)(1u << g);
+            cabs[g] = std::max(cabs[g], (float)abs(c));
+        }
+    }
+    int bad = 0;
+    for (int rl = 0; rl < kFTR; ++rl)
+        for (int cb = 0; cb < kFTD / kFNPX; ++cb) {
+            unsigned lvpk = 0, mask = 0, hm = 0;
+            int codes[kFNPX];
+            for (int i = 0; i < kFNPX; ++i) {
+                const int code = (U(rng) < 0.2) ? 0xF : (int)(U(rng) * ncode);
+                codes[i] = code;
+                lvpk |= (unsigned)code << (4 * i);
+                if (code != 0xF) { mask |= 1u << code; hm |= hmask[code]; }
+            }
+            if (!mask) continue;
+            int ft = W0; for (int c = 0; c < ncode; ++c) if ((mask >> c) & 1u) ft = W0 + c;
+            float K[kFNPX] = {0}, Y[kFNPX] = {0}, EK[kFNPX] = {0}, EY[kFNPX] = {0};
+            int got[kFNPX] = {0};
+            FastPassGen<FM>::run(xs.data() + (size_t)(rl + kFRowHalo) * PX + kFNPX * cb, W0, lvpk, mask, ft, hm, ctab.data(), cabs.data(),
+                    [&](auto I, unsigned sc, float kv, float yv, unsigned pk) {
+                        constexpr int i = decltype(I)::value;
+                        if ((int)sc != codes[i]) ++bad;
+                        K[i] = kv; Y[i] = yv; ++got[i];
+                        union { unsigned u; float f; } a, b; a.u = pk << 16; b.u = pk & 0xFFFF0000u;
+                        EK[i] = a.f; EY[i] = b.f;
+                    });
+            for (int i = 0; i < kFNPX; ++i) {
+                if (got[i] != (codes[i] == 0xF ? 0 : 1)) ++bad;
+                if (codes[i] == 0xF) continue;
+                const int t = tstep[codes[i]], w = W0 + codes[i], r = r0 + rl, c = r + d0 + kFNPX * cb + i;
+                double ek = 0.0, ey = 0.0;                                 // the accumulators: every ring times its multiplicity
+                for (int a = -w; a <= w; ++a)
+                    for (int b = -w; b <= w; ++b) {
+                        if (a == 0 || b == 0) continue;
+                        const int g = std::max(abs(a), abs(b));
+                        const int dd = (c + b) - (r + a);
+                        const double v = (dd >= 0 ? at(r + a, c + b) : 0.0) * mult[t][g];
                         ek += v;
                         if (a > 0 && b < 0) ey += v;
                     }
@@ -168,8 +282,18 @@ int main() {
     bad += run_case<2, 5, 10>(3, 0.5, 0.001, worst);
     bad += run_case<1, 3, 10>(4, 0.2, 0.0, worst);
     bad += run_case<4, 7, 10>(5, 0.7, 0.005, worst);
+    bad += run_case<2, 5, 8, true>(1, 0.3, 0.0, worst);       // the compile-time forms of the usual pairs
+    bad += run_case<1, 3, 10, true>(4, 0.2, 0.0, worst);
+    bad += run_case<4, 7, 8, true>(8, 0.6, 0.003, worst);
     bad += run_case<3, 6, 10>(6, 0.4, 0.001, worst);          // a pair no exact-order kernel is compiled for
-    bad += run_case<0, 2, 8>(7, 0.3, 0.0, worst);             // p = 0: no peak square beyond the pixel itself
+    bad += run_case<0, 3, 8>(7, 0.3, 0.0, worst);             // p = 0: no peak square beyond the pixel itself
+    // the general form: every pair of the cfg3 union program (re-added rings: multiplicities up to 4), a two-pair program,
+    // and single pairs outside the single-pair kernel's compiled range (ww < 3, pw > 4)
+    for (int pair = 0; pair < 3; ++pair) bad += run_case_gen<10>(20 + pair, {1, 2, 4}, {3, 5, 7}, pair, 0.4, 0.002, worst);
+    for (int pair = 0; pair < 3; ++pair) bad += run_case_gen<8>(30 + pair, {4, 2, 1}, {7, 5, 3}, pair, 0.7, 0.0, worst);
+    for (int pair = 0; pair < 2; ++pair) bad += run_case_gen<10>(40 + pair, {1, 2}, {3, 5}, pair, 0.3, 0.001, worst);
+    bad += run_case_gen<8>(50, {0}, {2}, 0, 0.3, 0.0, worst);
+    bad += run_case_gen<10>(51, {5}, {7}, 0, 0.5, 0.001, worst);
     printf("sums bad %d worst_ratio_K %.4f worst_ratio_Y %.4f\n", bad, worst[0], worst[1]);
     bad += check_classify();
     printf("RESULT %s\n", bad ? "FAIL" : "OK");
