@@ -843,7 +843,8 @@ static const SpecKernel* find_spec(hp_ctx* ctx, int nexec) {
 }
 
 // ---- re-associated score kernels (hp_score_fast.cuh): any single (p, w) program, widths up to FM ----------------
-typedef int (*FastLaunch)(hp_ctx*, const CUtensorMap&, const FastArgs&, int, cudaStream_t);
+struct FastMaps { CUtensorMap raw, x, lvl; };        // count tile, fp32 balanced tile, level tile
+typedef int (*FastLaunch)(hp_ctx*, const FastMaps&, const FastArgs&, int, cudaStream_t);
 struct FastKernel {
     int fm;
     FastLaunch launch;              // one (pw, ww) pair, run-time values (pw <= kFMaxPeak, ww >= kFMinWidth)
@@ -851,20 +852,22 @@ struct FastKernel {
     FastLaunch launch_p1w3, launch_p2w5, launch_p4w7;      // the usual pairs, known at compile time
 };
 template <int FM, bool GEN, int CP = -1, int CW = -1>
-static int launch_fast(hp_ctx* ctx, const CUtensorMap& tm_raw, const FastArgs& A, int grid, cudaStream_t st) {
+static int launch_fast(hp_ctx* ctx, const FastMaps& M, const FastArgs& A, int grid, cudaStream_t st) {
     static std::atomic<size_t> granted[64];
     const size_t smem = FastLayout<FM, FM>::bytes;
     CK(want_smem(k_score_fast<FM, GEN, CP, CW>, ctx->device, smem, granted));
-    // the fp32 tile: box of fast_px(FM) diagonals x 96 rows of xf[r][d - dlo]; the levels: the same 3-D box of the
-    // quad-interleaved u8 plane as the raw counts
-    CUtensorMap tm_x, tm_lvl;
-    int rc = make_map_2d(ctx, &tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, ctx->d_xf, (uint64_t)(ctx->num - ctx->bal_first), (uint64_t)ctx->n,
-                         (uint64_t)ctx->xf_ndp * 4, fast_px(FM), kFXR);
-    if (rc) return rc;
-    rc = make_map_plane(ctx, &tm_lvl, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ctx->d_lvl, kFTR / 4, kFTD);
-    if (rc) return rc;
-    k_score_fast<FM, GEN, CP, CW><<<grid, kFThreads, smem, st>>>(tm_raw, tm_x, tm_lvl, A);
+    k_score_fast<FM, GEN, CP, CW><<<grid, kFThreads, smem, st>>>(M.raw, M.x, M.lvl, A);
     return HP_OK;
+}
+// the fp32 tile: box of fast_px(FM) diagonals x 96 rows of xf[r][d - dlo]; counts and levels: 3-D boxes (16 row quads, 4, 64
+// diagonals) of their quad-interleaved planes
+static int make_fast_maps(hp_ctx* ctx, int fm, FastMaps* M) {
+    int rc = make_map_plane(ctx, &M->raw, CU_TENSOR_MAP_DATA_TYPE_INT32, 4, ctx->d_raw, kFTR / 4, kFTD);
+    if (rc) return rc;
+    rc = make_map_2d(ctx, &M->x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, ctx->d_xf, (uint64_t)(ctx->num - ctx->bal_first), (uint64_t)ctx->n,
+                     (uint64_t)ctx->xf_ndp * 4, fast_px(fm), kFXR);
+    if (rc) return rc;
+    return make_map_plane(ctx, &M->lvl, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ctx->d_lvl, kFTR / 4, kFTD);
 }
 #ifdef HP_FAST_BUILD
 #define HP_FASTK(FM) {FM, launch_fast<FM, false>, launch_fast<FM, true>, nullptr, launch_fast<FM, false, 2, 5>, nullptr}
@@ -940,7 +943,6 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
 
     // ---- K1: levels --------------------------------------------------------------------------
     const int F1 = P.maxww;
-    CK(cudaEventRecord(ctx->ev[0], st));
     CK(cudaMemsetAsync(ctx->d_lhist, 0, (HP_MAX_STEPS + 2) * sizeof(unsigned long long), st));
     {
         const SpecKernel* lspec = spec_ok ? find_spec(ctx, G.nsteps) : nullptr;
@@ -954,6 +956,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
             if (rc) return rc;
             const size_t smem = (size_t)A.BD * 4 * A.NQ * 4 + 16 + (G.nsteps + 2) * 4;
             dim3 grid((n + kTR - 1) / kTR, (dhi - dlo + 3 + A.TD) / A.TD);
+            CK(cudaEventRecord(ctx->ev[0], st));      // (right before the launch: host work in between would count as kernel time)
             rc = lspec->launch_levels(ctx, tm_raw, A, grid, smem, st);
             if (rc) return rc;
         } else {
@@ -964,6 +967,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
             static std::atomic<size_t> granted[64];
             CK(want_smem(k_levels, ctx->device, smem, granted));
             dim3 grid((n + kTR - 1) / kTR, (dhi - dlo + A.TD) / A.TD);
+            CK(cudaEventRecord(ctx->ev[0], st));
             k_levels<<<grid, kThreads, smem, st>>>(tm_raw, A);
         }
         ++launches;
@@ -1099,13 +1103,14 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     for (int t = 0; t < nexec; ++t) ++pair_nc[G.step_pi[t]];
     FfsLayout ffsl{};
     size_t want_x = std::max<size_t>(65536, (size_t)total / 8);
-    CUtensorMap tm_bal, tm_rawf;
+    CUtensorMap tm_bal;
+    FastMaps fmaps;
     // the specialised kernel loads its tile as kTileParts boxes of consecutive planes
     rc = make_map_plane(ctx, &tm_bal, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, ctx->d_bal, A.NQ,
                         spec ? (A.BD + kTileParts - 1) / kTileParts : A.BD);
     if (rc) return rc;
     if (fast) {
-        rc = make_map_plane(ctx, &tm_rawf, CU_TENSOR_MAP_DATA_TYPE_INT32, 4, ctx->d_raw, kFTR / 4, kFTD);
+        rc = make_fast_maps(ctx, fast->fm, &fmaps);
         if (rc) return rc;
         CK(ensure(&ctx->d_ffac, &ctx->cap_ffac, (size_t)(1 + 2 * F) * 2 * nexec * num));
         if (!ctx->d_fscratch) CK(cudaMalloc(&ctx->d_fscratch, (size_t)ctx->sm_count * kFScratch * sizeof(int4)));
@@ -1143,7 +1148,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
         for (int i = 0; i < P.npw; ++i) A.ww[i] = P.ww[i];
         for (int k = 0; k < nexec; ++k) { A.step_pi[k] = (unsigned char)G.step_pi[k]; A.step_lo[k] = G.step_lo[k]; }
         memcpy(A.last_need, G.last_need, sizeof(A.last_need));
-        CK(cudaEventRecord(ctx->ev[2], st));      // ms_score = the score kernel alone (roofline leg of bench.py)
+        if (!use_fast) CK(cudaEventRecord(ctx->ev[2], st));      // ms_score = the score kernel alone (roofline leg of bench.py)
         if (use_fast) {
             FastArgs FA{};
             FA.ffac = ctx->d_ffac; FA.ffs = ctx->d_ffs; FA.b1f = ctx->d_b1f; FA.b2s = ctx->d_b2s;
@@ -1170,6 +1175,10 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
                     FA.elo[i] = nextafterf((float)(ctx->chunks.rv[i - 1] * (1.0 + 1e-9)), INFINITY);
             }
             const int items = FA.nstrips * FA.ntr;
+            // every launch's arguments first, then the event and the launches back to back: whatever the host does between
+            // the event and a launch would be counted as kernel time (with 8 ranks on one box the host is the slow side)
+            std::vector<FastArgs> fas;
+            std::vector<FastLaunch> fns;
             for (int pi = 0; pi < P.npw; ++pi) {
                 if (pair_nc[pi] == 0) continue;                // no executed step of this pair: nothing resolves for it
                 FA.pair = pi; FA.p = P.pw[pi]; FA.w0 = P.ww[pi]; FA.wpair = P.ww[pi]; FA.ncode = pair_nc[pi];
@@ -1206,11 +1215,16 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
                         FA.cabs[g] = std::max(FA.cabs[g], (float)abs(c));
                     }
                 }
-                rc = pick_fast(fast, P.npw, P.pw[pi], P.ww[pi])(ctx, tm_rawf, FA, std::min(items, ctx->sm_count), st);
+                fas.push_back(FA);
+                fns.push_back(pick_fast(fast, P.npw, P.pw[pi], P.ww[pi]));
+            }
+            CK(cudaEventRecord(ctx->ev[2], st));
+            for (size_t k = 0; k < fas.size(); ++k) {
+                rc = fns[k](ctx, fmaps, fas[k], std::min(items, ctx->sm_count), st);
                 if (rc) return rc;
                 ++launches;
-                CK(cudaGetLastError());
             }
+            CK(cudaGetLastError());
             CK(cudaEventRecord(ctx->ev[3], st));
             // the records the fast kernel could not settle + the E.max() contenders, in the reference's fp64 order
             static std::atomic<size_t> granted_x[64];
