@@ -322,25 +322,27 @@ __host__ __device__ __forceinline__ int fast_chunk_index(unsigned bits, unsigned
 // bound allows.  inf = cinfo[chunk] = {first histogram bin, bins, candidate threshold, lower edge}.
 __host__ __device__ __forceinline__ int fast_classify(float S, float es, float f, float bb, const FastEdges& ed, int mc,
                                                       const int4* __restrict__ cinfo, int& chunk, float& lo, float& hi, int4& inf) {
-    chunk = 0; lo = 0.f; hi = 0.f;
-    inf = make_int4(0, 1, 0x7fffffff, 0);
-    if (f == 0.f || bb == 0.f || es == 0.f) return 0;    // bE == 0 / IR == 0 / a zero bias, or every cell in reach is zero
+    // straight-line on purpose (no early returns): the donut and the lower-left classification of a record are independent
+    // chains and the compiler interleaves them only when neither sits behind a branch
+    const bool zero = f == 0.f || bb == 0.f || es == 0.f;   // bE == 0 / IR == 0 / a zero bias, or every cell in reach is zero
     const float fm = f * bb;
     const float ea = S * fm;
     const float err = es * fabsf(fm) + fabsf(ea) * kFCRel;
     lo = ea - err;
     hi = ea + err;
-    if (!(hi < 1e37f)) return 2;
-    const int ih = fast_chunk_index(fast_bits(hi), ed.c1dn, ed.c2dn);
-    chunk = ih > mc ? mc + 1 : ih;
-    inf = cinfo[chunk];
+    const int ih = fast_chunk_index(fast_bits(hi), ed.c1dn, ed.c2dn);      // (garbage in, some index out: clamped below)
+    const int ic = ih > mc ? mc + 1 : ih;
+    inf = cinfo[ic];
 #ifdef __CUDA_ARCH__
     const float elo = __int_as_float(inf.w);
 #else
     float elo; { union { int i; float f; } v; v.i = inf.w; elo = v.f; }
 #endif
-    if (!(lo > elo)) return 2;                           // (also lo <= 0 and NaN)
-    return 1;
+    const bool sure = hi < 1e37f && lo > elo;            // (false for lo <= 0 and for NaN)
+    const int code = zero ? 0 : (sure ? 1 : 2);
+    chunk = code == 1 ? ic : 0;
+    if (zero) { lo = 0.f; hi = 0.f; }
+    return code;
 }
 
 // shared-memory layout of a k_score_fast CTA (offsets in bytes): kFStages tile stages, then the per-CTA state
