@@ -514,11 +514,11 @@ extern "C" int hp_band_upload(hp_ctx* ctx, const hp_band_desc* b) {
         for (int d = d_begin; d < d_end; ++d) {
             const size_t len = (size_t)(n - d);
             int* rr = hraw + (size_t)d * pitch;
-            memcpy(rr, b->raw_diags[d], len * sizeof(int));
+            stream_copy(rr, b->raw_diags[d], len * sizeof(int));
             memset(rr + len, 0, (pitch - len) * sizeof(int));
             double* br = hbal + (size_t)d * pitch;
             if (d >= bf) {
-                memcpy(br, b->bal_diags[d - bf], len * sizeof(double));
+                stream_copy(br, b->bal_diags[d - bf], len * sizeof(double));
                 memset(br + len, 0, (pitch - len) * sizeof(double));
             } else {
                 memset(br, 0, (size_t)pitch * sizeof(double));

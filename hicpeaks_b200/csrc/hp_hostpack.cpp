@@ -12,6 +12,7 @@
 // plain C++ otherwise.
 #include "hp_hostpack.h"
 
+#include <cstdint>
 #include <cstring>
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -43,6 +44,19 @@ bool narrow16_scalar(const int32_t* s, size_t n, uint16_t* d) {
 
 #if defined(__x86_64__)
 // ---- AVX2: 32 counts per iteration -----------------------------------------------------------
+// NT: the destination is 16-byte aligned -> non-temporal stores.  The staging buffer is written once and next read by the
+// copy engine, never by this core: a regular store would first read the line it is about to overwrite (read for
+// ownership), 1 B per pixel of host DRAM traffic on a path that is bound by exactly that (7 -> 6 B per pixel).
+template <bool NT>
+__attribute__((target("avx2"))) static inline void put256(void* p, __m256i v) {
+    if (NT) {
+        _mm_stream_si128((__m128i*)p, _mm256_castsi256_si128(v));
+        _mm_stream_si128((__m128i*)p + 1, _mm256_extracti128_si256(v, 1));
+    } else {
+        _mm256_storeu_si256((__m256i*)p, v);
+    }
+}
+template <bool NT>
 __attribute__((target("avx2"))) bool narrow8_avx2(const int32_t* s, size_t n, uint8_t* d) {
     __m256i acc = _mm256_setzero_si256();
     const __m256i fix = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);      // undo the per-lane interleave of the two packs
@@ -56,7 +70,7 @@ __attribute__((target("avx2"))) bool narrow8_avx2(const int32_t* s, size_t n, ui
         const __m256i ab = _mm256_packus_epi32(a, b);                    // values out of range saturate; acc notices
         const __m256i ce = _mm256_packus_epi32(c, e);
         const __m256i o = _mm256_permutevar8x32_epi32(_mm256_packus_epi16(ab, ce), fix);
-        _mm256_storeu_si256((__m256i*)(d + i), o);
+        put256<NT>(d + i, o);
     }
     alignas(32) uint32_t t[8];
     _mm256_store_si256((__m256i*)t, acc);
@@ -68,6 +82,7 @@ __attribute__((target("avx2"))) bool narrow8_avx2(const int32_t* s, size_t n, ui
     }
     return (r & ~0xFFu) == 0;
 }
+template <bool NT>
 __attribute__((target("avx2"))) bool narrow16_avx2(const int32_t* s, size_t n, uint16_t* d) {
     __m256i acc = _mm256_setzero_si256();
     size_t i = 0;
@@ -76,7 +91,7 @@ __attribute__((target("avx2"))) bool narrow16_avx2(const int32_t* s, size_t n, u
         const __m256i b = _mm256_loadu_si256((const __m256i*)(s + i + 8));
         acc = _mm256_or_si256(acc, _mm256_or_si256(a, b));
         const __m256i o = _mm256_permute4x64_epi64(_mm256_packus_epi32(a, b), 0xD8);
-        _mm256_storeu_si256((__m256i*)(d + i), o);
+        put256<NT>(d + i, o);
     }
     alignas(32) uint32_t t[8];
     _mm256_store_si256((__m256i*)t, acc);
@@ -98,6 +113,32 @@ constexpr size_t kBlock = 8192;      // range check granularity: a diagonal that
 
 }  // namespace
 
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static void stream_copy_avx2(unsigned char* d, const unsigned char* s, size_t n) {
+    const size_t head = (32 - ((uintptr_t)d & 31)) & 31;               // up to the first 32-byte boundary of the destination
+    if (head >= n) { memcpy(d, s, n); return; }
+    memcpy(d, s, head);
+    d += head; s += head; n -= head;
+    size_t i = 0;
+    for (; i + 128 <= n; i += 128) {
+        const __m256i a = _mm256_loadu_si256((const __m256i*)(s + i)), b = _mm256_loadu_si256((const __m256i*)(s + i + 32));
+        const __m256i c = _mm256_loadu_si256((const __m256i*)(s + i + 64)), e = _mm256_loadu_si256((const __m256i*)(s + i + 96));
+        _mm256_stream_si256((__m256i*)(d + i), a);
+        _mm256_stream_si256((__m256i*)(d + i + 32), b);
+        _mm256_stream_si256((__m256i*)(d + i + 64), c);
+        _mm256_stream_si256((__m256i*)(d + i + 96), e);
+    }
+    memcpy(d + i, s + i, n - i);
+    _mm_sfence();
+}
+#endif
+void stream_copy(void* dst, const void* src, size_t bytes) {
+#if defined(__x86_64__)
+    if (have_avx2() && bytes >= 4096) { stream_copy_avx2((unsigned char*)dst, (const unsigned char*)src, bytes); return; }
+#endif
+    memcpy(dst, src, bytes);
+}
+
 int narrow_diagonal(const int32_t* src, size_t len, void* dst) {
 #if defined(__x86_64__)
     const bool simd = have_avx2();
@@ -105,10 +146,15 @@ int narrow_diagonal(const int32_t* src, size_t len, void* dst) {
     const bool simd = false;
 #endif
     bool ok = true;
+#if defined(__x86_64__)
+    const bool nt = simd && ((uintptr_t)dst & 15) == 0;      // (kBlock keeps every block's start 16-byte aligned)
+    struct Fence { bool on; ~Fence() { if (on) _mm_sfence(); } } fence{nt};      // the copy engine reads what was streamed
+#endif
     for (size_t i = 0; i < len && ok; i += kBlock) {
         const size_t m = len - i < kBlock ? len - i : kBlock;
 #if defined(__x86_64__)
-        ok = simd ? narrow8_avx2(src + i, m, (uint8_t*)dst + i) : narrow8_scalar(src + i, m, (uint8_t*)dst + i);
+        ok = !simd ? narrow8_scalar(src + i, m, (uint8_t*)dst + i)
+                   : nt ? narrow8_avx2<true>(src + i, m, (uint8_t*)dst + i) : narrow8_avx2<false>(src + i, m, (uint8_t*)dst + i);
 #else
         ok = narrow8_scalar(src + i, m, (uint8_t*)dst + i);
 #endif
@@ -118,13 +164,14 @@ int narrow_diagonal(const int32_t* src, size_t len, void* dst) {
     for (size_t i = 0; i < len && ok; i += kBlock) {
         const size_t m = len - i < kBlock ? len - i : kBlock;
 #if defined(__x86_64__)
-        ok = simd ? narrow16_avx2(src + i, m, (uint16_t*)dst + i) : narrow16_scalar(src + i, m, (uint16_t*)dst + i);
+        ok = !simd ? narrow16_scalar(src + i, m, (uint16_t*)dst + i)
+                   : nt ? narrow16_avx2<true>(src + i, m, (uint16_t*)dst + i) : narrow16_avx2<false>(src + i, m, (uint16_t*)dst + i);
 #else
         ok = narrow16_scalar(src + i, m, (uint16_t*)dst + i);
 #endif
     }
     if (ok) return 2;
-    memcpy(dst, src, len * sizeof(int32_t));
+    stream_copy(dst, src, len * sizeof(int32_t));
     return 4;
 }
 

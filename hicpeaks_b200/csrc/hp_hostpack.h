@@ -10,4 +10,8 @@ namespace hp {
 // chosen: 1, 2 or 4.
 int narrow_diagonal(const int32_t* src, size_t len, void* dst);
 
+// memcpy into a staging buffer that this core will not read again (the copy engine will): non-temporal stores, so the
+// destination lines are not read before they are overwritten.  Any alignment, any size.
+void stream_copy(void* dst, const void* src, size_t bytes);
+
 }  // namespace hp
