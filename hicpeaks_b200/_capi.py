@@ -179,16 +179,20 @@ def program_dump(pw, ww, maxww):
     return out
 
 
-def narrow_diagonal(counts) -> np.ndarray:
-    """Host-only: the narrowed form (uint8 / uint16 / int32 array) hp_band_upload_counts sends for one count diagonal."""
+def narrow_diagonal(counts, misalign: int = 0) -> np.ndarray:
+    """Host-only: the narrowed form (uint8 / uint16 / int32 array) hp_band_upload_counts sends for one count diagonal.
+    ``misalign``: byte offset of the destination from a 64-byte boundary (0: the streaming-store path of the library,
+    anything not a multiple of 16: its plain-store path)."""
     a = np.ascontiguousarray(counts, dtype=np.int32)
-    buf = np.empty(max(a.size, 1) * 4, dtype=np.uint8)
+    raw = np.empty(max(a.size, 1) * 4 + 128, dtype=np.uint8)
+    off = (-raw.ctypes.data) % 64 + int(misalign)
+    buf = raw[off: off + max(a.size, 1) * 4]
     es = C.c_int32()
-    rc = load_library().hp_narrow_diagonal(_ptr(a), a.size, _ptr(buf), C.byref(es))
+    rc = load_library().hp_narrow_diagonal(_ptr(a), a.size, buf.ctypes.data_as(C.c_void_p), C.byref(es))
     if rc != HP_OK:
         raise EngineError(rc, "hp_narrow_diagonal failed")
     dt = {1: np.uint8, 2: np.uint16, 4: np.int32}[es.value]
-    return buf[: a.size * es.value].view(dt).copy()
+    return buf[: a.size * es.value].copy().view(dt)
 
 
 def chunk_edges(max_chunks: int) -> np.ndarray:

@@ -86,7 +86,7 @@ def test_upload_narrowing_is_lossless_on_the_host():
             a[rng.integers(0, n)] = 65536 + int(rng.integers(0, 2 ** 30))
         if n and kind == 4:
             a[rng.integers(0, n)] = -1 - int(rng.integers(0, 1000))
-        out = _capi.narrow_diagonal(a)
+        out = _capi.narrow_diagonal(a, misalign=(0, 16, 4, 1)[trial % 4])      # streaming stores (aligned) and plain stores
         want = np.int32 if (n and (a.min() < 0 or a.max() > 65535)) else np.uint16 if (n and a.max() > 255) else np.uint8
         assert out.dtype == want, (trial, n, out.dtype, want)
         assert np.array_equal(out.astype(np.int64), a.astype(np.int64))
