@@ -1130,7 +1130,7 @@ extern "C" int hp_hiccups_score(hp_ctx* ctx, const hp_hiccups_params* prm, hp_hi
     for (int attempt = 0;; ++attempt) {
         CK(ensure(&ctx->d_cand, &ctx->cap_cand, use_fast ? std::max<size_t>(65536, want_x) : want));
         if (use_fast) {
-            CK(ensure(&ctx->d_fcand, &ctx->cap_fcand, want + (size_t)kFCandChunk * kFWarps * ctx->sm_count));   // + every warp's last piece
+            CK(ensure(&ctx->d_fcand, &ctx->cap_fcand, want + (size_t)kFCandChunk * kFWarps * ctx->sm_count * P.npw));   // + every warp's last piece, per launch
             CK(ensure(&ctx->d_xrec, &ctx->cap_xrec, want_x));
         }
         CK(cudaMemsetAsync(ctx->d_hist, 0, (size_t)P.npw * 2 * tb * sizeof(unsigned int), st));
