@@ -571,6 +571,9 @@ def main():
         "config": {"workload": "cfg2: synthetic 20000-bin chromosome @10kb, 5 Mb band (num=511), p=2 w=5, maxww 10",
                    "chromosomes_per_gpu_per_step": len(ctxs), "pixels_per_step": px_total,
                    "l2": "batch of %d chromosomes = %.0f MB resident input per GPU > 126 MB L2" % (len(ctxs), h2d / 1e6),
+                   "resident": "per chromosome: int32 count planes + fp64 balanced planes (what the algorithmic 12 B/pixel counts) and the fp32 "
+                               "row-major copy of the balanced band the upload leaves for the score kernel (k_f32plane, ~25 us per chromosome: "
+                               "inside e2e, not inside value)",
                    "timing": "CUDA events bracketing the K steps on the first context's stream (every C-ABI call ends with a "
                              "stream sync, so the closing event follows all streams), max over ranks; host clock kept as "
                              "ms_per_step_host; kernel times from CUDA events on the engine stream",
